@@ -1,0 +1,207 @@
+/*
+ * nanosnp_b200 -- C ABI of the B200-native NanoSNP pileup-model hot path (stages s1 + s2).
+ *
+ * NanoSNP itself has no FFI: its stages are coupled by CLIs and files.  Every
+ * entry point below therefore cites the reference *program or function* whose work it replaces.
+ * A maintainer binds this library from Python with ctypes (INTEGRATION.md shows the stub); there are
+ * no torch / C++ types in any signature: plain pointers, sizes, a cudaStream_t passed as void*.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative NSNP_E_* code on failure; nothing throws,
+ *     nothing aborts, nothing falls back to the CPU.  nsnp_last_error() gives a thread-local message.
+ *   - "dev" pointers are device memory owned by the caller (torch tensors in the Python host code);
+ *     the library never allocates device memory: workspaces are sized by nsnp_*_workspace_bytes().
+ *   - positions are 0-based on the contig inside this ABI; VCF / .tensor text is 1-based.
+ *   - kernels are enqueued on the caller's stream and do not synchronise unless stated.
+ */
+#ifndef NANOSNP_B200_H
+#define NANOSNP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSNP_ABI_VERSION 1
+
+/* error codes */
+#define NSNP_OK               0
+#define NSNP_E_INVALID       -1   /* bad argument (null pointer, negative size, unsorted reads ...) */
+#define NSNP_E_CUDA          -2   /* a CUDA runtime call failed; see nsnp_last_error() */
+#define NSNP_E_WORKSPACE     -3   /* caller workspace too small */
+#define NSNP_E_OVERFLOW      -4   /* a device-side capacity was exceeded (depth > 65535, indel slab full) */
+#define NSNP_E_NO_DEVICE     -5   /* no CUDA device: there is deliberately no CPU fallback */
+#define NSNP_E_UNSUPPORTED   -6
+
+/* channel order of the count tensor: reference dna_sv_tensor/src/common/tensor.hpp:6-26 */
+enum {
+    NSNP_CH_A = 0, NSNP_CH_C, NSNP_CH_G, NSNP_CH_T, NSNP_CH_I, NSNP_CH_I1, NSNP_CH_D, NSNP_CH_D1,
+    NSNP_CH_STAR, NSNP_CH_a, NSNP_CH_c, NSNP_CH_g, NSNP_CH_t, NSNP_CH_i, NSNP_CH_i1, NSNP_CH_d,
+    NSNP_CH_d1, NSNP_CH_POUND, NSNP_CHANNELS /* = 18 */
+};
+#define NSNP_FLANK       16      /* make_predict_data.sh:119 FLANKING_BASES */
+#define NSNP_WINDOW      33      /* make_candidate_snp_tensor/main.cpp:126 */
+#define NSNP_MAX_INDEL   60      /* tensor_maker.cpp:5 kMaxIndelSize */
+#define NSNP_GT_CLASSES  21      /* PileupModel/options.py:8-28 */
+#define NSNP_ZY_CLASSES  3       /* PileupModel/options.py:30 */
+
+/* bits of the per-position flag byte written by nsnp_pileup_counts */
+#define NSNP_F_COVERED   1       /* an mpileup row exists for this position */
+#define NSNP_F_GATE      2       /* refbase in ACGT && pass_af && depth >= min_coverage (main.cpp:196) */
+
+/*
+ * Aligned reads of ONE contig region as flat packed arrays (what a host BAM decoder produces;
+ * replaces the BAM -> `samtools mpileup` text hand-off of make_predict_data.sh:117,151).
+ * Reads must be sorted by pos (coordinate-sorted BAM order); ties keep file order.
+ */
+typedef struct nsnp_reads {
+    int64_t         n_reads;
+    const int32_t*  pos;        /* [n] 0-based leftmost reference position (BAM pos) */
+    const uint16_t* flag;       /* [n] SAM flag; reads with (flag & excl_flags) are dropped */
+    const uint8_t*  mapq;       /* [n] reads with mapq < min_mapq are dropped */
+    const int64_t*  cigar_off;  /* [n+1] index of the read's first op in cigar[] */
+    const uint32_t* cigar;      /* BAM encoding: len<<4 | op, op = MIDNSHP=X -> 0..8 */
+    const int64_t*  seq_off;    /* [n] index (in bases) of the read's first SEQ base in seq2/nmask */
+    const uint8_t*  seq2;       /* 2-bit bases A0 C1 G2 T3: base k lives in byte k>>2, bits 2*(k&3) */
+    const uint8_t*  nmask;      /* optional (may be NULL): bit (k&7) of byte k>>3 set => base k is N */
+    const uint8_t*  qual;       /* optional, unused: s1/s2 run with --min-BQ 0 and never read qualities */
+    int64_t         n_cigar;    /* total ops  (= cigar_off[n]) */
+    int64_t         n_bases;    /* capacity of seq2/nmask in bases */
+} nsnp_reads_t;
+
+/* s1 parameters; defaults = make_predict_data.sh:117-125 */
+typedef struct nsnp_params {
+    double   snp_min_af;     /* 0.12 */
+    double   indel_min_af;   /* 0.12 */
+    int32_t  min_coverage;   /* 6 */
+    int32_t  min_mapq;       /* 20   (--min-MQ) */
+    uint32_t excl_flags;     /* 2316 (--excl-flags) */
+    int32_t  reserved;
+} nsnp_params_t;
+
+void        nsnp_default_params(nsnp_params_t* p);
+int         nsnp_abi_version(void);
+const char* nsnp_last_error(void);
+int         nsnp_device_count(void);          /* 0 when no GPU is visible (library still loads) */
+
+/* ---- s1, step A: pileup counts ------------------------------------------------------------------
+ * Replaces `samtools mpileup` + TensorMaker::make_tensor (tensor_maker.cpp:61-249) for the region
+ * [region_start, region_start + region_len) of one contig.
+ *   ref_dev      [contig_len]      ASCII reference of the whole contig (raw case)
+ *   counts_dev   [region_len][18]  int32, final values incl. the reference-channel overwrite
+ *   flags_dev    [region_len]      NSNP_F_COVERED | NSNP_F_GATE
+ *   status_dev   [4] int32         device-side status words (0 = ok); read with nsnp_check_status
+ * reads may include reads that do not overlap the region (they are skipped).
+ */
+size_t nsnp_pileup_workspace_bytes(int64_t n_reads, int64_t n_cigar, int64_t region_len);
+int nsnp_pileup_counts(const nsnp_reads_t* reads_dev, const uint8_t* ref_dev, int64_t contig_len,
+                       int64_t region_start, int64_t region_len, const nsnp_params_t* params,
+                       int32_t* counts_dev, uint8_t* flags_dev,
+                       void* workspace_dev, size_t workspace_bytes, int32_t* status_dev, void* stream);
+
+/* ---- s1, step B: candidate selection ------------------------------------------------------------
+ * Replaces the gate + 33-row contiguity rule of create_pileup_tensor (main.cpp:174-217).
+ * Emits, in ascending order, every 0-based position c in [emit_start, emit_end) with the GATE bit set
+ * and COVERED set on all of [c-16, c+16].  flags_dev covers [region_start, region_start+region_len).
+ *   recompute_gate != 0: ignore the GATE bit and recompute it from counts_dev + ref_dev
+ *   pos_dev [capacity] int32 (contig coordinates); n_dev [1] int32 receives the total count
+ *   (which may exceed capacity: then only the first `capacity` are written and NSNP_E_OVERFLOW is
+ *    reported through status_dev).
+ */
+size_t nsnp_select_workspace_bytes(int64_t region_len);
+int nsnp_select_candidates(const int32_t* counts_dev, uint8_t* flags_dev, const uint8_t* ref_dev,
+                           int64_t contig_len, int64_t region_start, int64_t region_len,
+                           int64_t emit_start, int64_t emit_end, const nsnp_params_t* params,
+                           int recompute_gate, int32_t* pos_dev, int64_t capacity, int32_t* n_dev,
+                           void* workspace_dev, size_t workspace_bytes, int32_t* status_dev, void* stream);
+
+/* ---- s1, step C: window gather ------------------------------------------------------------------
+ * Replaces the ring-buffer window emit (main.cpp:220-251), DNA_CreatePredictData
+ * (make_predict_data/main.cpp:76-127) and make_bin_predict_data.py:35-55: writes position_matrix
+ * [n][33][18] directly in the PileupModel input layout.  Either output may be NULL.
+ *   x_i32_dev int32 [n][33][18]   (PredictDataset.position_matrix, dataset.py:121)
+ *   x_f32_dev float [n][33][18]   (predict.py:49 .type(FloatTensor))
+ *   refbase_dev u8 [n]            upper-cased centre reference base (dataset.py:133 ord(seq[16]))
+ */
+int nsnp_gather_windows(const int32_t* counts_dev, const uint8_t* ref_dev, int64_t region_start,
+                        int64_t region_len, const int32_t* pos_dev, const int32_t* n_dev, int64_t n_max,
+                        int32_t* x_i32_dev, float* x_f32_dev, uint8_t* refbase_dev, void* stream);
+
+/* ---- s2: PileupModel forward ----------------------------------------------------------------------
+ * Replaces LSTMNetwork.predict (PileupModel/model.py:114-119): 2-layer BiLSTM(18->64) + output_proj
+ * + dense/tanh @t=16 + genotype/zygosity heads + softmax.  Weights are the fp32 tensors of the
+ * reference checkpoint (utils.py:67-77), packed by nsnp_model_pack_weights into one device blob.
+ */
+typedef struct nsnp_model_weights {      /* host pointers, PyTorch layouts, gate order i,f,g,o */
+    const float* w_ih[2][2];   /* [layer][dir]  [256][18] / [256][128] */
+    const float* w_hh[2][2];   /*               [256][64] */
+    const float* b_ih[2][2];   /*               [256] */
+    const float* b_hh[2][2];   /*               [256] */
+    const float* proj_w;  const float* proj_b;    /* [128][128], [128] */
+    const float* dense_w; const float* dense_b;   /* [256][128], [256] */
+    const float* gt_w;    const float* gt_b;      /* [21][256], [21] */
+    const float* zy_w;    const float* zy_b;      /* [3][256], [3] */
+} nsnp_model_weights_t;
+
+size_t nsnp_model_blob_bytes(void);
+/* packs into host_blob (caller copies it to the device once) */
+int nsnp_model_pack_weights(const nsnp_model_weights_t* w, void* host_blob, size_t blob_bytes);
+size_t nsnp_model_workspace_bytes(int64_t n_sites);
+/* x: exactly one of x_i32_dev / x_f32_dev non-NULL, [n][33][18].  n_dev (optional) overrides n. */
+int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, const float* x_f32_dev,
+                              int64_t n, const int32_t* n_dev, float* gt_prob_dev, float* zy_prob_dev,
+                              void* workspace_dev, size_t workspace_bytes, int precision, void* stream);
+#define NSNP_PREC_FP32    0   /* fp32 FFMA everywhere (parity path) */
+#define NSNP_PREC_BF16X3  1   /* tcgen05 bf16 split-precision tensor-core path */
+
+/* ---- status / utilities ----------------------------------------------------------------------- */
+/* copies status_dev[0..3] to the host (synchronises the stream) and maps it to an NSNP_E_* code */
+int nsnp_check_status(const int32_t* status_dev, void* stream);
+
+/* ---- s2 host side: VCF record formatting ----------------------------------------------------------
+ * Replaces the per-site loop of PileupModel/predict.py:66-194 for ONE batch (<= batch_size sites of
+ * one contig file), including its order-dependent quirks.  Host memory.
+ *   cov8 float[n][8] = centre counts of channels [A C G T a c g t] (predict.py:63)
+ * Returns the number of bytes written to out (or the negative of the required capacity).
+ */
+int64_t nsnp_vcf_format_batch(const char* contig, int64_t n, const int32_t* pos1, const uint8_t* refbase,
+                              const float* gt_prob, const float* zy_prob, const float* cov8,
+                              char* out, int64_t out_capacity);
+
+/* ---- synthetic inputs (bench / tests) --------------------------------------- */
+typedef struct nsnp_synth_cfg {
+    uint64_t seed_ref, seed_var, seed_reads;
+    int64_t  contig_len;
+    int64_t  n_reads;
+    uint32_t sub_thr, ins_thr, del_thr;        /* per-base probabilities * 2^32 */
+    uint32_t snp_thr;                          /* planted variant density * 2^32 */
+    uint32_t lowmapq_thr, secondary_thr, supp_thr, nbase_thr, softclip_thr, long_indel_thr;
+    int32_t  len_min;
+    int32_t  ref_n_period, ref_n_len;          /* every period bp, a run of N in the reference (0 = none) */
+    int32_t  ref_lower_period, ref_lower_len;  /* soft-masked (lower-case) runs */
+    int32_t  gap_period, gap_len;              /* coverage gaps: no passing read overlaps them */
+    int32_t  use_eqx;                          /* 1: emit =/X ops instead of M */
+    const int32_t*  len_quantiles;             /* [1025] read reference-span quantiles */
+    const uint32_t* mrun_cdf;                  /* [256]  P(match-run <= k+1) * 2^32 */
+    const uint32_t* indel_cdf;                 /* [60]   P(indel len <= k+1) * 2^32 */
+} nsnp_synth_cfg_t;
+
+/* host generator (plain C loops; used by CPU tests and small cases) */
+int nsnp_synth_ref_host(const nsnp_synth_cfg_t* cfg, uint8_t* ref_out);
+int nsnp_synth_count_host(const nsnp_synth_cfg_t* cfg, int32_t* pos, uint16_t* flag, uint8_t* mapq,
+                          int32_t* n_ops, int32_t* n_query);
+int nsnp_synth_fill_host(const nsnp_synth_cfg_t* cfg, const int64_t* cigar_off, const int64_t* seq_off,
+                         uint32_t* cigar, uint8_t* seq2, uint8_t* nmask);
+/* device generator: same arithmetic, one thread per read (tables in cfg must be device pointers) */
+int nsnp_synth_ref_dev(const nsnp_synth_cfg_t* cfg, uint8_t* ref_dev, void* stream);
+int nsnp_synth_count_dev(const nsnp_synth_cfg_t* cfg, int32_t* pos, uint16_t* flag, uint8_t* mapq,
+                         int32_t* n_ops, int32_t* n_query, void* stream);
+int nsnp_synth_fill_dev(const nsnp_synth_cfg_t* cfg, const int64_t* cigar_off, const int64_t* seq_off,
+                        uint32_t* cigar, uint8_t* seq2, uint8_t* nmask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANOSNP_B200_H */

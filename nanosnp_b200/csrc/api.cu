@@ -1,0 +1,63 @@
+// C-ABI plumbing: error reporting, defaults, device-side status decoding.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace nsnp {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_status(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return NSNP_OK;
+    return set_error(NSNP_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+}  // namespace nsnp
+
+extern "C" {
+
+int nsnp_abi_version(void) { return NSNP_ABI_VERSION; }
+const char* nsnp_last_error(void) { return nsnp::g_err; }
+
+void nsnp_default_params(nsnp_params_t* p) {
+    if (!p) return;
+    p->snp_min_af = 0.12;      // make_predict_data.sh:122
+    p->indel_min_af = 0.12;    // make_predict_data.sh:123
+    p->min_coverage = 6;       // make_predict_data.sh:124
+    p->min_mapq = 20;          // make_predict_data.sh:117 --min-MQ 20
+    p->excl_flags = 2316;      // make_predict_data.sh:117 --excl-flags 2316
+    p->reserved = 0;
+}
+
+int nsnp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int nsnp_check_status(const int32_t* status_dev, void* stream) {
+    if (!status_dev) return nsnp::set_error(NSNP_E_INVALID, "nsnp_check_status: null status");
+    int32_t h[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, status_dev, sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return nsnp::set_error(NSNP_E_CUDA, "nsnp_check_status: %s", cudaGetErrorString(e));
+    switch (h[nsnp::ST_ERR]) {
+        case nsnp::DEV_OK: return NSNP_OK;
+        case nsnp::DEV_E_DEPTH: return nsnp::set_error(NSNP_E_OVERFLOW, "column depth exceeds 65535 near position %d", h[1]);
+        case nsnp::DEV_E_INDEL_SLAB: return nsnp::set_error(NSNP_E_OVERFLOW, "indel event slab overflow in tile %d", h[1]);
+        case nsnp::DEV_E_SEQ_SPAN: return nsnp::set_error(NSNP_E_OVERFLOW, "reads over one tile span >= 2^32 bases (tile %d)", h[1]);
+        case nsnp::DEV_E_CAND_CAP: return nsnp::set_error(NSNP_E_OVERFLOW, "candidate buffer too small: %d sites", h[1]);
+        case nsnp::DEV_E_UNSORTED: return nsnp::set_error(NSNP_E_INVALID, "reads are not sorted by position (read %d)", h[1]);
+        default: return nsnp::set_error(NSNP_E_CUDA, "unknown device status %d", h[0]);
+    }
+}
+
+}  // extern "C"

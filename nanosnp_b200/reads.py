@@ -1,0 +1,146 @@
+"""Flat packed read arrays (struct nsnp_reads of include/nanosnp_b200.h).
+
+This is the hand-off format between a host BAM decoder and the GPU path: it replaces the
+BAM -> `samtools mpileup` text -> per-contig text files chain of
+dna_sv_tensor/src/scripts/make_predict_data.sh:147-176.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+FIELDS = ("pos", "flag", "mapq", "cigar_off", "cigar", "seq_off", "seq2", "nmask")
+DTYPES = {"pos": np.int32, "flag": np.uint16, "mapq": np.uint8, "cigar_off": np.int64, "cigar": np.uint32,
+          "seq_off": np.int64, "seq2": np.uint8, "nmask": np.uint8}
+
+CIGAR_OPS = "MIDNSHP=X"
+
+
+@dataclass
+class PackedReads:
+    """Reads of one contig, sorted by pos.  Arrays are numpy (host) or torch (host-pinned / device)."""
+    pos: object
+    flag: object
+    mapq: object
+    cigar_off: object          # [n+1]
+    cigar: object
+    seq_off: object            # [n]
+    seq2: object
+    nmask: Optional[object] = None
+
+    @property
+    def n_reads(self) -> int:
+        return int(self.pos.shape[0])
+
+    @property
+    def n_cigar(self) -> int:
+        return int(self.cigar.shape[0])
+
+    @property
+    def n_bases(self) -> int:
+        return int(self.seq2.shape[0]) * 4
+
+    def is_torch(self) -> bool:
+        return not isinstance(self.pos, np.ndarray)
+
+    def nbytes(self) -> int:
+        tot = 0
+        for f in FIELDS:
+            a = getattr(self, f)
+            if a is None:
+                continue
+            tot += a.nbytes if isinstance(a, np.ndarray) else a.numel() * a.element_size()
+        return tot
+
+    def _ptr(self, a) -> int:
+        if a is None:
+            return 0
+        if isinstance(a, np.ndarray):
+            assert a.flags["C_CONTIGUOUS"]
+            return a.ctypes.data
+        assert a.is_contiguous()
+        return a.data_ptr()
+
+    def as_struct(self) -> _lib.Reads:
+        """ctypes view; the caller must keep `self` alive while the struct is in use."""
+        r = _lib.Reads()
+        r.n_reads = self.n_reads
+        for f in FIELDS:
+            setattr(r, f, self._ptr(getattr(self, f)))
+        r.qual = 0
+        r.n_cigar = self.n_cigar
+        r.n_bases = self.n_bases
+        return r
+
+    def to_torch(self, device, pin: bool = False, non_blocking: bool = False) -> "PackedReads":
+        import torch
+
+        def conv(a):
+            if a is None:
+                return None
+            if isinstance(a, np.ndarray):
+                # torch has no uint16/uint32 arithmetic, but storage + data_ptr is all we need
+                t = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a.view(np.int32) if a.dtype == np.uint32 else a)
+            else:
+                t = a
+            if pin and t.device.type == "cpu":
+                t = t.pin_memory()
+            return t.to(device, non_blocking=non_blocking)
+        return PackedReads(*[conv(getattr(self, f)) for f in FIELDS])
+
+    def to_numpy(self) -> "PackedReads":
+        def conv(f, a):
+            if a is None or isinstance(a, np.ndarray):
+                return a
+            return a.detach().cpu().numpy().view(DTYPES[f])
+        return PackedReads(*[conv(f, getattr(self, f)) for f in FIELDS])
+
+    def prefix(self, n: int) -> "PackedReads":
+        """First n reads (host arrays only): the bounded CPU-baseline sample of bench.py."""
+        assert isinstance(self.pos, np.ndarray)
+        nc = int(self.cigar_off[n])
+        # bases of the first n reads end where read n starts (reads are laid out in order)
+        nb = int(self.seq_off[n]) if n < self.n_reads else self.n_bases
+        nb4 = (nb + 3) // 4
+        return PackedReads(self.pos[:n], self.flag[:n], self.mapq[:n], self.cigar_off[: n + 1], self.cigar[:nc],
+                           self.seq_off[:n], self.seq2[:nb4], None if self.nmask is None else self.nmask[: (nb + 7) // 8])
+
+
+def reference_span(cigar: np.ndarray) -> int:
+    ops = cigar & 15
+    lens = cigar >> 4
+    return int(lens[(ops == 0) | (ops == 2) | (ops == 3) | (ops == 7) | (ops == 8)].sum())
+
+
+def from_records(records, with_nmask: bool = True) -> PackedReads:
+    """Builds PackedReads from an iterable of (pos0, flag, mapq, cigar_string, seq_string) tuples (tests, small inputs)."""
+    import re
+    pos, flag, mapq, coff, cig, soff = [], [], [], [0], [], []
+    bases = []
+    nb = 0
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    for (p, f, q, cs, seq) in records:
+        pos.append(p); flag.append(f); mapq.append(q)
+        for m in re.finditer(r"(\d+)([MIDNSHP=X])", cs):
+            cig.append((int(m.group(1)) << 4) | CIGAR_OPS.index(m.group(2)))
+        coff.append(len(cig))
+        soff.append(nb)
+        bases.append(seq)
+        nb += (len(seq) + 15) // 16 * 16
+    seq2 = np.zeros((nb + 3) // 4 + 8, np.uint8)
+    nmask = np.zeros((nb + 7) // 8 + 8, np.uint8)
+    for so, seq in zip(soff, bases):
+        for j, ch in enumerate(seq.upper()):
+            k = so + j
+            if ch in code:
+                seq2[k >> 2] |= code[ch] << (2 * (k & 3))
+            else:
+                nmask[k >> 3] |= 1 << (k & 7)
+    return PackedReads(np.asarray(pos, np.int32), np.asarray(flag, np.uint16), np.asarray(mapq, np.uint8),
+                       np.asarray(coff, np.int64), np.asarray(cig, np.uint32), np.asarray(soff, np.int64), seq2,
+                       nmask if with_nmask else None)

@@ -1,0 +1,318 @@
+// s2: PileupModel forward (PileupModel/model.py:14-73,114-119; config/ont_pileup.yaml:6-20).
+//
+//   x[N,33,18] -> BiLSTM(18->64) -> BiLSTM(128->64) -> Linear(128->128) -> Linear(128->256)+tanh @t=16
+//             -> Linear(256->21), Linear(256->3) -> softmax
+//
+// Exact-output pruning: layer 1 runs only the 17 steps per direction that reach
+// t=16, output_proj/dense run only at t=16, the two indel heads are never computed.
+//
+// This file holds the fp32 path (NSNP_PREC_FP32): plain FFMA with fp32 accumulation and accurate
+// expf/tanhf -- it is the parity path and the fallback for low-margin sites of the tensor-core path.
+//   lstm_dir_kernel<L0>  one CTA = 64 sites x one direction, weights resident in shared memory (85 KB),
+//                        lanes own hidden-unit pairs, warps own site groups, cell state in registers.
+//   lstm_dir_kernel<L1>  one CTA = 32 sites x one direction, 197 KB of weights resident.
+//   tail_kernel          proj + dense/tanh + heads + softmax on the t=16 state.
+#include "common.cuh"
+
+namespace nsnp {
+namespace {
+
+constexpr int kH = 64;               // hidden size
+constexpr int kG = 256;              // 4 gates x 64
+constexpr int kT = NSNP_WINDOW;      // 33
+constexpr int kF = NSNP_CHANNELS;    // 18
+constexpr int kMid = NSNP_FLANK;     // 16
+constexpr int kKP0 = 84;             // [x 18 | pad 2 | h 64]
+constexpr int kIn0 = 20;
+constexpr int kKP1 = 192;            // [l0 fwd 64 | l0 rev 64 | h 64]
+constexpr int kIn1 = 128;
+
+// blob layout (floats)
+constexpr size_t kOffW0 = 0;                                        // [2][kKP0][256]
+constexpr size_t kOffB0 = kOffW0 + 2 * (size_t)kKP0 * kG;           // [2][256]
+constexpr size_t kOffW1 = kOffB0 + 2 * kG;                          // [2][kKP1][256]
+constexpr size_t kOffB1 = kOffW1 + 2 * (size_t)kKP1 * kG;           // [2][256]
+constexpr size_t kOffProjW = kOffB1 + 2 * kG;                       // [128 k][128]
+constexpr size_t kOffProjB = kOffProjW + 128 * 128;
+constexpr size_t kOffDenseW = kOffProjB + 128;                      // [128 k][256]
+constexpr size_t kOffDenseB = kOffDenseW + 128 * 256;
+constexpr size_t kOffHeadW = kOffDenseB + 256;                      // [256 k][24]
+constexpr size_t kOffHeadB = kOffHeadW + 256 * 24;
+constexpr size_t kBlobFloats = kOffHeadB + 24 + 8;
+
+// column of gate row (gate g, unit u) in the shared-memory weight tile: two lane-contiguous halves so that
+// every LDS.128 of a warp is conflict free.  half = g>>1, lane = u>>1.
+__host__ __device__ constexpr int gate_col(int g, int u) { return (g >> 1) * 128 + (u >> 1) * 4 + (g & 1) * 2 + (u & 1); }
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int LAYER> struct Cfg;
+template <> struct Cfg<0> { static constexpr int KP = kKP0, IN = kIn0, S = 64, STEPS = 33; };
+template <> struct Cfg<1> { static constexpr int KP = kKP1, IN = kIn1, S = 32, STEPS = 17; };
+
+template <int LAYER>
+__global__ void __launch_bounds__(256, 1) lstm_dir_kernel(const float* __restrict__ blob, const int32_t* __restrict__ xi,
+                                                          const float* __restrict__ xf, const float* __restrict__ h0_in,
+                                                          float* __restrict__ out, int64_t n_max, const int32_t* __restrict__ n_dev)
+{
+    using C = Cfg<LAYER>;
+    constexpr int KP = C::KP, IN = C::IN, S = C::S, SPT = S / 8;
+    extern __shared__ __align__(16) float smem[];
+    float* W = smem;                       // [KP][256]
+    float* bias = W + KP * kG;             // [256]
+    float* act = bias + kG;                // [S][KP]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int dir = blockIdx.y;
+    int64_t n = n_max;
+    if (n_dev) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
+    const int64_t site0 = (int64_t)blockIdx.x * S;
+    if (site0 >= n) return;
+
+    {   // weights of this (layer, direction) -> shared memory
+        const float* gw = blob + (LAYER == 0 ? kOffW0 : kOffW1) + (size_t)dir * KP * kG;
+        const float4* g4 = reinterpret_cast<const float4*>(gw);
+        float4* s4 = reinterpret_cast<float4*>(W);
+        for (int i = tid; i < KP * kG / 4; i += 256) s4[i] = __ldg(g4 + i);
+        bias[tid] = __ldg(blob + (LAYER == 0 ? kOffB0 : kOffB1) + dir * kG + tid);
+        for (int i = tid; i < S * KP; i += 256) act[i] = 0.0f;
+    }
+    float c[2][SPT];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) { c[0][s] = 0.f; c[1][s] = 0.f; }
+    __syncthreads();
+
+    for (int step = 0; step < C::STEPS; ++step) {
+        const int t = dir == 0 ? step : (kT - 1 - step);
+        // ---- stage the input rows of time t ----
+        if (LAYER == 0) {
+            for (int i = tid; i < S * kF; i += 256) {
+                const int s = i / kF, j = i - s * kF;
+                int64_t site = site0 + s; if (site >= n) site = n - 1;
+                const int64_t g = (site * kT + t) * kF + j;
+                act[s * KP + j] = xi ? (float)__ldg(xi + g) : __ldg(xf + g);
+            }
+        } else {
+            for (int i = tid; i < S * (kIn1 / 4); i += 256) {
+                const int s = i / (kIn1 / 4), j = i - s * (kIn1 / 4);
+                int64_t site = site0 + s; if (site >= n) site = n - 1;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(h0_in + (site * kT + t) * kIn1) + j);
+                *reinterpret_cast<float4*>(act + s * KP + 4 * j) = v;
+            }
+        }
+        __syncthreads();
+        // ---- gates = W . [in ; h] + b ----
+        float acc[4][2][SPT];
+        {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + lane * 4);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + 128 + lane * 4);
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) {
+                acc[0][0][s] = b0.x; acc[0][1][s] = b0.y; acc[1][0][s] = b0.z; acc[1][1][s] = b0.w;
+                acc[2][0][s] = b1.x; acc[2][1][s] = b1.y; acc[3][0][s] = b1.z; acc[3][1][s] = b1.w;
+            }
+        }
+        const float* arow = act + (warp * SPT) * KP;
+#pragma unroll 2
+        for (int k4 = 0; k4 < KP / 4; ++k4) {
+            float4 a[SPT];
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) a[s] = *reinterpret_cast<const float4*>(arow + s * KP + 4 * k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 w0 = *reinterpret_cast<const float4*>(W + (4 * k4 + kk) * kG + lane * 4);
+                const float4 w1 = *reinterpret_cast<const float4*>(W + (4 * k4 + kk) * kG + 128 + lane * 4);
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) {
+                    const float av = kk == 0 ? a[s].x : kk == 1 ? a[s].y : kk == 2 ? a[s].z : a[s].w;
+                    acc[0][0][s] = fmaf(w0.x, av, acc[0][0][s]); acc[0][1][s] = fmaf(w0.y, av, acc[0][1][s]);
+                    acc[1][0][s] = fmaf(w0.z, av, acc[1][0][s]); acc[1][1][s] = fmaf(w0.w, av, acc[1][1][s]);
+                    acc[2][0][s] = fmaf(w1.x, av, acc[2][0][s]); acc[2][1][s] = fmaf(w1.y, av, acc[2][1][s]);
+                    acc[3][0][s] = fmaf(w1.z, av, acc[3][0][s]); acc[3][1][s] = fmaf(w1.w, av, acc[3][1][s]);
+                }
+            }
+        }
+        __syncthreads();                   // everyone is done reading h_{t-1}
+        // ---- cell update (PyTorch gate order i, f, g, o) ----
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            float hv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float ig = sigmoid_acc(acc[0][u][s]), fg = sigmoid_acc(acc[1][u][s]);
+                const float gg = tanhf(acc[2][u][s]), og = sigmoid_acc(acc[3][u][s]);
+                c[u][s] = fg * c[u][s] + ig * gg;
+                hv[u] = og * tanhf(c[u][s]);
+            }
+            const int sl = warp * SPT + s;
+            *reinterpret_cast<float2*>(act + sl * KP + IN + 2 * lane) = make_float2(hv[0], hv[1]);
+            const int64_t site = site0 + sl;
+            if (site < n) {
+                if (LAYER == 0) *reinterpret_cast<float2*>(out + (site * kT + t) * 128 + dir * kH + 2 * lane) = make_float2(hv[0], hv[1]);
+                else if (step == C::STEPS - 1) *reinterpret_cast<float2*>(out + site * 128 + dir * kH + 2 * lane) = make_float2(hv[0], hv[1]);
+            }
+        }
+        // the next iteration's staging writes only act[.. < IN]; the barrier after it orders the h writes
+    }
+}
+
+// out[s][c] = b[c] + sum_k in[s][k] * Wt[k][c]   (Wt k-major in global memory, read through L1)
+template <int IN, int OUT, int SG, bool TANH>
+__device__ __forceinline__ void dense_layer(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ b,
+                                            float* __restrict__ outp, int S)
+{
+    const int items = OUT * (S / SG);
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int cidx = it % OUT, sg = it / OUT;
+        float acc[SG];
+        const float bb = __ldg(b + cidx);
+#pragma unroll
+        for (int s = 0; s < SG; ++s) acc[s] = bb;
+        for (int k = 0; k < IN; k += 4) {
+            const float w0 = __ldg(Wt + (size_t)(k + 0) * OUT + cidx), w1 = __ldg(Wt + (size_t)(k + 1) * OUT + cidx);
+            const float w2 = __ldg(Wt + (size_t)(k + 2) * OUT + cidx), w3 = __ldg(Wt + (size_t)(k + 3) * OUT + cidx);
+#pragma unroll
+            for (int s = 0; s < SG; ++s) {
+                const float4 a = *reinterpret_cast<const float4*>(in + (sg * SG + s) * IN + k);
+                acc[s] = fmaf(w0, a.x, acc[s]); acc[s] = fmaf(w1, a.y, acc[s]);
+                acc[s] = fmaf(w2, a.z, acc[s]); acc[s] = fmaf(w3, a.w, acc[s]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SG; ++s) outp[(sg * SG + s) * OUT + cidx] = TANH ? tanhf(acc[s]) : acc[s];
+    }
+}
+
+constexpr int kTailS = 16;
+__global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ blob, const float* __restrict__ h16, int64_t n_max,
+                                                   const int32_t* __restrict__ n_dev, float* __restrict__ gt, float* __restrict__ zy)
+{
+    __shared__ __align__(16) float in[kTailS * 128];
+    __shared__ __align__(16) float pj[kTailS * 128];
+    __shared__ __align__(16) float dn[kTailS * 256];
+    __shared__ float lg[kTailS * 24];
+    int64_t n = n_max;
+    if (n_dev) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
+    const int64_t site0 = (int64_t)blockIdx.x * kTailS;
+    if (site0 >= n) return;
+    for (int i = threadIdx.x; i < kTailS * 32; i += 256) {
+        const int s = i >> 5, j = i & 31;        // 32 float4 per site
+        int64_t site = site0 + s; if (site >= n) site = n - 1;
+        reinterpret_cast<float4*>(in)[i] = __ldg(reinterpret_cast<const float4*>(h16 + site * 128) + j);
+    }
+    __syncthreads();
+    dense_layer<128, 128, 8, false>(in, blob + kOffProjW, blob + kOffProjB, pj, kTailS);      // output_proj, model.py:37
+    __syncthreads();
+    dense_layer<128, 256, 8, true>(pj, blob + kOffDenseW, blob + kOffDenseB, dn, kTailS);     // dense + tanh, model.py:67
+    __syncthreads();
+    dense_layer<256, 24, 8, false>(dn, blob + kOffHeadW, blob + kOffHeadB, lg, kTailS);       // genotype + zygosity heads
+    __syncthreads();
+    if (threadIdx.x < kTailS) {
+        const int s = threadIdx.x;
+        const int64_t site = site0 + s;
+        if (site < n) {
+            const float* l = lg + s * 24;
+            float m = l[0];
+            for (int j = 1; j < 21; ++j) m = fmaxf(m, l[j]);
+            float e[21], sum = 0.f;
+            for (int j = 0; j < 21; ++j) { e[j] = expf(l[j] - m); sum += e[j]; }
+            for (int j = 0; j < 21; ++j) gt[site * 21 + j] = e[j] / sum;
+            float m2 = fmaxf(l[21], fmaxf(l[22], l[23]));
+            const float e0 = expf(l[21] - m2), e1 = expf(l[22] - m2), e2 = expf(l[23] - m2);
+            const float s2 = e0 + e1 + e2;
+            zy[site * 3 + 0] = e0 / s2; zy[site * 3 + 1] = e1 / s2; zy[site * 3 + 2] = e2 / s2;
+        }
+    }
+}
+
+constexpr int64_t kChunkSites = 1 << 16;
+
+}  // namespace
+}  // namespace nsnp
+
+using namespace nsnp;
+
+extern "C" {
+
+size_t nsnp_model_blob_bytes(void) { return kBlobFloats * sizeof(float); }
+
+int nsnp_model_pack_weights(const nsnp_model_weights_t* w, void* host_blob, size_t blob_bytes) {
+    if (!w || !host_blob) return set_error(NSNP_E_INVALID, "nsnp_model_pack_weights: null argument");
+    if (blob_bytes < nsnp_model_blob_bytes()) return set_error(NSNP_E_WORKSPACE, "model blob too small");
+    float* b = (float*)host_blob;
+    memset(b, 0, nsnp_model_blob_bytes());
+    for (int d = 0; d < 2; ++d) {
+        // layer 0: rows k = [x 0..17 | pad | h 20..83]
+        const float *wih = w->w_ih[0][d], *whh = w->w_hh[0][d], *bi = w->b_ih[0][d], *bh = w->b_hh[0][d];
+        if (!wih || !whh || !bi || !bh) return set_error(NSNP_E_INVALID, "missing layer-0 weights");
+        float* W0 = b + kOffW0 + (size_t)d * kKP0 * kG;
+        for (int g = 0; g < 4; ++g) for (int u = 0; u < kH; ++u) {
+            const int row = g * kH + u, col = gate_col(g, u);
+            for (int k = 0; k < kF; ++k) W0[k * kG + col] = wih[row * kF + k];
+            for (int k = 0; k < kH; ++k) W0[(kIn0 + k) * kG + col] = whh[row * kH + k];
+            b[kOffB0 + d * kG + col] = bi[row] + bh[row];
+        }
+        const float *wih1 = w->w_ih[1][d], *whh1 = w->w_hh[1][d], *bi1 = w->b_ih[1][d], *bh1 = w->b_hh[1][d];
+        if (!wih1 || !whh1 || !bi1 || !bh1) return set_error(NSNP_E_INVALID, "missing layer-1 weights");
+        float* W1 = b + kOffW1 + (size_t)d * kKP1 * kG;
+        for (int g = 0; g < 4; ++g) for (int u = 0; u < kH; ++u) {
+            const int row = g * kH + u, col = gate_col(g, u);
+            for (int k = 0; k < kIn1; ++k) W1[k * kG + col] = wih1[row * kIn1 + k];
+            for (int k = 0; k < kH; ++k) W1[(kIn1 + k) * kG + col] = whh1[row * kH + k];
+            b[kOffB1 + d * kG + col] = bi1[row] + bh1[row];
+        }
+    }
+    if (!w->proj_w || !w->proj_b || !w->dense_w || !w->dense_b || !w->gt_w || !w->gt_b || !w->zy_w || !w->zy_b)
+        return set_error(NSNP_E_INVALID, "missing head weights");
+    for (int o = 0; o < 128; ++o) { for (int k = 0; k < 128; ++k) b[kOffProjW + k * 128 + o] = w->proj_w[o * 128 + k]; b[kOffProjB + o] = w->proj_b[o]; }
+    for (int o = 0; o < 256; ++o) { for (int k = 0; k < 128; ++k) b[kOffDenseW + k * 256 + o] = w->dense_w[o * 128 + k]; b[kOffDenseB + o] = w->dense_b[o]; }
+    for (int o = 0; o < 21; ++o) { for (int k = 0; k < 256; ++k) b[kOffHeadW + k * 24 + o] = w->gt_w[o * 256 + k]; b[kOffHeadB + o] = w->gt_b[o]; }
+    for (int o = 0; o < 3; ++o) { for (int k = 0; k < 256; ++k) b[kOffHeadW + k * 24 + 21 + o] = w->zy_w[o * 256 + k]; b[kOffHeadB + 21 + o] = w->zy_b[o]; }
+    return NSNP_OK;
+}
+
+size_t nsnp_model_workspace_bytes(int64_t n_sites) {
+    int64_t ch = n_sites < kChunkSites ? n_sites : kChunkSites; if (ch < 1) ch = 1;
+    return (size_t)ch * (kT * 128 + 128) * sizeof(float) + 256;
+}
+
+int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, const float* x_f32_dev, int64_t n,
+                              const int32_t* n_dev, float* gt_prob_dev, float* zy_prob_dev, void* workspace_dev,
+                              size_t workspace_bytes, int precision, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!blob_dev || (!x_i32_dev == !x_f32_dev) || !gt_prob_dev || !zy_prob_dev || !workspace_dev)
+        return set_error(NSNP_E_INVALID, "nsnp_pileup_model_forward: null argument (exactly one of x_i32/x_f32)");
+    if (precision != NSNP_PREC_FP32) return set_error(NSNP_E_UNSUPPORTED, "precision %d not built", precision);
+    if (n < 0) return set_error(NSNP_E_INVALID, "negative n");
+    if (workspace_bytes < nsnp_model_workspace_bytes(n)) return set_error(NSNP_E_WORKSPACE, "model workspace too small");
+    if (nsnp_device_count() == 0) return set_error(NSNP_E_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (n == 0) return NSNP_OK;
+    const float* blob = (const float*)blob_dev;
+    const size_t smem0 = (size_t)(kKP0 * kG + kG + Cfg<0>::S * kKP0) * sizeof(float);
+    const size_t smem1 = (size_t)(kKP1 * kG + kG + Cfg<1>::S * kKP1) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(lstm_dir_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0) != cudaSuccess ||
+            cudaFuncSetAttribute(lstm_dir_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1) != cudaSuccess)
+            return cuda_status("cudaFuncSetAttribute(lstm_dir_kernel)");
+        attr_done = true;
+    }
+    float* h0 = (float*)workspace_dev;
+    const int64_t ch = n < kChunkSites ? n : kChunkSites;
+    float* h16 = h0 + ch * kT * 128;
+    // n_dev (device-side site count) only makes sense for a single chunk; larger batches are chunked by the host count
+    for (int64_t off = 0; off < n; off += ch) {
+        const int64_t m = (n - off) < ch ? (n - off) : ch;
+        const int32_t* nd = (off == 0 && n <= ch) ? n_dev : nullptr;
+        const int32_t* xi = x_i32_dev ? x_i32_dev + off * kT * kF : nullptr;
+        const float* xf = x_f32_dev ? x_f32_dev + off * kT * kF : nullptr;
+        dim3 g0((unsigned)((m + Cfg<0>::S - 1) / Cfg<0>::S), 2), g1((unsigned)((m + Cfg<1>::S - 1) / Cfg<1>::S), 2);
+        lstm_dir_kernel<0><<<g0, 256, smem0, stream>>>(blob, xi, xf, nullptr, h0, m, nd);
+        lstm_dir_kernel<1><<<g1, 256, smem1, stream>>>(blob, nullptr, nullptr, h0, h16, m, nd);
+        tail_kernel<<<(unsigned)((m + kTailS - 1) / kTailS), 256, 0, stream>>>(blob, h16, m, nd, gt_prob_dev + off * 21, zy_prob_dev + off * 3);
+        if (int e = cuda_status("pileup model kernels")) return e;
+    }
+    return NSNP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,520 @@
+// s1 step A: pileup count tensor [L][18] + per-position flags, straight from flat packed reads.
+//
+// Replaces `samtools mpileup` (make_predict_data.sh:117,151) + TensorMaker::make_tensor
+// (tensor_maker.cpp:61-249) + the candidate gate of create_pileup_tensor (main.cpp:196) using the event
+// formulation of SURVEY.md appendix A.8.  No text, no per-base atomics:
+//
+//   read_scan_kernel   one warp per read: reference end, (ref,query) checkpoints every 32 CIGAR ops,
+//                      first/last read index per position tile.
+//   pileup_tile_kernel persistent CTAs, one position tile (T bp) at a time in shared memory:
+//       - one warp per overlapping read, ONE LANE PER CIGAR OP (warp scan gives each op its ref/query start)
+//       - an aligned run (M/=/X) costs two run-boundary increments (depth by prefix sum later) plus a
+//         bit-parallel 2-bit XOR against the reference tile, 16 bases per word: only MISMATCHES touch a
+//         counter (matches are implied: the reference channel is -(A+C+G+T), tensor_maker.cpp:230-246)
+//       - a deletion costs two boundary increments ('*'/'#' depth) plus one indel event
+//       - indel events are chained per position (exact grouping for I1/D1 by length / sequence identity)
+//       - epilogue: prefix sums -> 18 channels + AF gate (IEEE double, tensor_maker.cpp:195-228)
+//         -> rows staged in shared memory -> coalesced 16-byte stores of the int32 [T][18] block.
+#include "common.cuh"
+
+namespace nsnp {
+namespace {
+
+constexpr int kCkShift = 5;                 // checkpoint every 32 ops
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kReadList = 1024;             // overlapping reads handled per round
+constexpr int kStageRows = kThreads;        // epilogue sub-block
+constexpr int kStageStride = 19;            // 18 + 1 pad: conflict-free row writes
+
+struct Event {                               // 16 bytes, lives in the per-CTA global slab (L2 resident)
+    uint32_t next;                           // previous event anchored at the same position (chain)
+    uint32_t info;                           // len | class << 8     class: 0 I, 1 i, 2 D, 3 d
+    uint64_t seq;                            // absolute base index of the inserted sequence
+};
+
+struct Workspace {
+    int32_t* rend;        // [n_reads]
+    int32_t* ck_ref;      // [n_slots]
+    int32_t* ck_q;        // [n_slots]
+    int32_t* tile_lo;     // [n_tiles]
+    int32_t* tile_hi;     // [n_tiles]
+    int32_t* counters;    // [16]  0: tile ticket
+    Event*   slabs;       // [n_ctas][slab_cap]
+    int64_t  slab_cap;
+};
+
+__device__ __forceinline__ bool op_ref(int op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
+__device__ __forceinline__ bool op_query(int op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }
+__device__ __forceinline__ bool op_aligned(int op) { return op == 0 || op == 7 || op == 8; }
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+    const int l = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, d); if (l >= d) v += t; }
+    return v;
+}
+
+// 16 two-bit bases starting at base index i of a packed array of 32-bit words
+__device__ __forceinline__ uint32_t bases16(const uint32_t* __restrict__ w, int64_t i) {
+    const int64_t k = i >> 4;
+    return __funnelshift_r(w[k], w[k + 1], (int)(i & 15) * 2);
+}
+__device__ __forceinline__ uint32_t bases16_g(const uint32_t* __restrict__ w, int64_t i) {
+    const int64_t k = i >> 4;
+    return __funnelshift_r(__ldg(w + k), __ldg(w + k + 1), (int)(i & 15) * 2);
+}
+// 16 one-bit flags starting at bit index i
+__device__ __forceinline__ uint32_t bits16_g(const uint32_t* __restrict__ w, int64_t i) {
+    const int64_t k = i >> 5;
+    return __funnelshift_r(__ldg(w + k), __ldg(w + k + 1), (int)(i & 31)) & 0xFFFFu;
+}
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {     // bit j -> bit 2j
+    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) read_scan_kernel(nsnp_reads_t rd, nsnp_params_t prm, int64_t region_start,
+                                                        int64_t region_end, int tile_shift, Workspace ws)
+{
+    const int lane = lane_id();
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < rd.n_reads; r += nwarps) {
+        const int32_t pos = rd.pos[r];
+        const uint32_t flag = rd.flag[r];
+        const bool pass = !(flag & 4u) && !(flag & prm.excl_flags) && (int)rd.mapq[r] >= prm.min_mapq;   // appendix B.1
+        if (!pass) { if (lane == 0) ws.rend[r] = INT32_MIN; continue; }          // never overlaps any tile
+        const int64_t c0 = rd.cigar_off[r], c1 = rd.cigar_off[r + 1];
+        const int64_t slot0 = (c0 >> kCkShift) + r;
+        int32_t R = pos, Q = 0;
+        for (int64_t k = c0; k < c1; k += 32) {
+            int rl = 0, ql = 0;
+            if (k + lane < c1) {
+                const uint32_t cg = __ldg(rd.cigar + k + lane);
+                const int op = cg & 15, len = cg >> 4;
+                rl = op_ref(op) ? len : 0; ql = op_query(op) ? len : 0;
+            }
+            if (lane == 0) { const int64_t s = slot0 + ((k - c0) >> kCkShift); ws.ck_ref[s] = R; ws.ck_q[s] = Q; }
+            R += __reduce_add_sync(0xffffffffu, rl);
+            Q += __reduce_add_sync(0xffffffffu, ql);
+        }
+        if (lane == 0) ws.rend[r] = R;
+        // tiles this read overlaps
+        const int64_t a = pos > region_start ? pos : region_start;
+        const int64_t b = R < region_end ? R : region_end;
+        if (a < b) {
+            const int t0 = (int)((a - region_start) >> tile_shift), t1 = (int)((b - 1 - region_start) >> tile_shift);
+            for (int t = t0 + lane; t <= t1; t += 32) { atomicMin(&ws.tile_lo[t], (int)r); atomicMax(&ws.tile_hi[t], (int)r + 1); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int T>
+struct TileSmem {
+    uint32_t base[4][T];          // mismatch counters, u16 pairs: [strand*2 + (b>>1)][p], half = b&1
+    uint32_t nn[T];               // read-N bases: fwd | rev << 16
+    uint32_t ms[T], me[T];        // aligned-run starts / ends (fwd | rev << 16); later: depth, I1|i1
+    uint32_t ds[T], de[T];        // deletion-span starts / ends;                later: depth, D1|d1
+    uint32_t head[T];             // indel event chain heads
+    uint32_t ref2[T / 16 + 2];    // 2-bit reference tile
+    uint32_t refx[T / 16 + 2];    // 01 at non-ACGT reference positions (forces a "mismatch" event)
+    uint32_t skipcov[T / 32];     // positions inside a reference skip (N op)
+    uint8_t  refc[T];
+    int32_t  stage[kStageRows * kStageStride];
+    int32_t  rlist[kReadList];
+    int32_t  warp_tot[kWarps][4];
+    int32_t  n_rlist, next_task, n_events, tile;
+};
+
+template <int T>
+__device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t& rd, const Workspace& ws, Event* slab,
+                                             int r, int64_t ts, int64_t te, int32_t* status)
+{
+    const int lane = lane_id();
+    const int32_t rpos = rd.pos[r];
+    const int64_t c0 = rd.cigar_off[r], c1 = rd.cigar_off[r + 1];
+    const int64_t sbase = rd.seq_off[r];
+    const int strand = (rd.flag[r] >> 4) & 1;
+    const uint32_t sinc = 1u << (16 * strand);
+    const int nchunks = (int)((c1 - c0 + 31) >> kCkShift);
+    const int32_t* ckr = ws.ck_ref + ((c0 >> kCkShift) + r);
+    const int32_t* ckq = ws.ck_q + ((c0 >> kCkShift) + r);
+    // last chunk whose first op starts at or before the tile start (32-ary search over the checkpoints)
+    int lo = 0, hi = nchunks;
+    if (rpos < ts) {
+        while (hi - lo > 1) {
+            const int step = (hi - lo + 31) >> 5;
+            const int c = lo + lane * step;
+            const bool le = c < hi && (int64_t)__ldg(ckr + c) <= ts;
+            const int cnt = __popc(__ballot_sync(0xffffffffu, le));      // monotone: lanes 0..cnt-1 are true, cnt >= 1
+            lo = lo + (cnt - 1) * step;
+            hi = min(hi, lo + step);
+        }
+    }
+    int chunk = lo;
+    int64_t R = __ldg(ckr + chunk), Q = __ldg(ckq + chunk);
+    const uint32_t* seqw = reinterpret_cast<const uint32_t*>(rd.seq2);
+    const uint32_t* nmw = reinterpret_cast<const uint32_t*>(rd.nmask);
+
+    for (int64_t k = c0 + ((int64_t)chunk << kCkShift); k < c1 && R <= te; k += 32) {
+        int op = 6, len = 0;                                            // pad: consumes nothing
+        if (k + lane < c1) { const uint32_t cg = __ldg(rd.cigar + k + lane); op = cg & 15; len = cg >> 4; }
+        const int rl = op_ref(op) ? len : 0, ql = op_query(op) ? len : 0;
+        const int ri = warp_incl_scan(rl), qi = warp_incl_scan(ql);
+        const int64_t rs = R + ri - rl;                                 // reference start of this lane's op
+        const int64_t qs = Q + qi - ql;                                 // query start (relative to the read)
+        R += __shfl_sync(0xffffffffu, ri, 31);
+        Q += __shfl_sync(0xffffffffu, qi, 31);
+
+        if (op_aligned(op)) {
+            const int64_t a = rs > ts ? rs : ts, b = (rs + len) < te ? (rs + len) : te;
+            if (a < b) {
+                const int pa = (int)(a - ts), n = (int)(b - a);
+                atomicAdd(&sm.ms[pa], sinc);
+                if (b < te) atomicAdd(&sm.me[pa + n], sinc);
+                const int64_t g = sbase + qs + (a - rs);
+                for (int o = 0; o < n; o += 16) {
+                    const int m = min(16, n - o);
+                    const uint32_t sw = bases16_g(seqw, g + o);
+                    const uint32_t rw = bases16(sm.ref2, pa + o);
+                    uint32_t x = sw ^ rw;
+                    uint32_t mm = ((x | (x >> 1)) & 0x55555555u) | bases16(sm.refx, pa + o);
+                    if (m < 16) mm &= (1u << (2 * m)) - 1u;
+                    if (nmw) {
+                        uint32_t nb = bits16_g(nmw, g + o);
+                        if (m < 16) nb &= (1u << m) - 1u;
+                        if (nb) {
+                            mm &= ~spread16(nb);
+                            while (nb) { const int j = __ffs(nb) - 1; nb &= nb - 1; atomicAdd(&sm.nn[pa + o + j], sinc); }
+                        }
+                    }
+                    while (mm) {
+                        const int j2 = __ffs(mm) - 1; mm &= mm - 1;
+                        const int bcode = (sw >> j2) & 3;
+                        atomicAdd(&sm.base[strand * 2 + (bcode >> 1)][pa + o + (j2 >> 1)], 1u << (16 * (bcode & 1)));
+                    }
+                }
+            }
+        } else if (op == 2 || op == 1) {
+            if (op == 2) {
+                const int64_t a = rs > ts ? rs : ts, b = (rs + len) < te ? (rs + len) : te;
+                if (a < b) {
+                    atomicAdd(&sm.ds[(int)(a - ts)], sinc);
+                    if (b < te) atomicAdd(&sm.de[(int)(b - ts)], sinc);
+                }
+            }
+            // indel event anchored at the preceding reference position (appendix A.8 iii/iv); leading ops are never reported
+            const int64_t anchor = rs - 1;
+            if (len <= NSNP_MAX_INDEL && rs > rpos && anchor >= ts && anchor < te) {
+                const int e = atomicAdd(&sm.n_events, 1);
+                if (e < ws.slab_cap) {
+                    Event ev;
+                    ev.next = atomicExch(&sm.head[(int)(anchor - ts)], (uint32_t)e);
+                    ev.info = (uint32_t)len | ((uint32_t)((op == 2 ? 2 : 0) + strand) << 8);
+                    ev.seq = (uint64_t)(sbase + qs);
+                    slab[e] = ev;
+                } else {
+                    dev_fail(status, DEV_E_INDEL_SLAB, sm.tile);
+                }
+            }
+        } else if (op == 3) {
+            const int64_t a = rs > ts ? rs : ts, b = (rs + len) < te ? (rs + len) : te;
+            for (int64_t p = a; p < b; ++p) atomicOr(&sm.skipcov[(int)(p - ts) >> 5], 1u << ((int)(p - ts) & 31));
+        }
+    }
+}
+
+__device__ __forceinline__ bool same_insert(const uint32_t* seqw, const uint32_t* nmw, uint64_t g1, uint64_t g2, int len) {
+    for (int o = 0; o < len; o += 16) {
+        const int m = min(16, len - o);
+        uint32_t x = bases16_g(seqw, (int64_t)g1 + o) ^ bases16_g(seqw, (int64_t)g2 + o);
+        if (nmw) {
+            uint32_t n1 = bits16_g(nmw, (int64_t)g1 + o), n2 = bits16_g(nmw, (int64_t)g2 + o);
+            if (m < 16) { n1 &= (1u << m) - 1u; n2 &= (1u << m) - 1u; }
+            if (n1 != n2) return false;
+            x &= ~(spread16(n1) * 3u);
+        }
+        if (m < 16) x &= (1u << (2 * m)) - 1u;
+        if (x) return false;
+    }
+    return true;
+}
+
+template <int T>
+__global__ void __launch_bounds__(kThreads) pileup_tile_kernel(nsnp_reads_t rd, nsnp_params_t prm, const uint8_t* __restrict__ ref,
+                                                               int64_t region_start, int64_t region_len, int n_tiles,
+                                                               Workspace ws, int32_t* __restrict__ counts,
+                                                               uint8_t* __restrict__ flags, int32_t* status)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<T>& sm = *reinterpret_cast<TileSmem<T>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Event* slab = ws.slabs + (int64_t)blockIdx.x * ws.slab_cap;
+    const uint32_t* seqw = reinterpret_cast<const uint32_t*>(rd.seq2);
+    const uint32_t* nmw = reinterpret_cast<const uint32_t*>(rd.nmask);
+
+    for (;;) {
+        __syncthreads();                                    // previous tile fully written, smem reusable
+        if (tid == 0) sm.tile = atomicAdd(&ws.counters[0], 1);
+        __syncthreads();
+        const int tile = sm.tile;
+        if (tile >= n_tiles) break;
+        const int64_t ts = region_start + (int64_t)tile * T;
+        const int64_t te = min(ts + T, region_start + region_len);
+        const int tn = (int)(te - ts);
+
+        // ---- clear counters, stage the reference tile ----
+        {
+            uint32_t* z = &sm.base[0][0];
+            for (int i = tid; i < 9 * T; i += kThreads) z[i] = 0u;                     // base, nn, ms, me, ds, de
+            for (int i = tid; i < T; i += kThreads) sm.head[i] = 0xFFFFFFFFu;
+            for (int i = tid; i < T / 32; i += kThreads) sm.skipcov[i] = 0u;
+            for (int i = tid; i < T; i += kThreads) sm.refc[i] = i < tn ? ref[ts + i] : (uint8_t)'N';
+            if (tid == 0) { sm.n_events = 0; }
+        }
+        __syncthreads();
+        for (int w = tid; w < T / 16 + 2; w += kThreads) {
+            uint32_t r2 = 0, rx = 0;
+            for (int j = 0; j < 16; ++j) {
+                const int p = w * 16 + j;
+                const int c = p < T ? nt4(sm.refc[p]) : 4;
+                if (c < 4) r2 |= (uint32_t)c << (2 * j); else rx |= 1u << (2 * j);
+            }
+            sm.ref2[w] = r2; sm.refx[w] = rx;
+        }
+
+        // ---- accumulate: reads [lo, hi) that overlap the tile, one warp per read ----
+        const int rlo = ws.tile_lo[tile], rhi = ws.tile_hi[tile];
+        for (int rb = rlo; rb < rhi; rb += kReadList) {
+            __syncthreads();
+            if (tid == 0) { sm.n_rlist = 0; sm.next_task = 0; }
+            __syncthreads();
+            for (int r = rb + tid; r < min(rhi, rb + kReadList); r += kThreads) {
+                // overlap test; a read that merely starts at te has no anchor inside the tile
+                if ((int64_t)rd.pos[r] < te && (int64_t)ws.rend[r] > ts) sm.rlist[atomicAdd(&sm.n_rlist, 1)] = r;
+            }
+            __syncthreads();
+            const int nr = sm.n_rlist;
+            for (;;) {
+                int t = 0;
+                if (lane == 0) t = atomicAdd(&sm.next_task, 1);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t >= nr) break;
+                process_read<T>(sm, rd, ws, slab, sm.rlist[t], ts, te, status);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && rhi - rlo > 65535) dev_fail(status, DEV_E_DEPTH, (int)(ts & 0x7fffffff));
+
+        // ---- prefix sums: run starts/ends -> depths (fwd | rev << 16 stays valid: depths are < 65536) ----
+        {
+            constexpr int K = T / kThreads;
+            int s0 = 0, s1 = 0, s2 = 0, s3 = 0;          // aligned fwd, aligned rev, del fwd, del rev
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int p = tid * K + j;
+                const uint32_t a = sm.ms[p], b = sm.me[p], c = sm.ds[p], d = sm.de[p];
+                s0 += (int)(a & 0xFFFF) - (int)(b & 0xFFFF); s1 += (int)(a >> 16) - (int)(b >> 16);
+                s2 += (int)(c & 0xFFFF) - (int)(d & 0xFFFF); s3 += (int)(c >> 16) - (int)(d >> 16);
+            }
+            const int i0 = warp_incl_scan(s0), i1 = warp_incl_scan(s1), i2 = warp_incl_scan(s2), i3 = warp_incl_scan(s3);
+            if (lane == 31) { sm.warp_tot[warp][0] = i0; sm.warp_tot[warp][1] = i1; sm.warp_tot[warp][2] = i2; sm.warp_tot[warp][3] = i3; }
+            __syncthreads();
+            int e0 = i0 - s0, e1 = i1 - s1, e2 = i2 - s2, e3 = i3 - s3;
+            for (int w = 0; w < warp; ++w) { e0 += sm.warp_tot[w][0]; e1 += sm.warp_tot[w][1]; e2 += sm.warp_tot[w][2]; e3 += sm.warp_tot[w][3]; }
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int p = tid * K + j;
+                const uint32_t a = sm.ms[p], b = sm.me[p], c = sm.ds[p], d = sm.de[p];
+                e0 += (int)(a & 0xFFFF) - (int)(b & 0xFFFF); e1 += (int)(a >> 16) - (int)(b >> 16);
+                e2 += (int)(c & 0xFFFF) - (int)(d & 0xFFFF); e3 += (int)(c >> 16) - (int)(d >> 16);
+                sm.ms[p] = (uint32_t)e0 | ((uint32_t)e1 << 16);
+                sm.ds[p] = (uint32_t)e2 | ((uint32_t)e3 << 16);
+            }
+        }
+        __syncthreads();
+
+        // ---- epilogue: 18 channels + gate per position, staged, then coalesced stores ----
+        for (int sb = 0; sb < tn; sb += kStageRows) {
+            const int p = sb + tid;
+            uint8_t fl = 0;
+            if (p < tn) {
+                // indel channels from the event chain: totals and the multiplicity of the most frequent identical indel
+                int tot0 = 0, tot1 = 0, tot2 = 0, tot3 = 0, mx0 = 0, mx1 = 0, mx2 = 0, mx3 = 0;
+                for (uint32_t e = sm.head[p]; e != 0xFFFFFFFFu;) {
+                    const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(slab + e));
+                    const int cls = (raw.y >> 8) & 3, len = raw.y & 0xFF;
+                    const uint64_t g = (uint64_t)raw.z | ((uint64_t)raw.w << 32);
+                    // multiplicity = this event + identical events further down the chain: the group member
+                    // nearest the head sees the whole group
+                    int mult = 1;
+                    for (uint32_t f = raw.x; f != 0xFFFFFFFFu;) {
+                        const uint4 o = __ldcg(reinterpret_cast<const uint4*>(slab + f));
+                        if ((o.y & 0x3FF) == (raw.y & 0x3FF) &&
+                            (cls >= 2 || same_insert(seqw, nmw, g, (uint64_t)o.z | ((uint64_t)o.w << 32), len))) ++mult;
+                        f = o.x;
+                    }
+                    if (cls == 0) { ++tot0; mx0 = max(mx0, mult); } else if (cls == 1) { ++tot1; mx1 = max(mx1, mult); }
+                    else if (cls == 2) { ++tot2; mx2 = max(mx2, mult); } else { ++tot3; mx3 = max(mx3, mult); }
+                    e = raw.x;
+                }
+                const int tot[4] = {tot0, tot1, tot2, tot3}, mx[4] = {mx0, mx1, mx2, mx3};
+                const uint32_t md = sm.ms[p], dd = sm.ds[p], nnv = sm.nn[p];
+                const int mf = (int)(md & 0xFFFF) - (int)(nnv & 0xFFFF), mr = (int)(md >> 16) - (int)(nnv >> 16);
+                const int df = (int)(dd & 0xFFFF), dr = (int)(dd >> 16);
+                int cf[4], cr[4];
+                { const uint32_t w0 = sm.base[0][p], w1 = sm.base[1][p], w2 = sm.base[2][p], w3 = sm.base[3][p];
+                  cf[0] = w0 & 0xFFFF; cf[1] = w0 >> 16; cf[2] = w1 & 0xFFFF; cf[3] = w1 >> 16;
+                  cr[0] = w2 & 0xFFFF; cr[1] = w2 >> 16; cr[2] = w3 & 0xFFFF; cr[3] = w3 >> 16; }
+                const int rc4 = nt4(sm.refc[p]);
+                const int chr = rc4 < 4 ? rc4 : 0;                                   // evc_base_from: non-ACGT -> 'A'
+                // merged-strand tallies in std::map key order A C D G I T (tensor_maker.cpp:124,197)
+                int oth = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) if (b != chr) oth += cf[b] + cr[b];
+                int tally[6];
+                tally[0] = chr == 0 ? (mf + mr - oth) : cf[0] + cr[0];
+                tally[1] = chr == 1 ? (mf + mr - oth) : cf[1] + cr[1];
+                tally[2] = tot[2] + tot[3];
+                tally[3] = chr == 2 ? (mf + mr - oth) : cf[2] + cr[2];
+                tally[4] = tot[0] + tot[1];
+                tally[5] = chr == 3 ? (mf + mr - oth) : cf[3] + cr[3];
+                const int depth = mf + mr + df + dr;
+                const int den = depth ? depth : 1;
+                int top = -1, topc = 0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) if (tally[k] > topc) { topc = tally[k]; top = k; }   // stable: first max wins
+                const int chr_key = chr == 0 ? 0 : chr == 1 ? 1 : chr == 2 ? 3 : 5;
+                bool pass = top >= 0 && top != chr_key;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    if (k == chr_key || tally[k] == 0) continue;
+                    const double f = 1.0 * tally[k] / den;
+                    pass = pass || (f >= ((k == 2 || k == 4) ? prm.indel_min_af : prm.snp_min_af));
+                }
+                const bool covered = (mf + mr + (int)(nnv & 0xFFFF) + (int)(nnv >> 16) + df + dr) > 0 ||
+                                     ((sm.skipcov[p >> 5] >> (p & 31)) & 1u);
+                const bool gate = covered && rc4 < 4 && pass && depth >= prm.min_coverage;       // main.cpp:196
+                fl = (uint8_t)((covered ? NSNP_F_COVERED : 0) | (gate ? NSNP_F_GATE : 0));
+                int32_t* row = sm.stage + tid * kStageStride;
+                row[0] = chr == 0 ? -mf : cf[0]; row[1] = chr == 1 ? -mf : cf[1];
+                row[2] = chr == 2 ? -mf : cf[2]; row[3] = chr == 3 ? -mf : cf[3];
+                row[4] = tot[0]; row[5] = mx[0]; row[6] = tot[2]; row[7] = mx[2]; row[8] = df;
+                row[9] = chr == 0 ? -mr : cr[0]; row[10] = chr == 1 ? -mr : cr[1];
+                row[11] = chr == 2 ? -mr : cr[2]; row[12] = chr == 3 ? -mr : cr[3];
+                row[13] = tot[1]; row[14] = mx[1]; row[15] = tot[3]; row[16] = mx[3]; row[17] = dr;
+                flags[(ts - region_start) + p] = fl;
+            }
+            __syncthreads();
+            {
+                const int rows = min(kStageRows, tn - sb);
+                const int n_int = rows * 18;                       // multiple of 2; 16-byte groups when rows is even
+                int32_t* out = counts + ((ts - region_start) + sb) * 18;
+                const int n4 = n_int >> 2;
+                for (int q = tid; q < n4; q += kThreads) {
+                    int v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const int e = q * 4 + j; const int rr = e / 18; v[j] = sm.stage[rr * kStageStride + (e - rr * 18)]; }
+                    st_stream(reinterpret_cast<int4*>(out) + q, make_int4(v[0], v[1], v[2], v[3]));
+                }
+                for (int e = (n4 << 2) + tid; e < n_int; e += kThreads) { const int rr = e / 18; out[e] = sm.stage[rr * kStageStride + (e - rr * 18)]; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+int tile_shift_for(int64_t region_len) { (void)region_len; return 10; }     // T = 1024
+
+}  // namespace
+}  // namespace nsnp
+
+using namespace nsnp;
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static constexpr int kMaxCtas = kNumSMs * 4;
+static constexpr int64_t kSlabCapMax = 32768;
+
+static void carve(void* base, int64_t n_reads, int64_t n_cigar, int64_t region_len, int tile_shift, Workspace* w, size_t* total) {
+    const int64_t n_slots = (n_cigar >> kCkShift) + n_reads + 2;
+    const int64_t n_tiles = (region_len + (1 << tile_shift) - 1) >> tile_shift;
+    int64_t cap = n_cigar < kSlabCapMax ? n_cigar : kSlabCapMax; if (cap < 64) cap = 64;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off += align_up(bytes, 256); return p; };
+    w->rend = (int32_t*)take((size_t)(n_reads + 1) * 4);
+    w->ck_ref = (int32_t*)take((size_t)n_slots * 4);
+    w->ck_q = (int32_t*)take((size_t)n_slots * 4);
+    w->tile_lo = (int32_t*)take((size_t)(n_tiles + 1) * 4);
+    w->tile_hi = (int32_t*)take((size_t)(n_tiles + 1) * 4);
+    w->counters = (int32_t*)take(64);
+    w->slabs = (Event*)take((size_t)kMaxCtas * (size_t)cap * sizeof(Event));
+    w->slab_cap = cap;
+    *total = off;
+}
+
+extern "C" {
+
+size_t nsnp_pileup_workspace_bytes(int64_t n_reads, int64_t n_cigar, int64_t region_len) {
+    Workspace w; size_t total = 0;
+    carve(nullptr, n_reads < 0 ? 0 : n_reads, n_cigar < 0 ? 0 : n_cigar, region_len < 0 ? 0 : region_len, tile_shift_for(region_len), &w, &total);
+    return total;
+}
+
+int nsnp_pileup_counts(const nsnp_reads_t* reads, const uint8_t* ref_dev, int64_t contig_len, int64_t region_start,
+                       int64_t region_len, const nsnp_params_t* params, int32_t* counts_dev, uint8_t* flags_dev,
+                       void* workspace_dev, size_t workspace_bytes, int32_t* status_dev, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!reads || !params || !ref_dev || !counts_dev || !flags_dev || !status_dev || !workspace_dev)
+        return set_error(NSNP_E_INVALID, "nsnp_pileup_counts: null argument");
+    if (region_start < 0 || region_len < 0 || region_start + region_len > contig_len)
+        return set_error(NSNP_E_INVALID, "nsnp_pileup_counts: region [%lld,+%lld) outside contig of %lld",
+                         (long long)region_start, (long long)region_len, (long long)contig_len);
+    if (reads->n_reads < 0 || (reads->n_reads > 0 && (!reads->pos || !reads->flag || !reads->mapq || !reads->cigar_off || !reads->cigar || !reads->seq_off || !reads->seq2)))
+        return set_error(NSNP_E_INVALID, "nsnp_pileup_counts: incomplete read arrays");
+    if (((uintptr_t)reads->seq2 & 3) || ((uintptr_t)reads->nmask & 3) || ((uintptr_t)counts_dev & 15))
+        return set_error(NSNP_E_INVALID, "nsnp_pileup_counts: seq2/nmask must be 4-byte and counts 16-byte aligned");
+    if (reads->n_reads > 0x7fffffff - 1) return set_error(NSNP_E_UNSUPPORTED, "more than 2^31 reads in one call");
+    if (nsnp_device_count() == 0) return set_error(NSNP_E_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (region_len == 0) return NSNP_OK;
+
+    const int tile_shift = tile_shift_for(region_len);
+    Workspace w; size_t need = 0;
+    carve(workspace_dev, reads->n_reads, reads->n_cigar, region_len, tile_shift, &w, &need);
+    if (need > workspace_bytes) return set_error(NSNP_E_WORKSPACE, "pileup workspace: need %zu bytes, have %zu", need, workspace_bytes);
+    const int n_tiles = (int)((region_len + (1 << tile_shift) - 1) >> tile_shift);
+
+    cudaMemsetAsync(w.tile_lo, 0x7f, (size_t)(n_tiles + 1) * 4, stream);
+    cudaMemsetAsync(w.tile_hi, 0, (size_t)(n_tiles + 1) * 4, stream);
+    cudaMemsetAsync(w.counters, 0, 64, stream);
+    if (reads->n_reads > 0) {
+        const int64_t warps = reads->n_reads;
+        int blocks = (int)((warps + 7) / 8); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        read_scan_kernel<<<blocks, 256, 0, stream>>>(*reads, *params, region_start, region_start + region_len, tile_shift, w);
+        if (int e = cuda_status("read_scan_kernel")) return e;
+    }
+    {
+        constexpr int T = 1024;
+        const size_t smem = sizeof(TileSmem<T>);
+        static bool attr_done = false;
+        if (!attr_done) {
+            if (cudaFuncSetAttribute(pileup_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return cuda_status("cudaFuncSetAttribute(pileup_tile_kernel)");
+            attr_done = true;
+        }
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pileup_tile_kernel<T>, kThreads, smem);
+        if (occ < 1) occ = 1; if (occ > 4) occ = 4;
+        int grid = kNumSMs * occ; if (grid > n_tiles) grid = n_tiles; if (grid > kMaxCtas) grid = kMaxCtas;
+        pileup_tile_kernel<T><<<grid, kThreads, smem, stream>>>(*reads, *params, ref_dev, region_start, region_len, n_tiles, w,
+                                                              counts_dev, flags_dev, status_dev);
+        if (int e = cuda_status("pileup_tile_kernel")) return e;
+    }
+    return NSNP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+// s2 host side: VCF record text for one batch of sites -- a native restatement of the per-site loop of
+// PileupModel/predict.py:54-194, including the behaviours that define "identical VCF" (SURVEY 8a, P13):
+//   * `gt_output[ti]` indexes the BATCH argmax array with a class index (predict.py:106,119,150,163), so the
+//     ALT of hom/het fix-up records depends on the first ten sites of the batch, and a batch with <= ti
+//     sites raises IndexError -> the record is silently dropped by the bare `except` (predict.py:193);
+//   * calculate_score (predict.py:31-34) runs in float32 under NumPy >= 2, so p == 1.0 gives log(0) ->
+//     ValueError -> record dropped;
+//   * QUAL is str(round(x, 2)) of a Python float, AF is '%f' of a float32 quotient, DP is '%d' of a float32.
+// Host code only (no kernels): this is the caller either side of the GPU path.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace {
+
+const char* const kGt[21] = {"AA", "AC", "AG", "AT", "CC", "CG", "CT", "GG", "GT", "TT", "DD",
+                             "AD", "CD", "GD", "TD", "II", "AI", "CI", "GI", "TI", "ID"};     // options.py:8-28
+const char* const kZy[3] = {"0/0", "1/1", "0/1"};                                              // options.py:30
+
+inline int base_idx(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+
+// calculate_score, predict.py:31-34.  Returns false when Python would raise (log of 0).
+bool calc_score(float p, double* out) {
+    const float a = 1.0f - p;            // (1.0 - p) + 1e-300 stays float32 under NumPy 2; 1e-300 -> 0.0f
+    const float r = a / p;
+    const double x = (double)r;
+    if (!(x > 0.0)) return false;        // math.log(0.0) / log(negative) / log(nan): ValueError
+    static const double kScale = -10.0 * (1.0 / log(10.0));     // -10 * log(e, 10) = -10 * (log(e) / log(10)), log(e) == 1.0
+    volatile double t = kScale * log(x);
+    t = t + 10.0;
+    double v = t > 0.0 ? t : 0.0;        // max(tmp, 0)
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.2f", v);          // round(tmp, 2): correctly rounded decimal, half-even on exact ties
+    *out = strtod(buf, nullptr);
+    return true;
+}
+
+// str(float) for a value that is the nearest double of a 2-decimal number
+int fmt_pyfloat(char* dst, double v) {
+    char buf[64];
+    int n = snprintf(buf, sizeof buf, "%.2f", v);
+    while (n > 0 && buf[n - 1] == '0' && buf[n - 2] != '.') --n;
+    memcpy(dst, buf, (size_t)n);
+    return n;
+}
+
+struct Out {
+    char* p; int64_t cap; int64_t n;
+    void put(const char* s, size_t len) { if (n + (int64_t)len <= cap) memcpy(p + n, s, len); n += (int64_t)len; }
+    void puts_(const char* s) { put(s, strlen(s)); }
+};
+
+void write_record(Out& o, const char* contig, long long pos, char ref, const char* alt, double q, const char* filter,
+                  const char* zy, float depth, float af, bool af_is_one)
+{
+    char line[512], qs[64];
+    const int qn = fmt_pyfloat(qs, q); qs[qn] = 0;
+    char afs[64];
+    const double afd = af_is_one ? 1.0 : (double)af;
+    if (isnan(afd)) strcpy(afs, "nan"); else if (isinf(afd)) strcpy(afs, afd > 0 ? "inf" : "-inf"); else snprintf(afs, sizeof afs, "%f", afd);
+    const int n = snprintf(line, sizeof line, "%s\t%lld\t.\t%c\t%s\t%s\t%s\t.\tGT:GQ:DP:AF\t%s:%lld:%lld:%s\n",
+                           contig, pos, ref, alt, qs, filter, zy, (long long)q, (long long)depth, afs);
+    o.put(line, (size_t)n);
+}
+
+}  // namespace
+
+extern "C" int64_t nsnp_vcf_format_batch(const char* contig, int64_t n, const int32_t* pos1, const uint8_t* refbase,
+                                         const float* gt_prob, const float* zy_prob, const float* cov8,
+                                         char* out, int64_t out_capacity)
+{
+    if (!contig || n < 0 || (n > 0 && (!pos1 || !refbase || !gt_prob || !zy_prob || !cov8))) return 0;
+    Out o{out, out ? out_capacity : 0, 0};
+    // batch-level argmax arrays (predict.py:56-57)
+    int head_gt[10];
+    const int nhead = n < 10 ? (int)n : 10;
+    auto argmax = [](const float* v, int m) { int b = 0; for (int i = 1; i < m; ++i) if (v[i] > v[b]) b = i; return b; };
+    for (int i = 0; i < nhead; ++i) head_gt[i] = argmax(gt_prob + (size_t)i * 21, 21);
+
+    for (int64_t j = 0; j < n; ++j) {
+        const float* gp = gt_prob + j * 21; const float* zp = zy_prob + j * 3;
+        const int gt = argmax(gp, 21), zyo = argmax(zp, 3);
+        if (gt >= 10) continue;                                               // predict.py:68
+        const char sref = (char)refbase[j];
+        const char* label = kGt[gt];
+        const char* zy = kZy[zyo];
+        const float* cov = cov8 + j * 8;
+        float neg = 0.f; for (int k = 0; k < 8; ++k) if (cov[k] < 0.f) neg += cov[k];
+        const float depth = -1.0f * neg;                                      // predict.py:76
+        // alt = label minus every occurrence of sref (predict.py:78,90)
+        char alt[4]; int na = 0;
+        for (int k = 0; k < 2; ++k) if (label[k] != sref) alt[na++] = label[k];
+        alt[na] = 0;
+        float support = 0.f;
+        for (int k = 0; k < na; ++k) { const int b = base_idx(alt[k]); if (b < 0) goto next_site; support += cov[b]; support += cov[b + 4]; }
+        {
+            float af = support / depth;                                       // float32 quotient (0/0 -> nan, x/0 -> inf)
+            bool af_one = false;
+            if (af > 1.0f) af_one = true;                                     // predict.py:83-84
+            double gt_q, zy_q;
+            if (!calc_score(gp[gt], &gt_q)) continue;                         // ValueError -> except: continue
+            if (!calc_score(zp[zyo], &zy_q)) continue;
+            const double qual = gt_q < zy_q ? gt_q : zy_q;
+
+            if (na == 0) {
+                if (zyo == 0) {
+                    const char a1[2] = {sref, 0};
+                    write_record(o, contig, pos1[j], sref, a1, qual, "RefCall", zy, depth, af, af_one);
+                } else if (zyo == 1) {
+                    static const int tis[4] = {0, 4, 7, 9};
+                    int max_ti = -1, max_v = -1; bool raised = false;
+                    for (int q = 0; q < 4; ++q) {
+                        const int ti = tis[q];
+                        if (kGt[ti][0] == sref) continue;
+                        if (ti >= n) { raised = true; break; }                // IndexError on the batch array
+                        if (head_gt[ti] > max_v) { max_v = head_gt[ti]; max_ti = ti; }
+                    }
+                    if (raised) continue;
+                    const char a1[2] = {kGt[max_ti][0], 0};
+                    write_record(o, contig, pos1[j], sref, a1, zy_q, "PASS", zy, depth, af, af_one);
+                } else {
+                    static const int tis[6] = {1, 2, 3, 5, 6, 8};
+                    int max_ti = -1, max_v = -1; bool raised = false;
+                    for (int q = 0; q < 6; ++q) {
+                        const int ti = tis[q];
+                        if (ti >= n) { raised = true; break; }
+                        if (head_gt[ti] > max_v) { max_v = head_gt[ti]; max_ti = ti; }
+                    }
+                    if (raised) continue;
+                    const char a1[2] = {kGt[max_ti][0] == sref ? kGt[max_ti][1] : kGt[max_ti][0], 0};
+                    write_record(o, contig, pos1[j], sref, a1, zy_q, "PASS", zy, depth, af, af_one);
+                }
+                continue;
+            }
+            char alts[8];
+            if (na == 1) { alts[0] = alt[0]; alts[1] = 0; }
+            else if (alt[0] == alt[1]) { alts[0] = alt[0]; alts[1] = 0; }     // "CC" -> "C"
+            else { alts[0] = alt[0]; alts[1] = ','; alts[2] = alt[1]; alts[3] = 0; }
+            if (strlen(alts) >= 3 && zyo != 2) zy = "1/2";                    // predict.py:140-141
+            // predict.py:143-176 (`alt == sref and zy != 0`) cannot fire: alt never contains sref
+            if (zyo == 0) {                                                   // predict.py:177-185
+                write_record(o, contig, pos1[j], sref, alts, gt_q, "PASS", zy, depth, af, af_one);
+                continue;
+            }
+            write_record(o, contig, pos1[j], sref, alts, qual, "PASS", zy, depth, af, af_one);
+        }
+    next_site:;
+    }
+    if (o.n > o.cap) return -o.n;
+    return o.n;
+}

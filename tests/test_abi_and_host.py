@@ -1,0 +1,128 @@
+"""CPU-side checks of the product library: the C-ABI shared object loads and exports every declared symbol, the
+host-only entry points (VCF formatter, synthetic generator) behave, and the GPU entry points refuse loudly
+instead of falling back when no device is present."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+from nanosnp_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = (_lib._HERE.parent / "include" / "nanosnp_b200.h").read_text()
+    declared = set(re.findall(r"\b(nsnp_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.nsnp_abi_version() == 1
+    p = _lib.default_params()
+    assert (p.snp_min_af, p.indel_min_af, p.min_coverage, p.min_mapq, p.excl_flags) == (0.12, 0.12, 6, 20, 2316)
+    assert lib.nsnp_model_blob_bytes() > 700_000
+    assert lib.nsnp_pileup_workspace_bytes(1000, 100000, 1 << 20) > 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    lib = _lib.load()
+    if lib.nsnp_device_count() > 0 and torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from nanosnp_b200.pipeline import PileupEngine
+    with pytest.raises(_lib.NsnpError) as ei:
+        PileupEngine("cuda:0")
+    assert ei.value.code == _lib.E_NO_DEVICE
+    with pytest.raises(_lib.NsnpError):
+        PileupEngine("cpu")
+    # the raw C entry points refuse as well
+    p = _lib.default_params()
+    r = _lib.Reads()
+    buf = (C.c_char * 4096)()
+    a = C.addressof(buf)
+    rc = lib.nsnp_pileup_counts(C.byref(r), a, 100, 0, 100, C.byref(p), a, a, a, 4096, a, None)
+    assert rc == _lib.E_NO_DEVICE, lib.nsnp_last_error()
+    rc = lib.nsnp_pileup_model_forward(a, a, None, 4, None, a, a, a, 1 << 30, _lib.PREC_FP32, None)
+    assert rc == _lib.E_NO_DEVICE
+
+
+def _native_vcf(contig, pos, refb, gt, zy, x, batch):
+    lib = _lib.load()
+    out = []
+    n = len(pos)
+    cov = np.ascontiguousarray(x[:, 16, [0, 1, 2, 3, 9, 10, 11, 12]].astype(np.float32))
+    for b in range(0, n, batch):
+        e = min(n, b + batch)
+        cap = (e - b) * 160 + 64
+        buf = C.create_string_buffer(cap)
+        p = np.ascontiguousarray(pos[b:e], np.int32); r = np.ascontiguousarray(refb[b:e], np.uint8)
+        g = np.ascontiguousarray(gt[b:e], np.float32); z = np.ascontiguousarray(zy[b:e], np.float32)
+        c = np.ascontiguousarray(cov[b:e])
+        m = lib.nsnp_vcf_format_batch(contig.encode(), e - b, p.ctypes.data, r.ctypes.data, g.ctypes.data, z.ctypes.data,
+                                      c.ctypes.data, C.addressof(buf), cap)
+        assert m >= 0
+        out.append(buf.raw[:m].decode())
+    return "".join(out)
+
+
+def test_native_vcf_formatter_matches_reference_python(golden, small_case):
+    from oracle.s2_restate import vcf_header
+    z = np.load(golden / "s2_small.npz")
+    hdr = vcf_header(open(golden / "s2_small.fai").read().splitlines())
+    body = _native_vcf("ctg1", small_case["site_pos"], small_case["site_refbase"], z["gt"], z["zy"], small_case["windows"], 1000)
+    assert hdr + body == (golden / "s2_small.vcf").read_text()
+    body = _native_vcf("ctg1", small_case["site_pos"][:61], small_case["site_refbase"][:61], z["gt"][:61], z["zy"][:61],
+                       small_case["windows"][:61], 7)
+    assert hdr + body == (golden / "s2_tiny_b7.vcf").read_text()
+
+
+def test_native_vcf_formatter_quirks_vs_oracle():
+    """Randomised probabilities (incl. p == 1.0, tiny batches, zero depth) against the Python restatement."""
+    from oracle.s2_restate import vcf_records
+    rng = np.random.default_rng(5)
+    for batch in (1, 3, 9, 10, 50):
+        n = 400
+        logits = rng.normal(size=(n, 21)).astype(np.float32) * 4
+        logits[:, 10:] -= 3
+        gt = np.exp(logits - logits.max(1, keepdims=True)); gt = (gt / gt.sum(1, keepdims=True)).astype(np.float32)
+        lz = rng.normal(size=(n, 3)).astype(np.float32) * 3
+        zy = np.exp(lz - lz.max(1, keepdims=True)); zy = (zy / zy.sum(1, keepdims=True)).astype(np.float32)
+        gt[::37] = 0; gt[::37, 4] = 1.0          # p == 1.0 -> calculate_score raises -> record dropped
+        x = rng.integers(0, 30, size=(n, 33, 18)).astype(np.float32)
+        refb = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)]
+        for i in range(n):
+            k = "ACGT".index(chr(refb[i]))
+            x[i, 16, k] = -x[i, 16, :4].sum(); x[i, 16, 9 + k] = -x[i, 16, 9:13].sum()
+        x[5, 16, :] = 0                           # depth 0 -> nan AF
+        pos = np.arange(100, 100 + n).astype(np.int32)
+        exp = ""
+        for b in range(0, n, batch):
+            e = min(n, b + batch)
+            exp += vcf_records(["chrZ"] * (e - b), pos[b:e].astype(np.int64), refb[b:e].astype(np.int64), x[b:e], gt[b:e], zy[b:e])
+        got = _native_vcf("chrZ", pos, refb, gt, zy, x, batch)
+        assert got == exp, batch
+
+
+def test_synth_generator_properties():
+    from nanosnp_b200.synth import SynthConfig, generate_host
+    from nanosnp_b200.reads import reference_span
+    cfg = SynthConfig(contig_len=50_000, coverage=12, nbase_rate=0.01, gap_period=20_000, gap_len=400, len_median=2000, len_min=150)
+    ref, rd = generate_host(cfg)
+    ref2, rd2 = generate_host(cfg)
+    assert np.array_equal(ref, ref2) and np.array_equal(rd.cigar, rd2.cigar) and np.array_equal(rd.seq2, rd2.seq2)
+    assert (np.diff(rd.pos) >= 0).all() and rd.n_reads > 100
+    assert (rd.seq_off % 16 == 0).all()
+    npass = 0
+    for r in range(rd.n_reads):
+        cg = rd.cigar[rd.cigar_off[r]:rd.cigar_off[r + 1]]
+        ops = "".join("MIDNSHP=X"[o] for o in (cg & 15))
+        # appendix B.4 subset: [S] M {(I|D) M}* [S]
+        assert re.fullmatch(r"S?M((I|D)M)*S?", ops), ops
+        assert rd.pos[r] + reference_span(cg) <= cfg.contig_len
+        if not (rd.flag[r] & 2316) and rd.mapq[r] >= 20:
+            npass += 1
+            # no passing read overlaps a coverage gap
+            s, e = int(rd.pos[r]), int(rd.pos[r]) + reference_span(cg)
+            assert (s % 20_000) < 19_600 and ((e - 1) % 20_000) < 19_600 and (e - s) < 20_000
+    assert npass > 0.9 * rd.n_reads * 0.9
+    assert set(np.unique(ref)) <= set(b"ACGTacgtNnR")

@@ -280,6 +280,7 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
                               size_t workspace_bytes, int precision, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return NSNP_OK;          // empty batch: nothing to launch (pointers of empty tensors may be null)
     if (!blob_dev || (!x_i32_dev == !x_f32_dev) || !gt_prob_dev || !zy_prob_dev || !workspace_dev)
         return set_error(NSNP_E_INVALID, "nsnp_pileup_model_forward: null argument (exactly one of x_i32/x_f32)");
     if (precision != NSNP_PREC_FP32) return set_error(NSNP_E_UNSUPPORTED, "precision %d not built", precision);

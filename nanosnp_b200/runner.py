@@ -1,0 +1,148 @@
+"""Runs the whole s1+s2 GPU path for one region: reads -> counts -> candidates -> windows -> probabilities.
+
+Used by bench.py (device-resident and host-buffer modes) and by the predict.py drop-in.  Buffers are
+allocated once and grown on demand; the only host synchronisation per region is the site count.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .pipeline import PileupEngine, PileupModelForward
+from .reads import FIELDS, PackedReads
+from .shard import Region
+
+COV_CHANNELS = [0, 1, 2, 3, 9, 10, 11, 12]           # predict.py:63
+
+
+@dataclass
+class RegionOutput:
+    n: int
+    pos0: torch.Tensor        # int32 [n]
+    refbase: torch.Tensor     # uint8 [n]
+    cov8: torch.Tensor        # float32 [n,8] centre counts of [A C G T a c g t]
+    gt: torch.Tensor          # float32 [n,21]
+    zy: torch.Tensor          # float32 [n,3]
+    x: Optional[torch.Tensor] = None
+
+
+class StageTimer:
+    """CUDA-event timing of the stages of one step on the launching stream (bench.py roofline numbers)."""
+    STAGES = ("h2d", "pileup", "select", "gather", "model", "d2h")
+
+    def __init__(self, enabled: bool):
+        self.enabled = enabled
+        self.pairs = {s: [] for s in self.STAGES}
+        self._open = None
+
+    def start(self, stage: str):
+        if not self.enabled:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._open = (stage, ev)
+
+    def stop(self):
+        if not self.enabled or self._open is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.pairs[self._open[0]].append((self._open[1], ev))
+        self._open = None
+
+    def totals_ms(self) -> Dict[str, float]:
+        torch.cuda.synchronize()
+        return {s: float(sum(a.elapsed_time(b) for a, b in p)) for s, p in self.pairs.items()}
+
+    def counts(self) -> Dict[str, int]:
+        return {s: len(p) for s, p in self.pairs.items()}
+
+
+class RegionRunner:
+    def __init__(self, engine: PileupEngine, model: PileupModelForward, keep_windows: bool = False):
+        self.eng = engine
+        self.model = model
+        self.device = engine.device
+        self.keep_windows = keep_windows
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self.launches = 0          # kernels of this library launched so far
+
+    def _buf(self, key: str, shape, dtype) -> torch.Tensor:
+        n = int(np.prod(shape))
+        t = self._bufs.get(key)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(int(n * 1.2) + 64, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t[:n].view(*shape)
+
+    def run_device(self, reads: PackedReads, ref: torch.Tensor, region: Region, timer: Optional[StageTimer] = None) -> RegionOutput:
+        eng = self.eng
+        rlen = region.length
+        timer = timer or StageTimer(False)
+        counts = self._buf("counts", (rlen, _lib.CHANNELS), torch.int32)
+        flags = self._buf("flags", (rlen,), torch.uint8)
+        timer.start("pileup")
+        eng.pileup_counts(reads, ref, region.start, rlen, counts=counts, flags=flags)
+        timer.stop()
+        self.launches += 2 if reads.n_reads else 1
+        cap = max(1024, region.emit_end - region.emit_start)
+        pos = self._buf("pos", (cap,), torch.int32)
+        n_dev = self._buf("n", (1,), torch.int32)
+        timer.start("select")
+        eng.select(flags, ref, region.start, region.emit_start, region.emit_end, cap, pos=pos, n_dev=n_dev)
+        timer.stop()
+        self.launches += 3
+        n = int(n_dev.item())                    # the one host sync per region
+        eng.check_status()
+        x = self._buf("x", (max(n, 1), _lib.WINDOW, _lib.CHANNELS), torch.int32)[:n]
+        refbase = self._buf("refbase", (max(n, 1),), torch.uint8)[:n]
+        gt = self._buf("gt", (max(n, 1), _lib.GT_CLASSES), torch.float32)[:n]
+        zy = self._buf("zy", (max(n, 1), _lib.ZY_CLASSES), torch.float32)[:n]
+        if n:
+            timer.start("gather")
+            eng.gather(counts, ref, region.start, pos, n_dev, n, x_i32=x, refbase=refbase)
+            timer.stop()
+            timer.start("model")
+            self.model(x, gt=gt, zy=zy)
+            timer.stop()
+            self.launches += 1 + 3 * (-(-n // 65536))
+        cov8 = x[:, 16, COV_CHANNELS].to(torch.float32) if n else torch.empty((0, 8), dtype=torch.float32, device=self.device)
+        return RegionOutput(n, pos[:n], refbase, cov8, gt, zy, x if self.keep_windows else None)
+
+    # ---- host-buffer mode: what a caller holding decoded reads in (pinned) host memory pays -------------
+    def upload(self, host_reads: PackedReads, key: str = "reads") -> PackedReads:
+        out = []
+        for f in FIELDS:
+            a = getattr(host_reads, f)
+            if a is None:
+                out.append(None)
+                continue
+            d = self._buf(f"{key}.{f}", tuple(a.shape), a.dtype)
+            d.copy_(a, non_blocking=True)
+            out.append(d)
+        return PackedReads(*out)
+
+    def run_host(self, host_reads: PackedReads, ref: torch.Tensor, region: Region, host_out: Optional[dict] = None,
+                 timer: Optional[StageTimer] = None):
+        timer = timer or StageTimer(False)
+        timer.start("h2d")
+        rd = self.upload(host_reads)
+        timer.stop()
+        out = self.run_device(rd, ref, region, timer)
+        timer.start("d2h")
+        res = {}
+        for k in ("pos0", "refbase", "cov8", "gt", "zy"):
+            t = getattr(out, k)
+            if host_out is not None and k in host_out and host_out[k].shape[0] >= out.n:
+                h = host_out[k][: out.n]
+                h.copy_(t, non_blocking=True)
+            else:
+                h = t.to("cpu", non_blocking=False)
+            res[k] = h
+        timer.stop()
+        res["n"] = out.n
+        return res

@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-kb", type=float, default=500.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "f16x3"])
     return ap.parse_args()
 
 
@@ -187,7 +187,7 @@ def main_ours(args):
 
     eng = PileupEngine(dev)
     enc, fwd = load_weights()
-    prec = _lib.PREC_FP32 if args.precision == "fp32" else _lib.PREC_BF16X3
+    prec = _lib.PREC_FP32 if args.precision == "fp32" else _lib.PREC_F16X3
     model = PileupModelForward(PileupModelWeights(enc, fwd, device=dev), precision=prec)
     runner = RegionRunner(eng, model)
 
@@ -296,11 +296,11 @@ def main_ours(args):
                 "unit": "TFLOP/s", "frac": tfs / tf_peak, "traffic": None, "ms_per_step": model_ms,
                 "share_of_step": model_ms / ms_step, "peak_source": peak_src,
                 "note": ("fp32 FFMA path (no tensor cores): algorithmic 6.22 MFLOP/site over bf16 sustained peak" if args.precision == "fp32"
-                         else "tcgen05 bf16x3 split precision: 3 MMAs per algorithmic MAC, so frac <= 1/3 by construction")}
+                         else "tcgen05 fp16 hi/lo split precision: 3 MMAs per algorithmic MAC, so frac <= 1/3 by construction")}
     line = {
         "metric": METRIC, "value": sites_all / (ms_total * 1e-3) * K, "unit": "sites/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32 counts, fp64 AF gate, " + ("fp32 model" if args.precision == "fp32" else "bf16x3 model (fp32 accumulate)"),
+        "dtype": "int32 counts, fp64 AF gate, " + ("fp32 model" if args.precision == "fp32" else "fp16 hi/lo split x3 tensor-core model (fp32 accumulate)"),
         "data": "synthetic",
         "config": {"workload": f"synthetic {args.contig_mb:g} Mb contig at {args.coverage:g}x per GPU: pileup tensor build + candidate filter + PileupModel inference",
                    "contig_mb": args.contig_mb, "coverage": args.coverage, "region_mb": args.region_mb, "regions_per_gpu": len(regions),

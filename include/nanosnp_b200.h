@@ -154,7 +154,12 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
                               int64_t n, const int32_t* n_dev, float* gt_prob_dev, float* zy_prob_dev,
                               void* workspace_dev, size_t workspace_bytes, int precision, void* stream);
 #define NSNP_PREC_FP32    0   /* fp32 FFMA everywhere (parity path) */
-#define NSNP_PREC_BF16X3  1   /* tcgen05 bf16 split-precision tensor-core path */
+#define NSNP_PREC_F16X3   1   /* tcgen05 tensor-core path: fp16 hi/lo split operands (3 MMAs per product), fp32 accumulate */
+
+/* debug aid for the tensor-core path: raw gate pre-activations [m][256] (TMEM column order) of the FIRST step of one
+ * (layer, direction); cg = 1 or 2 CTAs per MMA.  Used by the GPU tests to validate operand layouts. */
+int nsnp_debug_lstm_tc_gates(const void* blob_dev, const int32_t* x_i32_dev, int layer, int dir, int cg, const void* h0_dev,
+                             float* gates_out_dev, int64_t m, void* stream);
 
 /* ---- status / utilities ----------------------------------------------------------------------- */
 /* copies status_dev[0..3] to the host (synchronises the stream) and maps it to an NSNP_E_* code */

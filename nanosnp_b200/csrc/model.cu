@@ -12,33 +12,10 @@
 //                        lanes own hidden-unit pairs, warps own site groups, cell state in registers.
 //   lstm_dir_kernel<L1>  one CTA = 32 sites x one direction, 197 KB of weights resident.
 //   tail_kernel          proj + dense/tanh + heads + softmax on the t=16 state.
-#include "common.cuh"
+#include "model_common.cuh"
 
 namespace nsnp {
 namespace {
-
-constexpr int kH = 64;               // hidden size
-constexpr int kG = 256;              // 4 gates x 64
-constexpr int kT = NSNP_WINDOW;      // 33
-constexpr int kF = NSNP_CHANNELS;    // 18
-constexpr int kMid = NSNP_FLANK;     // 16
-constexpr int kKP0 = 84;             // [x 18 | pad 2 | h 64]
-constexpr int kIn0 = 20;
-constexpr int kKP1 = 192;            // [l0 fwd 64 | l0 rev 64 | h 64]
-constexpr int kIn1 = 128;
-
-// blob layout (floats)
-constexpr size_t kOffW0 = 0;                                        // [2][kKP0][256]
-constexpr size_t kOffB0 = kOffW0 + 2 * (size_t)kKP0 * kG;           // [2][256]
-constexpr size_t kOffW1 = kOffB0 + 2 * kG;                          // [2][kKP1][256]
-constexpr size_t kOffB1 = kOffW1 + 2 * (size_t)kKP1 * kG;           // [2][256]
-constexpr size_t kOffProjW = kOffB1 + 2 * kG;                       // [128 k][128]
-constexpr size_t kOffProjB = kOffProjW + 128 * 128;
-constexpr size_t kOffDenseW = kOffProjB + 128;                      // [128 k][256]
-constexpr size_t kOffDenseB = kOffDenseW + 128 * 256;
-constexpr size_t kOffHeadW = kOffDenseB + 256;                      // [256 k][24]
-constexpr size_t kOffHeadB = kOffHeadW + 256 * 24;
-constexpr size_t kBlobFloats = kOffHeadB + 24 + 8;
 
 // column of gate row (gate g, unit u) in the shared-memory weight tile: two lane-contiguous halves so that
 // every LDS.128 of a warp is conflict free.  half = g>>1, lane = u>>1.
@@ -233,7 +210,7 @@ using namespace nsnp;
 
 extern "C" {
 
-size_t nsnp_model_blob_bytes(void) { return kBlobFloats * sizeof(float); }
+size_t nsnp_model_blob_bytes(void) { return kBlobBytes; }
 
 int nsnp_model_pack_weights(const nsnp_model_weights_t* w, void* host_blob, size_t blob_bytes) {
     if (!w || !host_blob) return set_error(NSNP_E_INVALID, "nsnp_model_pack_weights: null argument");
@@ -267,7 +244,7 @@ int nsnp_model_pack_weights(const nsnp_model_weights_t* w, void* host_blob, size
     for (int o = 0; o < 256; ++o) { for (int k = 0; k < 128; ++k) b[kOffDenseW + k * 256 + o] = w->dense_w[o * 128 + k]; b[kOffDenseB + o] = w->dense_b[o]; }
     for (int o = 0; o < 21; ++o) { for (int k = 0; k < 256; ++k) b[kOffHeadW + k * 24 + o] = w->gt_w[o * 256 + k]; b[kOffHeadB + o] = w->gt_b[o]; }
     for (int o = 0; o < 3; ++o) { for (int k = 0; k < 256; ++k) b[kOffHeadW + k * 24 + 21 + o] = w->zy_w[o * 256 + k]; b[kOffHeadB + 21 + o] = w->zy_b[o]; }
-    return NSNP_OK;
+    return pack_tc_weights(w, (unsigned char*)host_blob);
 }
 
 size_t nsnp_model_workspace_bytes(int64_t n_sites) {
@@ -283,7 +260,7 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
     if (n == 0) return NSNP_OK;          // empty batch: nothing to launch (pointers of empty tensors may be null)
     if (!blob_dev || (!x_i32_dev == !x_f32_dev) || !gt_prob_dev || !zy_prob_dev || !workspace_dev)
         return set_error(NSNP_E_INVALID, "nsnp_pileup_model_forward: null argument (exactly one of x_i32/x_f32)");
-    if (precision != NSNP_PREC_FP32) return set_error(NSNP_E_UNSUPPORTED, "precision %d not built", precision);
+    if (precision != NSNP_PREC_FP32 && precision != NSNP_PREC_F16X3) return set_error(NSNP_E_UNSUPPORTED, "unknown precision %d", precision);
     if (n < 0) return set_error(NSNP_E_INVALID, "negative n");
     if (workspace_bytes < nsnp_model_workspace_bytes(n)) return set_error(NSNP_E_WORKSPACE, "model workspace too small");
     if (nsnp_device_count() == 0) return set_error(NSNP_E_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
@@ -308,8 +285,12 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
         const int32_t* xi = x_i32_dev ? x_i32_dev + off * kT * kF : nullptr;
         const float* xf = x_f32_dev ? x_f32_dev + off * kT * kF : nullptr;
         dim3 g0((unsigned)((m + Cfg<0>::S - 1) / Cfg<0>::S), 2), g1((unsigned)((m + Cfg<1>::S - 1) / Cfg<1>::S), 2);
-        lstm_dir_kernel<0><<<g0, 256, smem0, stream>>>(blob, xi, xf, nullptr, h0, m, nd);
-        lstm_dir_kernel<1><<<g1, 256, smem1, stream>>>(blob, nullptr, nullptr, h0, h16, m, nd);
+        if (precision == NSNP_PREC_F16X3) {
+            if (int e = launch_lstm_tc(blob_dev, xi, xf, h0, h16, m, stream)) return e;
+        } else {
+            lstm_dir_kernel<0><<<g0, 256, smem0, stream>>>(blob, xi, xf, nullptr, h0, m, nd);
+            lstm_dir_kernel<1><<<g1, 256, smem1, stream>>>(blob, nullptr, nullptr, h0, h16, m, nd);
+        }
         tail_kernel<<<(unsigned)((m + kTailS - 1) / kTailS), 256, 0, stream>>>(blob, h16, m, nd, gt_prob_dev + off * 21, zy_prob_dev + off * 3);
         if (int e = cuda_status("pileup model kernels")) return e;
     }

@@ -1,0 +1,415 @@
+// s2 on the 5th-generation tensor cores: the LSTM gate contractions of PileupModel (model.py:18-25,34-35)
+// as tcgen05.mma with TMEM accumulators, hand-written for sm_100a.
+//
+// One CTA = 128 candidate sites x one direction of one layer; per time step
+//     gates[128 x 256] = [in_t | 1 | h_{t-1}] [128 x K]  .  W^T [K x 256]        (K = 96 layer 0, 208 layer 1)
+// runs as K/16 x 3 tcgen05.mma (M=128 or 256, N=256, K=16, kind::f16, fp32 accumulate in 256 TMEM columns).
+//
+// Precision: fp32-grade results from fp16 tensor-core inputs by hi/lo operand splitting,
+//     a.w  ~=  a_hi.w_hi + a_hi.w_lo + a_lo.w_hi        (dropped term a_lo.w_lo ~ 2^-22 relative)
+// implemented as three K-passes into the same accumulator.  Counts (layer-0 inputs, integers that reach
+// hundreds) use a pre-scaled low part -- (x_hi 2^-10).(w_lo 2^10) -- so the low weight halves stay in the
+// normal fp16 range.  Biases ride in the GEMM as a constant-1 input column.
+//
+// Operands sit in shared memory in the UMMA canonical K-major / no-swizzle layout: 8x(16-byte) core
+// matrices, [k/8][row][k%8]; a thread owns one site row, so it writes whole 16-byte core-matrix rows
+// (conflict free) and the next step's A operand is produced directly by the epilogue.
+//
+// Epilogue (8 warps = 2 per TMEM lane quadrant): tcgen05.ld 32 columns = (i,f,g,o) of 8 hidden units,
+// cell update with one reciprocal per (c', h) pair (5 ex2 + 2 rcp on the MUFU pipe), h -> fp16 hi/lo ->
+// st.shared (next step's operand) and -> global for layer 1.
+//
+// CG = 2 pairs two CTAs (cta_group::2): M = 256, each CTA holds half of W (N/2 rows) -- that is what makes the
+// layer-1 weights (2 x 104 KB) fit; the leader CTA issues the MMAs, tcgen05.commit multicasts completion.
+#include <cuda_fp16.h>
+#include "model_common.cuh"
+
+namespace nsnp {
+namespace {
+
+constexpr int kRows = 128;             // sites per CTA = TMEM lanes
+constexpr int kTcThreads = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ---- raw PTX -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+
+template <int CG> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    if (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <int CG> __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (CG == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int CG> __device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    if (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   bits [0,14) start>>4, [16,30) leading-dim byte offset>>4 (between the two 16-byte K chunks of one MMA),
+//   [32,46) stride byte offset>>4 (between 8-row groups), [46,48) version = 1, [61,64) layout = 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+
+__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); }
+
+struct HiLo8 { uint4 hi, lo; };
+// 8 floats -> 8 fp16 "hi" + 8 fp16 "lo" (v - float(hi)); scale_hi multiplies the hi copy (exact power of two)
+__device__ __forceinline__ HiLo8 split8(const float (&v)[8]) {
+    __half h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h[i] = __float2half_rn(v[i]); l[i] = __float2half_rn(v[i] - __half2float(h[i])); }
+    HiLo8 o;
+    o.hi = make_uint4(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]), pack_half2(h[4], h[5]), pack_half2(h[6], h[7]));
+    o.lo = make_uint4(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]), pack_half2(l[4], l[5]), pack_half2(l[6], l[7]));
+    return o;
+}
+
+template <int LAYER> struct TcCfg;
+template <> struct TcCfg<0> { static constexpr int K = kTcK0, IN = kTcIn0, STEPS = 33; };
+template <> struct TcCfg<1> { static constexpr int K = kTcK1, IN = kTcIn1, STEPS = 17; };
+
+template <int LAYER, int CG> struct TcSmem {
+    static constexpr int K = TcCfg<LAYER>::K;
+    static constexpr int RB = 256 / CG;                        // weight rows held by this CTA
+    static constexpr size_t b_bytes = (size_t)K * RB * 2;      // one of hi / lo
+    static constexpr size_t a_bytes = (size_t)K * kRows * 2;
+    static constexpr size_t sc_bytes = LAYER == 0 ? (size_t)kTcIn0 * kRows * 2 : 0;
+    static constexpr size_t off_bhi = 0, off_blo = b_bytes, off_ahi = 2 * b_bytes, off_alo = off_ahi + a_bytes,
+                            off_asc = off_alo + a_bytes, off_bar = off_asc + sc_bytes, total = off_bar + 64;
+};
+
+// DEBUG: dump raw accumulators of the first step and return
+template <int LAYER, int CG, bool DEBUG>
+__global__ void __launch_bounds__(kTcThreads, 1)
+lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict__ xi, const float* __restrict__ xf,
+               const __half* __restrict__ h0_in, __half* __restrict__ h0_out, float* __restrict__ h16, float* __restrict__ dbg,
+               int64_t n, int dir_override)
+{
+    using C = TcCfg<LAYER>;
+    using S = TcSmem<LAYER, CG>;
+    constexpr int K = C::K, IN = C::IN, RB = S::RB;
+    constexpr int KB = K / 16;                                   // MMA k-blocks per pass
+    constexpr uint32_t LBO_A = kRows * 16, LBO_B = RB * 16, SBO = 128;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sBhi = smem + S::off_bhi; unsigned char* sBlo = smem + S::off_blo;
+    unsigned char* sAhi = smem + S::off_ahi; unsigned char* sAlo = smem + S::off_alo; unsigned char* sAsc = smem + S::off_asc;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::off_bar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_bar + 16);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;                            // site row = TMEM lane
+    const int dir = DEBUG ? dir_override : (int)blockIdx.y;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int64_t site0 = (int64_t)blockIdx.x * kRows;
+    int64_t site = site0 + row;
+    const bool live = site < n;
+    if (!live) site = n - 1;                                     // clamp loads, skip stores
+
+    // ---- one-time setup ----
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<CG>(tmem_slot, 256);
+    {   // this CTA's weight rows: global [K/8][256][8] halfs -> shared [K/8][RB][8]
+        const uint4* ghi = reinterpret_cast<const uint4*>(blob + tc_off(LAYER, dir, 0));
+        const uint4* glo = reinterpret_cast<const uint4*>(blob + tc_off(LAYER, dir, 1));
+        uint4* dhi = reinterpret_cast<uint4*>(sBhi); uint4* dlo = reinterpret_cast<uint4*>(sBlo);
+        for (int i = tid; i < (K / 8) * RB; i += kTcThreads) {
+            const int ch = i / RB, r = i - ch * RB;
+            const int g = ch * 256 + (int)cta_rank * RB + r;
+            dhi[i] = __ldg(ghi + g); dlo[i] = __ldg(glo + g);
+        }
+        uint4* a = reinterpret_cast<uint4*>(sAhi);
+        const int n16 = (int)((2 * S::a_bytes + S::sc_bytes) / 16);
+        for (int i = tid; i < n16; i += kTcThreads) a[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    // constant chunk holding the bias column (1.0) -- layer 0: chunk 2 is rewritten every step with x16, x17
+    if (LAYER == 1 && half == 0) {
+        reinterpret_cast<uint4*>(sAhi + (size_t)(kIn1 / 8) * LBO_A)[row] = make_uint4(0x3C00u, 0, 0, 0);      // [1.0, 0 ...]
+    }
+
+    float c[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[j][u] = 0.f;
+
+    // stage the input part of A for time index t
+    auto stage_input = [&](int t) {
+        if (LAYER == 0) {
+            const int64_t g = (site * kT + t) * kF;
+            if (half == 0) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        if (xi) { const int2 p = __ldg(reinterpret_cast<const int2*>(xi + g + ch * 8 + j)); v[j] = (float)p.x; v[j + 1] = (float)p.y; }
+                        else { const float2 p = __ldg(reinterpret_cast<const float2*>(xf + g + ch * 8 + j)); v[j] = p.x; v[j + 1] = p.y; }
+                    }
+                    const HiLo8 s = split8(v);
+                    float w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[j] = __half2float(__float2half_rn(v[j])) * (1.0f / kTcLoScale);
+                    const HiLo8 sc = split8(w);                   // exact: hi copy scaled by a power of two
+                    reinterpret_cast<uint4*>(sAhi + ch * LBO_A)[row] = s.hi;
+                    reinterpret_cast<uint4*>(sAlo + ch * LBO_A)[row] = s.lo;
+                    reinterpret_cast<uint4*>(sAsc + ch * LBO_A)[row] = sc.hi;
+                }
+            } else {
+                float v[8] = {0.f, 0.f, 1.0f, 0.f, 0.f, 0.f, 0.f, 0.f};       // x16, x17, bias column
+                if (xi) { const int2 p = __ldg(reinterpret_cast<const int2*>(xi + g + 16)); v[0] = (float)p.x; v[1] = (float)p.y; }
+                else { const float2 p = __ldg(reinterpret_cast<const float2*>(xf + g + 16)); v[0] = p.x; v[1] = p.y; }
+                const HiLo8 s = split8(v);
+                float w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = __half2float(__float2half_rn(v[j])) * (1.0f / kTcLoScale);
+                const HiLo8 sc = split8(w);
+                reinterpret_cast<uint4*>(sAhi + 2 * LBO_A)[row] = s.hi;
+                reinterpret_cast<uint4*>(sAlo + 2 * LBO_A)[row] = s.lo;
+                reinterpret_cast<uint4*>(sAsc + 2 * LBO_A)[row] = sc.hi;
+            }
+        } else {
+            // layer-1 input = layer-0 output of time t, already split: fp16 [site][33][hi|lo][128]
+            const uint4* ghi = reinterpret_cast<const uint4*>(h0_in + ((site * kT + t) * 2 + 0) * 128);
+            const uint4* glo = reinterpret_cast<const uint4*>(h0_in + ((site * kT + t) * 2 + 1) * 128);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int ch = half * 8 + q;
+                reinterpret_cast<uint4*>(sAhi + ch * LBO_A)[row] = __ldg(ghi + ch);
+                reinterpret_cast<uint4*>(sAlo + ch * LBO_A)[row] = __ldg(glo + ch);
+            }
+        }
+    };
+    stage_input(dir == 0 ? 0 : kT - 1);
+
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), a_sc = smem_u32(sAsc), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
+    constexpr uint32_t idesc = make_idesc(128 * CG, 256);
+    uint32_t phase = 0;
+
+    for (int step = 0; step < C::STEPS; ++step) {
+        const int t = dir == 0 ? step : (kT - 1 - step);
+        // ---- operands written by the generic proxy -> visible to the tensor core; TMEM reads of the last step retired ----
+        fence_async_smem();
+        tc_fence_before();
+        if (CG == 2) cluster_sync_all(); else __syncthreads();
+        if (cta_rank == 0 && tid == 0) {
+            tc_fence_after();
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll 1
+                for (int kb = 0; kb < KB; ++kb) {
+                    // pass 0: a_hi.w_hi   pass 1: a_hi.w_lo (layer-0 counts: scaled copy)   pass 2: a_lo.w_hi
+                    uint32_t aa = pass == 2 ? a_lo : a_hi;
+                    if (LAYER == 0 && pass == 1 && kb < kTcIn0 / 16) aa = a_sc;
+                    const uint32_t bb = pass == 1 ? b_lo : b_hi;
+                    umma_f16<CG>(tmem_base, make_desc(aa + kb * 2 * LBO_A, LBO_A, SBO), make_desc(bb + kb * 2 * LBO_B, LBO_B, SBO), idesc, acc);
+                    acc = 1;
+                }
+            }
+            umma_commit<CG>(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+
+        if (DEBUG) {
+#pragma unroll 1
+            for (int jb = half * 4; jb < half * 4 + 4; ++jb) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + jb * 32, v);
+                if (live) for (int i = 0; i < 32; ++i) dbg[(site0 + row) * 256 + jb * 32 + i] = v[i];
+            }
+            break;
+        }
+
+        // ---- epilogue: 4 blocks of 8 hidden units per thread ----
+#pragma unroll
+        for (int jl = 0; jl < 4; ++jl) {
+            const int jb = half * 4 + jl;
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + jb * 32, v);
+            float hv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float gi = fminf(fmaxf(v[u], -25.f), 25.f), gf = fminf(fmaxf(v[8 + u], -25.f), 25.f);
+                const float gg = fminf(fmaxf(v[16 + u], -12.5f), 12.5f), go = fminf(fmaxf(v[24 + u], -25.f), 25.f);
+                const float ei = ex2_approx(-kLog2e * gi), ef = ex2_approx(-kLog2e * gf), eg = ex2_approx(-2.f * kLog2e * gg);
+                const float pi = 1.f + ei, pf = 1.f + ef, pg = 1.f + eg;
+                // c' = sigmoid(f) c + sigmoid(i) tanh(g) over one common denominator
+                const float pig = pi * pg;
+                const float num = fmaf(c[jl][u], pig, (1.f - eg) * pf);
+                const float cn = num * rcp_approx(pf * pig);
+                c[jl][u] = cn;
+                const float cc = fminf(fmaxf(cn, -12.5f), 12.5f);
+                const float ec = ex2_approx(-2.f * kLog2e * cc), eo = ex2_approx(-kLog2e * go);
+                hv[u] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));        // sigmoid(o) tanh(c')
+            }
+            const HiLo8 s = split8(hv);
+            reinterpret_cast<uint4*>(sAhi + (IN / 8 + jb) * LBO_A)[row] = s.hi;
+            reinterpret_cast<uint4*>(sAlo + (IN / 8 + jb) * LBO_A)[row] = s.lo;
+            if (live) {
+                if (LAYER == 0) {
+                    __half* o = h0_out + ((site * kT + t) * 2) * 128 + dir * kH + jb * 8;
+                    *reinterpret_cast<uint4*>(o) = s.hi;
+                    *reinterpret_cast<uint4*>(o + 128) = s.lo;
+                } else if (step == C::STEPS - 1) {
+                    float4* o = reinterpret_cast<float4*>(h16 + site * 128 + dir * kH + jb * 8);
+                    o[0] = make_float4(hv[0], hv[1], hv[2], hv[3]); o[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                }
+            }
+        }
+        if (step + 1 < C::STEPS) stage_input(dir == 0 ? step + 1 : kT - 2 - step);
+    }
+
+    // ---- teardown: nobody may still be reading TMEM / the peer's shared memory ----
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 0) tmem_dealloc<CG>(tmem_base, 256);
+}
+
+template <int LAYER, int CG, bool DEBUG>
+int launch_one(const void* blob, const int32_t* xi, const float* xf, const void* h0_in, void* h0_out, float* h16, float* dbg,
+               int64_t m, int dir_override, cudaStream_t stream)
+{
+    using S = TcSmem<LAYER, CG>;
+    auto kern = lstm_tc_kernel<LAYER, CG, DEBUG>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total) != cudaSuccess) return cuda_status("cudaFuncSetAttribute(lstm_tc_kernel)");
+        attr_done = true;
+    }
+    unsigned gx = (unsigned)((m + kRows - 1) / kRows);
+    if (CG == 2 && (gx & 1)) ++gx;                               // whole clusters; the padding CTA works on clamped rows
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, DEBUG ? 1 : 2, 1);
+    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.dynamicSmemBytes = S::total;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)blob, xi, xf, (const __half*)h0_in, (__half*)h0_out, h16, dbg, m, dir_override);
+    if (e != cudaSuccess) return set_error(NSNP_E_CUDA, "lstm_tc_kernel<%d,%d>: %s", LAYER, CG, cudaGetErrorString(e));
+    return NSNP_OK;
+}
+
+}  // namespace
+
+int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, cudaStream_t stream) {
+    if (int e = launch_one<0, 1, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e;
+    return launch_one<1, 2, false>(blob, nullptr, nullptr, h0, nullptr, h16, nullptr, m, 0, stream);
+}
+
+int debug_tc_gates(const void* blob, const int32_t* xi, int layer, int dir, int cg, const void* h0, float* gates_out, int64_t m, cudaStream_t stream) {
+    if (layer == 0 && cg == 1) return launch_one<0, 1, true>(blob, xi, nullptr, nullptr, nullptr, nullptr, gates_out, m, dir, stream);
+    if (layer == 0 && cg == 2) return launch_one<0, 2, true>(blob, xi, nullptr, nullptr, nullptr, nullptr, gates_out, m, dir, stream);
+    if (layer == 1 && cg == 2) return launch_one<1, 2, true>(blob, nullptr, nullptr, h0, nullptr, nullptr, gates_out, m, dir, stream);
+    return set_error(NSNP_E_UNSUPPORTED, "debug_tc_gates: layer %d with cta_group %d is not built", layer, cg);
+}
+
+// host: fp16 hi/lo split weights in the [k/8][n][k%8] operand layout
+int pack_tc_weights(const nsnp_model_weights_t* w, unsigned char* blob) {
+    for (int layer = 0; layer < 2; ++layer) {
+        const int K = layer == 0 ? kTcK0 : kTcK1, IN = layer == 0 ? kTcIn0 : kTcIn1, nin = layer == 0 ? kF : 128;
+        for (int d = 0; d < 2; ++d) {
+            __half* hi = reinterpret_cast<__half*>(blob + tc_off(layer, d, 0));
+            __half* lo = reinterpret_cast<__half*>(blob + tc_off(layer, d, 1));
+            const float *wih = w->w_ih[layer][d], *whh = w->w_hh[layer][d], *bi = w->b_ih[layer][d], *bh = w->b_hh[layer][d];
+            for (int n = 0; n < 256; ++n) {
+                const int jb = n >> 5, gate = (n >> 3) & 3, u = n & 7;
+                const int rowi = gate * kH + jb * 8 + u;                 // PyTorch gate-major row
+                for (int k = 0; k < K; ++k) {
+                    float v = 0.f;
+                    if (k < nin) v = wih[rowi * nin + k];
+                    else if (k == nin) v = bi[rowi] + bh[rowi];
+                    else if (k >= IN) v = whh[rowi * kH + (k - IN)];
+                    const float scale = (layer == 0 && k < IN) ? kTcLoScale : 1.0f;
+                    const __half h = __float2half_rn(v);
+                    const __half l = __float2half_rn((v - __half2float(h)) * scale);
+                    const size_t idx = ((size_t)(k >> 3) * 256 + n) * 8 + (k & 7);
+                    hi[idx] = h; lo[idx] = l;
+                }
+            }
+        }
+    }
+    return NSNP_OK;
+}
+
+}  // namespace nsnp
+
+extern "C" int nsnp_debug_lstm_tc_gates(const void* blob_dev, const int32_t* x_i32_dev, int layer, int dir, int cg, const void* h0_dev,
+                                        float* gates_out_dev, int64_t m, void* stream)
+{
+    if (!blob_dev || !gates_out_dev || m <= 0 || dir < 0 || dir > 1) return nsnp::set_error(NSNP_E_INVALID, "nsnp_debug_lstm_tc_gates: bad argument");
+    if (nsnp_device_count() == 0) return nsnp::set_error(NSNP_E_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    return nsnp::debug_tc_gates(blob_dev, x_i32_dev, layer, dir, cg, h0_dev, gates_out_dev, m, (cudaStream_t)stream);
+}

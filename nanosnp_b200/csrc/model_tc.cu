@@ -28,7 +28,6 @@ namespace nsnp {
 namespace {
 
 constexpr int kRows = 128;             // sites per CTA = TMEM lanes
-constexpr int kTcThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // ---- raw PTX -----------------------------------------------------------------------------------
@@ -112,19 +111,33 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at 17, M>>4 at 24
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
 
-__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); }
-
 struct HiLo8 { uint4 hi, lo; };
-// 8 floats -> 8 fp16 "hi" + 8 fp16 "lo" (v - float(hi)); scale_hi multiplies the hi copy (exact power of two)
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// 8 floats -> 8 fp16 "hi" + 8 fp16 "lo" (v - float(hi)), two values per cvt.rn.f16x2.f32
 __device__ __forceinline__ HiLo8 split8(const float (&v)[8]) {
-    __half h[8], l[8];
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { h[i] = __float2half_rn(v[i]); l[i] = __float2half_rn(v[i] - __half2float(h[i])); }
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 f = __half22float2(hh);
+        h[i] = h2_bits(hh);
+        l[i] = h2_bits(__floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y));
+    }
     HiLo8 o;
-    o.hi = make_uint4(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]), pack_half2(h[4], h[5]), pack_half2(h[6], h[7]));
-    o.lo = make_uint4(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]), pack_half2(l[4], l[5]), pack_half2(l[6], l[7]));
+    o.hi = make_uint4(h[0], h[1], h[2], h[3]);
+    o.lo = make_uint4(l[0], l[1], l[2], l[3]);
     return o;
 }
+// hi copy of integer counts scaled by 2^-10 (exact: counts are integers, results stay normal or zero)
+__device__ __forceinline__ uint4 scale_hi(const uint4& hi) {
+    const __half2 k = __float2half2_rn(1.0f / kTcLoScale);
+    auto m = [&](uint32_t x) { __half2 t = *reinterpret_cast<__half2*>(&x); return h2_bits(__hmul2(t, k)); };
+    return make_uint4(m(hi.x), m(hi.y), m(hi.z), m(hi.w));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
 template <int LAYER> struct TcCfg;
 template <> struct TcCfg<0> { static constexpr int K = kTcK0, IN = kTcIn0, STEPS = 33; };
@@ -140,9 +153,10 @@ template <int LAYER, int CG> struct TcSmem {
                             off_asc = off_alo + a_bytes, off_bar = off_asc + sc_bytes, total = off_bar + 64;
 };
 
-// DEBUG: dump raw accumulators of the first step and return
-template <int LAYER, int CG, bool DEBUG>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// NWQ warps share each TMEM lane quadrant (each thread = one site row x 64/NWQ hidden units).
+// DEBUG: dump the raw accumulators of the first step and return.
+template <int LAYER, int CG, int NWQ, bool DEBUG>
+__global__ void __launch_bounds__(128 * NWQ, (LAYER == 0 && CG == 2 && NWQ == 2) ? 2 : 1)
 lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict__ xi, const float* __restrict__ xf,
                const __half* __restrict__ h0_in, __half* __restrict__ h0_out, float* __restrict__ h16, float* __restrict__ dbg,
                int64_t n, int dir_override)
@@ -151,6 +165,8 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     using S = TcSmem<LAYER, CG>;
     constexpr int K = C::K, IN = C::IN, RB = S::RB;
     constexpr int KB = K / 16;                                   // MMA k-blocks per pass
+    constexpr int kThreads = 128 * NWQ;
+    constexpr int UB = 8 / NWQ;                                  // blocks of 8 hidden units per thread
     constexpr uint32_t LBO_A = kRows * 16, LBO_B = RB * 16, SBO = 128;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sBhi = smem + S::off_bhi; unsigned char* sBlo = smem + S::off_blo;
@@ -159,7 +175,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_bar + 16);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, sub = warp >> 2;
     const int row = quad * 32 + lane;                            // site row = TMEM lane
     const int dir = DEBUG ? dir_override : (int)blockIdx.y;
     const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -175,75 +191,80 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
         const uint4* ghi = reinterpret_cast<const uint4*>(blob + tc_off(LAYER, dir, 0));
         const uint4* glo = reinterpret_cast<const uint4*>(blob + tc_off(LAYER, dir, 1));
         uint4* dhi = reinterpret_cast<uint4*>(sBhi); uint4* dlo = reinterpret_cast<uint4*>(sBlo);
-        for (int i = tid; i < (K / 8) * RB; i += kTcThreads) {
+        for (int i = tid; i < (K / 8) * RB; i += kThreads) {
             const int ch = i / RB, r = i - ch * RB;
             const int g = ch * 256 + (int)cta_rank * RB + r;
             dhi[i] = __ldg(ghi + g); dlo[i] = __ldg(glo + g);
         }
         uint4* a = reinterpret_cast<uint4*>(sAhi);
         const int n16 = (int)((2 * S::a_bytes + S::sc_bytes) / 16);
-        for (int i = tid; i < n16; i += kTcThreads) a[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < n16; i += kThreads) a[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     // constant chunk holding the bias column (1.0) -- layer 0: chunk 2 is rewritten every step with x16, x17
-    if (LAYER == 1 && half == 0) {
-        reinterpret_cast<uint4*>(sAhi + (size_t)(kIn1 / 8) * LBO_A)[row] = make_uint4(0x3C00u, 0, 0, 0);      // [1.0, 0 ...]
-    }
+    if (LAYER == 1 && sub == 0) reinterpret_cast<uint4*>(sAhi + (size_t)(kIn1 / 8) * LBO_A)[row] = make_uint4(0x3C00u, 0, 0, 0);
 
-    float c[4][8];
+    float c[UB][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < UB; ++j)
 #pragma unroll
         for (int u = 0; u < 8; ++u) c[j][u] = 0.f;
 
-    // stage the input part of A for time index t
-    auto stage_input = [&](int t) {
-        if (LAYER == 0) {
-            const int64_t g = (site * kT + t) * kF;
-            if (half == 0) {
+    // ---- input staging.  Layer 0: counts row -> registers (prefetch) -> fp16 hi / lo / scaled-hi chunks.
+    //      Layer 1: layer-0 output is already fp16 hi|lo in global memory -> cp.async straight into the operand. ----
+    // layer 0 work split: sub 0 converts x[0..15] (chunks 0,1); the last sub converts x16, x17 + the bias column (chunk 2)
+    float xr[16];
+    auto load_x = [&](int t) {
+        if (LAYER != 0) return;
+        const int64_t g = (site * kT + t) * kF;
+        if (sub == 0) {
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j += 2) {
-                        if (xi) { const int2 p = __ldg(reinterpret_cast<const int2*>(xi + g + ch * 8 + j)); v[j] = (float)p.x; v[j + 1] = (float)p.y; }
-                        else { const float2 p = __ldg(reinterpret_cast<const float2*>(xf + g + ch * 8 + j)); v[j] = p.x; v[j + 1] = p.y; }
-                    }
-                    const HiLo8 s = split8(v);
-                    float w[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) w[j] = __half2float(__float2half_rn(v[j])) * (1.0f / kTcLoScale);
-                    const HiLo8 sc = split8(w);                   // exact: hi copy scaled by a power of two
-                    reinterpret_cast<uint4*>(sAhi + ch * LBO_A)[row] = s.hi;
-                    reinterpret_cast<uint4*>(sAlo + ch * LBO_A)[row] = s.lo;
-                    reinterpret_cast<uint4*>(sAsc + ch * LBO_A)[row] = sc.hi;
-                }
-            } else {
-                float v[8] = {0.f, 0.f, 1.0f, 0.f, 0.f, 0.f, 0.f, 0.f};       // x16, x17, bias column
-                if (xi) { const int2 p = __ldg(reinterpret_cast<const int2*>(xi + g + 16)); v[0] = (float)p.x; v[1] = (float)p.y; }
-                else { const float2 p = __ldg(reinterpret_cast<const float2*>(xf + g + 16)); v[0] = p.x; v[1] = p.y; }
-                const HiLo8 s = split8(v);
-                float w[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = __half2float(__float2half_rn(v[j])) * (1.0f / kTcLoScale);
-                const HiLo8 sc = split8(w);
-                reinterpret_cast<uint4*>(sAhi + 2 * LBO_A)[row] = s.hi;
-                reinterpret_cast<uint4*>(sAlo + 2 * LBO_A)[row] = s.lo;
-                reinterpret_cast<uint4*>(sAsc + 2 * LBO_A)[row] = sc.hi;
+            for (int j = 0; j < 16; j += 2) {
+                if (xi) { const int2 p = __ldg(reinterpret_cast<const int2*>(xi + g + j)); xr[j] = (float)p.x; xr[j + 1] = (float)p.y; }
+                else { const float2 p = __ldg(reinterpret_cast<const float2*>(xf + g + j)); xr[j] = p.x; xr[j + 1] = p.y; }
             }
-        } else {
-            // layer-1 input = layer-0 output of time t, already split: fp16 [site][33][hi|lo][128]
-            const uint4* ghi = reinterpret_cast<const uint4*>(h0_in + ((site * kT + t) * 2 + 0) * 128);
-            const uint4* glo = reinterpret_cast<const uint4*>(h0_in + ((site * kT + t) * 2 + 1) * 128);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int ch = half * 8 + q;
-                reinterpret_cast<uint4*>(sAhi + ch * LBO_A)[row] = __ldg(ghi + ch);
-                reinterpret_cast<uint4*>(sAlo + ch * LBO_A)[row] = __ldg(glo + ch);
-            }
+        } else if (sub == NWQ - 1) {
+            if (xi) { const int2 p = __ldg(reinterpret_cast<const int2*>(xi + g + 16)); xr[0] = (float)p.x; xr[1] = (float)p.y; }
+            else { const float2 p = __ldg(reinterpret_cast<const float2*>(xf + g + 16)); xr[0] = p.x; xr[1] = p.y; }
         }
     };
-    stage_input(dir == 0 ? 0 : kT - 1);
+    auto store_x = [&]() {
+        if (LAYER != 0) return;
+        if (sub == 0) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = xr[ch * 8 + j];
+                const HiLo8 s = split8(v);
+                reinterpret_cast<uint4*>(sAhi + ch * LBO_A)[row] = s.hi;
+                reinterpret_cast<uint4*>(sAlo + ch * LBO_A)[row] = s.lo;
+                reinterpret_cast<uint4*>(sAsc + ch * LBO_A)[row] = scale_hi(s.hi);
+            }
+        } else if (sub == NWQ - 1) {
+            const float v[8] = {xr[0], xr[1], 1.0f, 0.f, 0.f, 0.f, 0.f, 0.f};      // x16, x17, bias column
+            const HiLo8 s = split8(v);
+            reinterpret_cast<uint4*>(sAhi + 2 * LBO_A)[row] = s.hi;
+            reinterpret_cast<uint4*>(sAlo + 2 * LBO_A)[row] = s.lo;
+            reinterpret_cast<uint4*>(sAsc + 2 * LBO_A)[row] = scale_hi(s.hi);
+        }
+    };
+    auto stage_h0_async = [&](int t) {                               // layer 1: fp16 [site][33][hi|lo][128]
+        if (LAYER != 1) return;
+        const __half* ghi = h0_in + ((site * kT + t) * 2 + 0) * 128;
+        const __half* glo = ghi + 128;
+        constexpr int CH = 16 / NWQ;
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+            const int ch = sub * CH + q;
+            cp_async16(sAhi + ch * LBO_A + row * 16, ghi + ch * 8);
+            cp_async16(sAlo + ch * LBO_A + row * 16, glo + ch * 8);
+        }
+    };
+    {
+        const int t0 = dir == 0 ? 0 : kT - 1;
+        load_x(t0); store_x(); stage_h0_async(t0);
+    }
 
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -255,7 +276,10 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
 
     for (int step = 0; step < C::STEPS; ++step) {
         const int t = dir == 0 ? step : (kT - 1 - step);
+        const int tn = dir == 0 ? step + 1 : (kT - 2 - step);
+        const bool more = step + 1 < C::STEPS;
         // ---- operands written by the generic proxy -> visible to the tensor core; TMEM reads of the last step retired ----
+        if (LAYER == 1) cp_async_wait_all();
         fence_async_smem();
         tc_fence_before();
         if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -276,13 +300,15 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
             }
             umma_commit<CG>(bar);
         }
+        if (more) load_x(tn);                                       // global latency hides under the MMAs
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
+        if (more) stage_h0_async(tn);                               // the MMAs are done reading the input part of A
 
         if (DEBUG) {
 #pragma unroll 1
-            for (int jb = half * 4; jb < half * 4 + 4; ++jb) {
+            for (int jb = sub * UB; jb < sub * UB + UB; ++jb) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + jb * 32, v);
                 if (live) for (int i = 0; i < 32; ++i) dbg[(site0 + row) * 256 + jb * 32 + i] = v[i];
@@ -290,10 +316,10 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
             break;
         }
 
-        // ---- epilogue: 4 blocks of 8 hidden units per thread ----
+        // ---- epilogue: UB blocks of 8 hidden units per thread ----
 #pragma unroll
-        for (int jl = 0; jl < 4; ++jl) {
-            const int jb = half * 4 + jl;
+        for (int jl = 0; jl < UB; ++jl) {
+            const int jb = sub * UB + jl;
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + jb * 32, v);
             float hv[8];
@@ -326,7 +352,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
                 }
             }
         }
-        if (step + 1 < C::STEPS) stage_input(dir == 0 ? step + 1 : kT - 2 - step);
+        if (more) store_x();
     }
 
     // ---- teardown: nobody may still be reading TMEM / the peer's shared memory ----
@@ -335,12 +361,12 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     if (warp == 0) tmem_dealloc<CG>(tmem_base, 256);
 }
 
-template <int LAYER, int CG, bool DEBUG>
+template <int LAYER, int CG, int NWQ, bool DEBUG>
 int launch_one(const void* blob, const int32_t* xi, const float* xf, const void* h0_in, void* h0_out, float* h16, float* dbg,
                int64_t m, int dir_override, cudaStream_t stream)
 {
     using S = TcSmem<LAYER, CG>;
-    auto kern = lstm_tc_kernel<LAYER, CG, DEBUG>;
+    auto kern = lstm_tc_kernel<LAYER, CG, NWQ, DEBUG>;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total) != cudaSuccess) return cuda_status("cudaFuncSetAttribute(lstm_tc_kernel)");
@@ -350,7 +376,7 @@ int launch_one(const void* blob, const int32_t* xi, const float* xf, const void*
     if (CG == 2 && (gx & 1)) ++gx;                               // whole clusters; the padding CTA works on clamped rows
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(gx, DEBUG ? 1 : 2, 1);
-    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.blockDim = dim3(128 * NWQ, 1, 1);
     cfg.dynamicSmemBytes = S::total;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -358,21 +384,23 @@ int launch_one(const void* blob, const int32_t* xi, const float* xf, const void*
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)blob, xi, xf, (const __half*)h0_in, (__half*)h0_out, h16, dbg, m, dir_override);
-    if (e != cudaSuccess) return set_error(NSNP_E_CUDA, "lstm_tc_kernel<%d,%d>: %s", LAYER, CG, cudaGetErrorString(e));
+    if (e != cudaSuccess) return set_error(NSNP_E_CUDA, "lstm_tc_kernel<%d,%d,%d>: %s", LAYER, CG, NWQ, cudaGetErrorString(e));
     return NSNP_OK;
 }
 
 }  // namespace
 
 int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, cudaStream_t stream) {
-    if (int e = launch_one<0, 1, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e;
-    return launch_one<1, 2, false>(blob, nullptr, nullptr, h0, nullptr, h16, nullptr, m, 0, stream);
+    // layer 0: CTA pairs share W (53 KB each) so two CTAs fit per SM and one CTA's MMAs overlap the other's epilogue
+    if (int e = launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e;
+    // layer 1: W only fits split across a CTA pair (2 x 104 KB); one CTA per SM, 16 warps for the epilogue
+    return launch_one<1, 2, 4, false>(blob, nullptr, nullptr, h0, nullptr, h16, nullptr, m, 0, stream);
 }
 
 int debug_tc_gates(const void* blob, const int32_t* xi, int layer, int dir, int cg, const void* h0, float* gates_out, int64_t m, cudaStream_t stream) {
-    if (layer == 0 && cg == 1) return launch_one<0, 1, true>(blob, xi, nullptr, nullptr, nullptr, nullptr, gates_out, m, dir, stream);
-    if (layer == 0 && cg == 2) return launch_one<0, 2, true>(blob, xi, nullptr, nullptr, nullptr, nullptr, gates_out, m, dir, stream);
-    if (layer == 1 && cg == 2) return launch_one<1, 2, true>(blob, nullptr, nullptr, h0, nullptr, nullptr, gates_out, m, dir, stream);
+    if (layer == 0 && cg == 1) return launch_one<0, 1, 2, true>(blob, xi, nullptr, nullptr, nullptr, nullptr, gates_out, m, dir, stream);
+    if (layer == 0 && cg == 2) return launch_one<0, 2, 2, true>(blob, xi, nullptr, nullptr, nullptr, nullptr, gates_out, m, dir, stream);
+    if (layer == 1 && cg == 2) return launch_one<1, 2, 4, true>(blob, nullptr, nullptr, h0, nullptr, nullptr, gates_out, m, dir, stream);
     return set_error(NSNP_E_UNSUPPORTED, "debug_tc_gates: layer %d with cta_group %d is not built", layer, cg);
 }
 

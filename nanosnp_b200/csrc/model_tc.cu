@@ -52,6 +52,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Per-step hand-off inside a CTA pair.  Every thread has already made its shared-memory operand writes visible to
+// the async proxy (fence.proxy.async) and retired its TMEM loads, so only execution ordering is needed here; a
+// .release arrive would additionally drain this thread's outstanding GLOBAL stores (the layer-0 output rows) to L2
+// at cluster scope on every step, which ncu showed as 37% of all stall samples (membar).
+__device__ __forceinline__ void cluster_sync_exec() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 
 template <int CG> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -213,20 +220,21 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     // ---- input staging.  Layer 0: counts row -> registers (prefetch) -> fp16 hi / lo / scaled-hi chunks.
     //      Layer 1: layer-0 output is already fp16 hi|lo in global memory -> cp.async straight into the operand. ----
     // layer 0 work split: sub 0 converts x[0..15] (chunks 0,1); the last sub converts x16, x17 + the bias column (chunk 2)
-    float xr[16];
+    int2 xraw[8];                                                    // raw bits: converted only when stored (no stall at the load)
     auto load_x = [&](int t) {
         if (LAYER != 0) return;
-        const int64_t g = (site * kT + t) * kF;
+        const int2* g = reinterpret_cast<const int2*>(xi ? (const void*)(xi + (site * kT + t) * kF) : (const void*)(xf + (site * kT + t) * kF));
         if (sub == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                if (xi) { const int2 p = __ldg(reinterpret_cast<const int2*>(xi + g + j)); xr[j] = (float)p.x; xr[j + 1] = (float)p.y; }
-                else { const float2 p = __ldg(reinterpret_cast<const float2*>(xf + g + j)); xr[j] = p.x; xr[j + 1] = p.y; }
-            }
+            for (int j = 0; j < 8; ++j) xraw[j] = __ldg(g + j);
         } else if (sub == NWQ - 1) {
-            if (xi) { const int2 p = __ldg(reinterpret_cast<const int2*>(xi + g + 16)); xr[0] = (float)p.x; xr[1] = (float)p.y; }
-            else { const float2 p = __ldg(reinterpret_cast<const float2*>(xf + g + 16)); xr[0] = p.x; xr[1] = p.y; }
+            xraw[0] = __ldg(g + 8);
         }
+    };
+    auto xval = [&](int j) -> float {
+        const int2 p = xraw[j >> 1];
+        const int b = (j & 1) ? p.y : p.x;
+        return xi ? (float)b : __int_as_float(b);
     };
     auto store_x = [&]() {
         if (LAYER != 0) return;
@@ -235,14 +243,14 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
             for (int ch = 0; ch < 2; ++ch) {
                 float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = xr[ch * 8 + j];
+                for (int j = 0; j < 8; ++j) v[j] = xval(ch * 8 + j);
                 const HiLo8 s = split8(v);
                 reinterpret_cast<uint4*>(sAhi + ch * LBO_A)[row] = s.hi;
                 reinterpret_cast<uint4*>(sAlo + ch * LBO_A)[row] = s.lo;
                 reinterpret_cast<uint4*>(sAsc + ch * LBO_A)[row] = scale_hi(s.hi);
             }
         } else if (sub == NWQ - 1) {
-            const float v[8] = {xr[0], xr[1], 1.0f, 0.f, 0.f, 0.f, 0.f, 0.f};      // x16, x17, bias column
+            const float v[8] = {xval(0), xval(1), 1.0f, 0.f, 0.f, 0.f, 0.f, 0.f};  // x16, x17, bias column
             const HiLo8 s = split8(v);
             reinterpret_cast<uint4*>(sAhi + 2 * LBO_A)[row] = s.hi;
             reinterpret_cast<uint4*>(sAlo + 2 * LBO_A)[row] = s.lo;
@@ -282,7 +290,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
         if (LAYER == 1) cp_async_wait_all();
         fence_async_smem();
         tc_fence_before();
-        if (CG == 2) cluster_sync_all(); else __syncthreads();
+        if (CG == 2) cluster_sync_exec(); else __syncthreads();
         if (cta_rank == 0 && tid == 0) {
             tc_fence_after();
             uint32_t acc = 0;

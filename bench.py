@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-kb", type=float, default=500.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "f16x3"])
+    ap.add_argument("--precision", default="f16x3", choices=["fp32", "f16x3"])
     return ap.parse_args()
 
 

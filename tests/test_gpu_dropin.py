@@ -1,0 +1,69 @@
+"""The drop-in entry points on a GPU: `python -m nanosnp_b200.predict` with the reference's CLI must reproduce the
+reference Python's VCF from (a) the reference's own .pd text hand-off and (b) packed reads (s1 on the GPU too)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare_vcf(got_text, ref_text):
+    got = [l for l in got_text.splitlines() if not l.startswith("#")]
+    ref = [l for l in ref_text.splitlines() if not l.startswith("#")]
+    assert [l for l in got_text.splitlines() if l.startswith("#")] == [l for l in ref_text.splitlines() if l.startswith("#")]
+    assert len(got) == len(ref)
+    nq = 0
+    for a, b in zip(got, ref):
+        fa, fb = a.split("\t"), b.split("\t")
+        assert fa[:5] == fb[:5] and fa[6:9] == fb[6:9], (a, b)           # CHROM POS ID REF ALT | FILTER INFO FORMAT
+        sa, sb = fa[9].split(":"), fb[9].split(":")
+        assert sa[0] == sb[0] and sa[2:] == sb[2:], (a, b)               # GT, DP, AF identical
+        if fa[5] != fb[5]:
+            nq += 1
+            assert abs(float(fa[5]) - float(fb[5])) <= 0.0101            # QUAL: last printed digit
+    assert nq <= 0.03 * len(ref)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16x3"])
+def test_predict_cli_from_pd_text_and_from_reads(tmp_path, golden, small_case, precision):
+    from nanosnp_b200 import predict as P
+    from nanosnp_b200.dataset import save_reads_npz
+    from oracle.pyoracle import write_fasta
+    fa = str(tmp_path / "ref.fa")
+    write_fasta(fa, {"ctg1": small_case["ref"]})
+    cfg = str(P.__file__).replace("predict.py", "config/ont_pileup.yaml")
+    # (a) the reference's text seam
+    d1 = tmp_path / "pd"; d1.mkdir()
+    up = np.char.upper(small_case["ref"].view("S1")).view(np.uint8)
+    with open(d1 / "ctg1.pd", "w") as f:
+        for p, w in zip(small_case["site_pos"], small_case["windows"]):
+            seq = bytes(up[p - 17:p + 16]).decode()
+            f.write(" ".join(map(str, w.reshape(-1))) + " \tctg1:%d:%s\t0-\n" % (p, seq))
+    out1 = str(tmp_path / "a.vcf")
+    P.main(["-config", cfg, "-model_path", str(golden / "ont_pileup_weights.npz"), "-data", str(d1), "-reference", fa, "-output", out1,
+            "--precision", precision])
+    _compare_vcf(open(out1).read(), (golden / "s2_small.vcf").read_text())
+    # (b) packed reads: s1 + s2 on the GPU
+    d2 = tmp_path / "reads"; d2.mkdir()
+    save_reads_npz(str(d2 / "ctg1.reads.npz"), small_case["reads"], "ctg1", len(small_case["ref"]))
+    out2 = str(tmp_path / "b.vcf")
+    P.main(["-config", cfg, "-model_path", str(golden / "ont_pileup_weights.npz"), "-data", str(d2), "-reference", fa, "-output", out2,
+            "--precision", precision])
+    assert open(out2).read() == open(out1).read()
+    with pytest.raises(SystemExit):
+        P.main(["-config", cfg, "-model_path", "x", "-data", str(d2), "-reference", fa, "-output", out2, "--no_cuda"])
+
+
+def test_lstmnetwork_seam(golden_weights, small_case, golden):
+    import torch
+    from nanosnp_b200.model import LSTMNetwork
+    enc, fwd = golden_weights
+    net = LSTMNetwork(None, precision="fp32").to("cuda")
+    with pytest.raises(RuntimeError):
+        net.encoder.load_state_dict({"lstm.weight_ih_l0": enc["lstm.weight_ih_l0"]})
+    net.encoder.load_state_dict(enc); net.forward_layer.load_state_dict(fwd)
+    net.eval()
+    x = torch.from_numpy(small_case["windows"][:1000]).type(torch.FloatTensor).to("cuda")       # predict.py:49
+    gt, zy = net.predict(x)
+    z = np.load(golden / "s2_small.npz")
+    assert gt.shape == (1000, 21) and zy.shape == (1000, 3) and gt.is_cuda
+    assert np.abs(gt.detach().cpu().numpy() - z["gt"][:1000]).max() < 2e-5

@@ -25,7 +25,6 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kReadList = 1024;             // overlapping reads handled per round
 constexpr int kStageRows = kThreads;        // epilogue sub-block
-constexpr int kStageStride = 19;            // 18 + 1 pad: conflict-free row writes
 
 struct Event {                               // 16 bytes, lives in the per-CTA global slab (L2 resident)
     uint32_t next;                           // previous event anchored at the same position (chain)
@@ -113,21 +112,25 @@ __global__ void __launch_bounds__(256) read_scan_kernel(nsnp_reads_t rd, nsnp_pa
 }
 
 // ------------------------------------------------------------------------------------------------
+constexpr int kGateTab = 256;            // AF-gate thresholds are tabulated for depths below this
+
 template <int T>
 struct TileSmem {
     uint32_t base[4][T];          // mismatch counters, u16 pairs: [strand*2 + (b>>1)][p], half = b&1
     uint32_t nn[T];               // read-N bases: fwd | rev << 16
-    uint32_t ms[T], me[T];        // aligned-run starts / ends (fwd | rev << 16); later: depth, I1|i1
-    uint32_t ds[T], de[T];        // deletion-span starts / ends;                later: depth, D1|d1
+    uint32_t ms[T], me[T];        // aligned-run starts / ends (fwd | rev << 16); after the scan: aligned depth
+    uint32_t ds[T], de[T];        // deletion-span starts / ends;                after the scan: '*' / '#' depth
+    uint32_t cnt4[T];             // indel events per class (I i D d), one byte each (exact while <= 255 reads overlap)
     uint32_t head[T];             // indel event chain heads
     uint32_t ref2[T / 16 + 2];    // 2-bit reference tile
     uint32_t refx[T / 16 + 2];    // 01 at non-ACGT reference positions (forces a "mismatch" event)
     uint32_t skipcov[T / 32];     // positions inside a reference skip (N op)
     uint8_t  refc[T];
-    int32_t  stage[kStageRows * kStageStride];
+    int32_t  stage[kStageRows * 18];
+    int32_t  thr_snp[kGateTab], thr_indel[kGateTab];   // smallest count c with (double)c / den >= min_af
     int32_t  rlist[kReadList];
     int32_t  warp_tot[kWarps][4];
-    int32_t  n_rlist, next_task, n_events, tile;
+    int32_t  n_rlist, next_task, n_events, tile, ref_has_x;
 };
 
 template <int T>
@@ -141,6 +144,7 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
     const int strand = (rd.flag[r] >> 4) & 1;
     const uint32_t sinc = 1u << (16 * strand);
     const int nchunks = (int)((c1 - c0 + 31) >> kCkShift);
+    const bool ref_has_x = sm.ref_has_x != 0;                       // tile-uniform
     const int32_t* ckr = ws.ck_ref + ((c0 >> kCkShift) + r);
     const int32_t* ckq = ws.ck_q + ((c0 >> kCkShift) + r);
     // last chunk whose first op starts at or before the tile start (32-ary search over the checkpoints)
@@ -182,7 +186,8 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
                     const uint32_t sw = bases16_g(seqw, g + o);
                     const uint32_t rw = bases16(sm.ref2, pa + o);
                     uint32_t x = sw ^ rw;
-                    uint32_t mm = ((x | (x >> 1)) & 0x55555555u) | bases16(sm.refx, pa + o);
+                    uint32_t mm = (x | (x >> 1)) & 0x55555555u;
+                    if (ref_has_x) mm |= bases16(sm.refx, pa + o);
                     if (m < 16) mm &= (1u << (2 * m)) - 1u;
                     if (nmw) {
                         uint32_t nb = bits16_g(nmw, g + o);
@@ -211,6 +216,7 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
             const int64_t anchor = rs - 1;
             if (len <= NSNP_MAX_INDEL && rs > rpos && anchor >= ts && anchor < te) {
                 const int e = atomicAdd(&sm.n_events, 1);
+                atomicAdd(&sm.cnt4[(int)(anchor - ts)], 1u << (8 * ((op == 2 ? 2 : 0) + strand)));
                 if (e < ws.slab_cap) {
                     Event ev;
                     ev.next = atomicExch(&sm.head[(int)(anchor - ts)], (uint32_t)e);
@@ -244,8 +250,19 @@ __device__ __forceinline__ bool same_insert(const uint32_t* seqw, const uint32_t
     return true;
 }
 
+__device__ __forceinline__ int min_count_for_af(double af, int den) {
+    if (!(af == af)) return INT32_MAX;                      // NaN threshold: the comparison is never true
+    if (af <= 0.0) return 0;
+    const double x = af * den;
+    if (x > 2.0e9) return INT32_MAX;
+    int c = (int)ceil(x);
+    while (c > 0 && (double)(c - 1) / den >= af) --c;
+    while ((double)c / den < af) ++c;
+    return c;
+}
+
 template <int T>
-__global__ void __launch_bounds__(kThreads) pileup_tile_kernel(nsnp_reads_t rd, nsnp_params_t prm, const uint8_t* __restrict__ ref,
+__global__ void __launch_bounds__(kThreads, 3) pileup_tile_kernel(nsnp_reads_t rd, nsnp_params_t prm, const uint8_t* __restrict__ ref,
                                                                int64_t region_start, int64_t region_len, int n_tiles,
                                                                Workspace ws, int32_t* __restrict__ counts,
                                                                uint8_t* __restrict__ flags, int32_t* status)
@@ -256,6 +273,15 @@ __global__ void __launch_bounds__(kThreads) pileup_tile_kernel(nsnp_reads_t rd, 
     Event* slab = ws.slabs + (int64_t)blockIdx.x * ws.slab_cap;
     const uint32_t* seqw = reinterpret_cast<const uint32_t*>(rd.seq2);
     const uint32_t* nmw = reinterpret_cast<const uint32_t*>(rd.nmask);
+
+    // AF gate as integer thresholds: thr[den] = smallest count c with (double)c / den >= min_af, evaluated with the
+    // same IEEE double division as tensor_maker.cpp:213,218 -- the comparison result is identical, the divide is
+    // done once per CTA instead of ~6 times per position
+    for (int d = tid; d < kGateTab; d += kThreads) {
+        const int den = d ? d : 1;                          // tensor_maker.cpp:195
+        sm.thr_snp[d] = min_count_for_af(prm.snp_min_af, den);
+        sm.thr_indel[d] = min_count_for_af(prm.indel_min_af, den);
+    }
 
     for (;;) {
         __syncthreads();                                    // previous tile fully written, smem reusable
@@ -269,23 +295,29 @@ __global__ void __launch_bounds__(kThreads) pileup_tile_kernel(nsnp_reads_t rd, 
 
         // ---- clear counters, stage the reference tile ----
         {
-            uint32_t* z = &sm.base[0][0];
-            for (int i = tid; i < 9 * T; i += kThreads) z[i] = 0u;                     // base, nn, ms, me, ds, de
+            uint4* z = reinterpret_cast<uint4*>(&sm.base[0][0]);
+            for (int i = tid; i < 10 * T / 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);   // base, nn, ms, me, ds, de, cnt4
             for (int i = tid; i < T; i += kThreads) sm.head[i] = 0xFFFFFFFFu;
             for (int i = tid; i < T / 32; i += kThreads) sm.skipcov[i] = 0u;
-            for (int i = tid; i < T; i += kThreads) sm.refc[i] = i < tn ? ref[ts + i] : (uint8_t)'N';
             if (tid == 0) { sm.n_events = 0; }
+            // 4 reference bases per thread -> one byte of the 2-bit tile and of the non-ACGT mask
+            static_assert(T == 4 * kThreads, "one thread packs 4 reference bases");
+            uint32_t r2 = 0, rx = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int pp = tid * 4 + j;
+                const uint8_t ch = pp < tn ? ref[ts + pp] : (uint8_t)'N';
+                sm.refc[pp] = ch;
+                const int cd = nt4(ch);
+                if (cd < 4) r2 |= (uint32_t)cd << (2 * j); else rx |= 1u << (2 * j);
+            }
+            reinterpret_cast<uint8_t*>(sm.ref2)[tid] = (uint8_t)r2;
+            reinterpret_cast<uint8_t*>(sm.refx)[tid] = (uint8_t)rx;
+            if (tid < 8) { reinterpret_cast<uint8_t*>(sm.ref2)[T / 4 + tid] = 0; reinterpret_cast<uint8_t*>(sm.refx)[T / 4 + tid] = 0x55; }
+            const int any_x = __syncthreads_or(rx != 0u && tid * 4 < tn);
+            if (tid == 0) sm.ref_has_x = any_x;
         }
         __syncthreads();
-        for (int w = tid; w < T / 16 + 2; w += kThreads) {
-            uint32_t r2 = 0, rx = 0;
-            for (int j = 0; j < 16; ++j) {
-                const int p = w * 16 + j;
-                const int c = p < T ? nt4(sm.refc[p]) : 4;
-                if (c < 4) r2 |= (uint32_t)c << (2 * j); else rx |= 1u << (2 * j);
-            }
-            sm.ref2[w] = r2; sm.refx[w] = rx;
-        }
 
         // ---- accumulate: reads [lo, hi) that overlap the tile, one warp per read ----
         const int rlo = ws.tile_lo[tile], rhi = ws.tile_hi[tile];
@@ -308,6 +340,7 @@ __global__ void __launch_bounds__(kThreads) pileup_tile_kernel(nsnp_reads_t rd, 
             }
         }
         __syncthreads();
+        const bool deep = rhi - rlo > 255;                  // class counters are bytes: exact only below 256 overlapping reads
         if (tid == 0 && rhi - rlo > 65535) dev_fail(status, DEV_E_DEPTH, (int)(ts & 0x7fffffff));
 
         // ---- prefix sums: run starts/ends -> depths (fwd | rev << 16 stays valid: depths are < 65536) ----
@@ -341,28 +374,33 @@ __global__ void __launch_bounds__(kThreads) pileup_tile_kernel(nsnp_reads_t rd, 
         // ---- epilogue: 18 channels + gate per position, staged, then coalesced stores ----
         for (int sb = 0; sb < tn; sb += kStageRows) {
             const int p = sb + tid;
-            uint8_t fl = 0;
             if (p < tn) {
-                // indel channels from the event chain: totals and the multiplicity of the most frequent identical indel
-                int tot0 = 0, tot1 = 0, tot2 = 0, tot3 = 0, mx0 = 0, mx1 = 0, mx2 = 0, mx3 = 0;
-                for (uint32_t e = sm.head[p]; e != 0xFFFFFFFFu;) {
-                    const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(slab + e));
-                    const int cls = (raw.y >> 8) & 3, len = raw.y & 0xFF;
-                    const uint64_t g = (uint64_t)raw.z | ((uint64_t)raw.w << 32);
-                    // multiplicity = this event + identical events further down the chain: the group member
-                    // nearest the head sees the whole group
-                    int mult = 1;
-                    for (uint32_t f = raw.x; f != 0xFFFFFFFFu;) {
-                        const uint4 o = __ldcg(reinterpret_cast<const uint4*>(slab + f));
-                        if ((o.y & 0x3FF) == (raw.y & 0x3FF) &&
-                            (cls >= 2 || same_insert(seqw, nmw, g, (uint64_t)o.z | ((uint64_t)o.w << 32), len))) ++mult;
-                        f = o.x;
+                // indel channels: totals from the class counters; the chain is walked only where a class holds >= 2
+                // events (multiplicity of the most frequent identical indel, I1/D1) or the counters may have wrapped
+                int tot0, tot1, tot2, tot3, mx0, mx1, mx2, mx3;
+                const uint32_t c4 = sm.cnt4[p];
+                tot0 = c4 & 0xFF; tot1 = (c4 >> 8) & 0xFF; tot2 = (c4 >> 16) & 0xFF; tot3 = c4 >> 24;
+                mx0 = tot0; mx1 = tot1; mx2 = tot2; mx3 = tot3;
+                if (deep || ((c4 + 0x7E7E7E7Eu) & 0x80808080u)) {             // some byte >= 2
+                    tot0 = tot1 = tot2 = tot3 = 0; mx0 = mx1 = mx2 = mx3 = 0;
+                    for (uint32_t e = sm.head[p]; e != 0xFFFFFFFFu;) {
+                        const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(slab + e));
+                        const int cls = (raw.y >> 8) & 3, len = raw.y & 0xFF;
+                        const uint64_t g = (uint64_t)raw.z | ((uint64_t)raw.w << 32);
+                        // multiplicity = this event + identical events further down the chain: the group member
+                        // nearest the head sees the whole group
+                        int mult = 1;
+                        for (uint32_t f = raw.x; f != 0xFFFFFFFFu;) {
+                            const uint4 o = __ldcg(reinterpret_cast<const uint4*>(slab + f));
+                            if ((o.y & 0x3FF) == (raw.y & 0x3FF) &&
+                                (cls >= 2 || same_insert(seqw, nmw, g, (uint64_t)o.z | ((uint64_t)o.w << 32), len))) ++mult;
+                            f = o.x;
+                        }
+                        if (cls == 0) { ++tot0; mx0 = max(mx0, mult); } else if (cls == 1) { ++tot1; mx1 = max(mx1, mult); }
+                        else if (cls == 2) { ++tot2; mx2 = max(mx2, mult); } else { ++tot3; mx3 = max(mx3, mult); }
+                        e = raw.x;
                     }
-                    if (cls == 0) { ++tot0; mx0 = max(mx0, mult); } else if (cls == 1) { ++tot1; mx1 = max(mx1, mult); }
-                    else if (cls == 2) { ++tot2; mx2 = max(mx2, mult); } else { ++tot3; mx3 = max(mx3, mult); }
-                    e = raw.x;
                 }
-                const int tot[4] = {tot0, tot1, tot2, tot3}, mx[4] = {mx0, mx1, mx2, mx3};
                 const uint32_t md = sm.ms[p], dd = sm.ds[p], nnv = sm.nn[p];
                 const int mf = (int)(md & 0xFFFF) - (int)(nnv & 0xFFFF), mr = (int)(md >> 16) - (int)(nnv >> 16);
                 const int df = (int)(dd & 0xFFFF), dr = (int)(dd >> 16);
@@ -372,56 +410,60 @@ __global__ void __launch_bounds__(kThreads) pileup_tile_kernel(nsnp_reads_t rd, 
                   cr[0] = w2 & 0xFFFF; cr[1] = w2 >> 16; cr[2] = w3 & 0xFFFF; cr[3] = w3 >> 16; }
                 const int rc4 = nt4(sm.refc[p]);
                 const int chr = rc4 < 4 ? rc4 : 0;                                   // evc_base_from: non-ACGT -> 'A'
-                // merged-strand tallies in std::map key order A C D G I T (tensor_maker.cpp:124,197)
-                int oth = 0;
+                // merged-strand tallies (tensor_maker.cpp:124,168-171): the reference base's own count is implied
+                const int allb = mf + mr;
+                int tb[4];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) if (b != chr) oth += cf[b] + cr[b];
-                int tally[6];
-                tally[0] = chr == 0 ? (mf + mr - oth) : cf[0] + cr[0];
-                tally[1] = chr == 1 ? (mf + mr - oth) : cf[1] + cr[1];
-                tally[2] = tot[2] + tot[3];
-                tally[3] = chr == 2 ? (mf + mr - oth) : cf[2] + cr[2];
-                tally[4] = tot[0] + tot[1];
-                tally[5] = chr == 3 ? (mf + mr - oth) : cf[3] + cr[3];
-                const int depth = mf + mr + df + dr;
-                const int den = depth ? depth : 1;
-                int top = -1, topc = 0;
+                for (int b = 0; b < 4; ++b) tb[b] = cf[b] + cr[b];
+                tb[chr] = 0;
+                const int refcnt = allb - (tb[0] + tb[1] + tb[2] + tb[3]);
+                const int tI = tot0 + tot1, tD = tot2 + tot3;
+                const int depth = allb + df + dr;
+                // pass_af (tensor_maker.cpp:195-228,248): top allele (stable order A<C<D<G<I<T on ties) differs from the
+                // reference, or a non-reference allele / indel class reaches its minimum frequency
+                bool pass;
+                {
+                    // top != ref  <=>  some non-ref entry beats the ref count, or ties it while sorting before it
+                    const int key_ref = chr == 0 ? 0 : chr == 1 ? 1 : chr == 2 ? 3 : 5;
+                    bool top_other = false;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) if (tally[k] > topc) { topc = tally[k]; top = k; }   // stable: first max wins
-                const int chr_key = chr == 0 ? 0 : chr == 1 ? 1 : chr == 2 ? 3 : 5;
-                bool pass = top >= 0 && top != chr_key;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    if (k == chr_key || tally[k] == 0) continue;
-                    const double f = 1.0 * tally[k] / den;
-                    pass = pass || (f >= ((k == 2 || k == 4) ? prm.indel_min_af : prm.snp_min_af));
+                    for (int b = 0; b < 4; ++b) {
+                        const int key = b == 0 ? 0 : b == 1 ? 1 : b == 2 ? 3 : 5;
+                        if (b != chr) top_other = top_other || (tb[b] > 0 && (tb[b] > refcnt || (tb[b] == refcnt && key < key_ref)));
+                    }
+                    top_other = top_other || (tD > 0 && (tD > refcnt || (tD == refcnt && 2 < key_ref)));
+                    top_other = top_other || (tI > 0 && (tI > refcnt || (tI == refcnt && 4 < key_ref)));
+                    const int mxb = max(max(tb[0], tb[1]), max(tb[2], tb[3]));
+                    const int mxi = max(tI, tD);
+                    bool af_pass;
+                    if (depth < kGateTab) {
+                        af_pass = (mxb > 0 && mxb >= sm.thr_snp[depth]) || (mxi > 0 && mxi >= sm.thr_indel[depth]);
+                    } else {
+                        af_pass = (mxb > 0 && 1.0 * mxb / depth >= prm.snp_min_af) || (mxi > 0 && 1.0 * mxi / depth >= prm.indel_min_af);
+                    }
+                    pass = top_other || af_pass;
                 }
-                const bool covered = (mf + mr + (int)(nnv & 0xFFFF) + (int)(nnv >> 16) + df + dr) > 0 ||
-                                     ((sm.skipcov[p >> 5] >> (p & 31)) & 1u);
+                const bool covered = (int)(md & 0xFFFF) + (int)(md >> 16) + df + dr > 0 || ((sm.skipcov[p >> 5] >> (p & 31)) & 1u);
                 const bool gate = covered && rc4 < 4 && pass && depth >= prm.min_coverage;       // main.cpp:196
-                fl = (uint8_t)((covered ? NSNP_F_COVERED : 0) | (gate ? NSNP_F_GATE : 0));
-                int32_t* row = sm.stage + tid * kStageStride;
-                row[0] = chr == 0 ? -mf : cf[0]; row[1] = chr == 1 ? -mf : cf[1];
-                row[2] = chr == 2 ? -mf : cf[2]; row[3] = chr == 3 ? -mf : cf[3];
-                row[4] = tot[0]; row[5] = mx[0]; row[6] = tot[2]; row[7] = mx[2]; row[8] = df;
-                row[9] = chr == 0 ? -mr : cr[0]; row[10] = chr == 1 ? -mr : cr[1];
-                row[11] = chr == 2 ? -mr : cr[2]; row[12] = chr == 3 ? -mr : cr[3];
-                row[13] = tot[1]; row[14] = mx[1]; row[15] = tot[3]; row[16] = mx[3]; row[17] = dr;
-                flags[(ts - region_start) + p] = fl;
+                flags[(ts - region_start) + p] = (uint8_t)((covered ? NSNP_F_COVERED : 0) | (gate ? NSNP_F_GATE : 0));
+                int2* row = reinterpret_cast<int2*>(sm.stage + tid * 18);
+                row[0] = make_int2(chr == 0 ? -mf : cf[0], chr == 1 ? -mf : cf[1]);
+                row[1] = make_int2(chr == 2 ? -mf : cf[2], chr == 3 ? -mf : cf[3]);
+                row[2] = make_int2(tot0, mx0); row[3] = make_int2(tot2, mx2);
+                row[4] = make_int2(df, chr == 0 ? -mr : cr[0]);
+                row[5] = make_int2(chr == 1 ? -mr : cr[1], chr == 2 ? -mr : cr[2]);
+                row[6] = make_int2(chr == 3 ? -mr : cr[3], tot1);
+                row[7] = make_int2(mx1, tot3); row[8] = make_int2(mx3, dr);
             }
             __syncthreads();
             {
                 const int rows = min(kStageRows, tn - sb);
-                const int n_int = rows * 18;                       // multiple of 2; 16-byte groups when rows is even
+                const int n_int = rows * 18;
                 int32_t* out = counts + ((ts - region_start) + sb) * 18;
                 const int n4 = n_int >> 2;
-                for (int q = tid; q < n4; q += kThreads) {
-                    int v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { const int e = q * 4 + j; const int rr = e / 18; v[j] = sm.stage[rr * kStageStride + (e - rr * 18)]; }
-                    st_stream(reinterpret_cast<int4*>(out) + q, make_int4(v[0], v[1], v[2], v[3]));
-                }
-                for (int e = (n4 << 2) + tid; e < n_int; e += kThreads) { const int rr = e / 18; out[e] = sm.stage[rr * kStageStride + (e - rr * 18)]; }
+                const int4* st4 = reinterpret_cast<const int4*>(sm.stage);
+                for (int q = tid; q < n4; q += kThreads) st_stream(reinterpret_cast<int4*>(out) + q, st4[q]);
+                for (int e = (n4 << 2) + tid; e < n_int; e += kThreads) out[e] = sm.stage[e];
             }
             __syncthreads();
         }

@@ -113,6 +113,67 @@ class RegionRunner:
         cov8 = x[:, 16, COV_CHANNELS].to(torch.float32) if n else torch.empty((0, 8), dtype=torch.float32, device=self.device)
         return RegionOutput(n, pos[:n], refbase, cov8, gt, zy, x if self.keep_windows else None)
 
+    # ---- host-buffer mode, pipelined: H2D of region k+1 and D2H of region k-1 overlap the kernels of region k ----
+    def run_host_many(self, host_regions, regions, ref: torch.Tensor, host_outs, consume=None):
+        """host_regions: PackedReads of pinned host tensors, one per region; host_outs: two dicts of pinned result
+        buffers (double buffered).  consume(k, result_dict) is called on the host once region k's results have landed
+        (e.g. VCF formatting); it runs while the GPU works on later regions.  Returns the total site count."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        up_s, down_s = self._copy_streams
+        n_reg = len(regions)
+        up_done = [None] * n_reg
+        comp_done = [None] * n_reg
+        down_done = [None] * n_reg
+        results = [None] * n_reg
+        dev_reads = [None] * n_reg
+
+        def start_upload(k):
+            with torch.cuda.stream(up_s):
+                if k >= 2:
+                    up_s.wait_event(comp_done[k - 2])            # buffer set k%2 is free once region k-2 has been computed
+                dev_reads[k] = self.upload(host_regions[k], key=f"reads{k % 2}")
+                ev = torch.cuda.Event(); ev.record(up_s); up_done[k] = ev
+
+        def finish(k):
+            down_done[k].synchronize()
+            if consume is not None:
+                consume(k, results[k])
+
+        up_s.wait_stream(main)
+        start_upload(0)
+        total = 0
+        for k in range(n_reg):
+            if k + 1 < n_reg:
+                if k + 1 >= 2 and comp_done[k - 1] is None:
+                    raise RuntimeError("pipeline order")
+                start_upload(k + 1)
+            main.wait_event(up_done[k])
+            out = self.run_device(dev_reads[k], ref, regions[k])
+            ev = torch.cuda.Event(); ev.record(main); comp_done[k] = ev
+            # results: device -> device staging (so the next region can reuse the work buffers) -> pinned host
+            ho = host_outs[k % 2]
+            with torch.cuda.stream(down_s):
+                down_s.wait_event(ev)
+                res = {"n": out.n}
+                for name in ("pos0", "refbase", "cov8", "gt", "zy"):
+                    t = getattr(out, name)
+                    if ho[name].shape[0] < out.n:
+                        raise _lib.NsnpError(_lib.E_WORKSPACE, f"host result buffer '{name}' too small for {out.n} sites")
+                    h = ho[name][: out.n]
+                    h.copy_(t, non_blocking=True)
+                    res[name] = h
+                ev2 = torch.cuda.Event(); ev2.record(down_s); down_done[k] = ev2
+            main.wait_event(ev2)                                  # run_device's buffers are reused by region k+1
+            results[k] = res
+            total += out.n
+            if k >= 1:
+                finish(k - 1)                                     # host-side consumer of the previous region
+        finish(n_reg - 1)
+        return total
+
     # ---- host-buffer mode: what a caller holding decoded reads in (pinned) host memory pays -------------
     def upload(self, host_reads: PackedReads, key: str = "reads") -> PackedReads:
         out = []

@@ -32,3 +32,9 @@ for (f, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:topn]:
     if want and want not in f: continue
     st = sorted(v[4].items(), key=lambda kv: -kv[1])[:2]
     print(f"{v[0]/ti*100:5.1f}%i {v[1]/ts*100:5.1f}%s thr{v[2]:4.0f} {f}:{ln:>4} {v[3][:95]}  [{', '.join(f'{k[6:]}={int(x)}' for k, x in st)}]")
+if len(sys.argv) > 4 and sys.argv[4] == "bylines":
+    print("---- by line (file filter applied), warp-inst % and stall-sample % ----")
+    for (f, ln), v in sorted(agg.items(), key=lambda kv: (kv[0][0], int(kv[0][1]))):
+        if want and want not in f: continue
+        if v[0] / ti < 0.002 and v[1] / ts < 0.002: continue
+        print(f"{v[0]/ti*100:5.1f}%i {v[1]/ts*100:5.1f}%s {f}:{ln:>4} {v[3][:110]}")

@@ -132,41 +132,57 @@ __global__ void __launch_bounds__(256, 1) lstm_dir_kernel(const float* __restric
     }
 }
 
-// out[s][c] = b[c] + sum_k in[s][k] * Wt[k][c]   (Wt k-major in global memory, read through L1)
-template <int IN, int OUT, int SG, bool TANH>
-__device__ __forceinline__ void dense_layer(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ b,
-                                            float* __restrict__ outp, int S)
+// ---- tail: output_proj -> dense + tanh -> heads -> softmax on the t = 16 state (model.py:37, 67-72, 117-118) ----
+// output_proj has no non-linearity, so it is folded into dense on the host (W' = W_dense W_proj, b' = W_dense b_proj +
+// b_dense, formed in double precision): one 128 -> 256 layer instead of 128 -> 128 -> 256.
+// One CTA = 32 sites (48 KB smem, 4 CTAs/SM).  Each layer is a register-tiled fp32 GEMM: a thread owns 4 adjacent
+// output columns x SPT sites, weights stream k-major from global memory (coalesced float4 rows, L1/L2 resident),
+// activations are float4 broadcasts from shared memory.
+constexpr int kTailS = 32;
+
+template <int IN, int OUT, bool TANH>
+__device__ __forceinline__ void dense_tile(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ b,
+                                           float* __restrict__ outp)
 {
-    const int items = OUT * (S / SG);
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int cidx = it % OUT, sg = it / OUT;
-        float acc[SG];
-        const float bb = __ldg(b + cidx);
+    constexpr int CG = OUT / 4;                  // column groups
+    constexpr int SGN = 256 / CG;                // site groups
+    constexpr int SPT = kTailS / SGN;            // sites per thread
+    const int cg = threadIdx.x % CG, sg = threadIdx.x / CG;
+    float acc[SPT][4];
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + cg);
 #pragma unroll
-        for (int s = 0; s < SG; ++s) acc[s] = bb;
-        for (int k = 0; k < IN; k += 4) {
-            const float w0 = __ldg(Wt + (size_t)(k + 0) * OUT + cidx), w1 = __ldg(Wt + (size_t)(k + 1) * OUT + cidx);
-            const float w2 = __ldg(Wt + (size_t)(k + 2) * OUT + cidx), w3 = __ldg(Wt + (size_t)(k + 3) * OUT + cidx);
+    for (int s = 0; s < SPT; ++s) { acc[s][0] = bb.x; acc[s][1] = bb.y; acc[s][2] = bb.z; acc[s][3] = bb.w; }
+    const float* arow = in + (sg * SPT) * IN;
+#pragma unroll 4
+    for (int k = 0; k < IN; k += 4) {
+        float4 w[4];
 #pragma unroll
-            for (int s = 0; s < SG; ++s) {
-                const float4 a = *reinterpret_cast<const float4*>(in + (sg * SG + s) * IN + k);
-                acc[s] = fmaf(w0, a.x, acc[s]); acc[s] = fmaf(w1, a.y, acc[s]);
-                acc[s] = fmaf(w2, a.z, acc[s]); acc[s] = fmaf(w3, a.w, acc[s]);
+        for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k + kk) * OUT) + cg);
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            const float4 a = *reinterpret_cast<const float4*>(arow + s * IN + k);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                acc[s][0] = fmaf(w[kk].x, av[kk], acc[s][0]); acc[s][1] = fmaf(w[kk].y, av[kk], acc[s][1]);
+                acc[s][2] = fmaf(w[kk].z, av[kk], acc[s][2]); acc[s][3] = fmaf(w[kk].w, av[kk], acc[s][3]);
             }
         }
+    }
 #pragma unroll
-        for (int s = 0; s < SG; ++s) outp[(sg * SG + s) * OUT + cidx] = TANH ? tanhf(acc[s]) : acc[s];
+    for (int s = 0; s < SPT; ++s) {
+        float4 o = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+        if (TANH) o = make_float4(tanhf(o.x), tanhf(o.y), tanhf(o.z), tanhf(o.w));
+        *reinterpret_cast<float4*>(outp + (sg * SPT + s) * OUT + 4 * cg) = o;
     }
 }
 
-constexpr int kTailS = 16;
-__global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ blob, const float* __restrict__ h16, int64_t n_max,
-                                                   const int32_t* __restrict__ n_dev, float* __restrict__ gt, float* __restrict__ zy)
+__global__ void __launch_bounds__(256, 4) tail_kernel(const float* __restrict__ blob, const float* __restrict__ h16, int64_t n_max,
+                                                      const int32_t* __restrict__ n_dev, float* __restrict__ gt, float* __restrict__ zy)
 {
-    __shared__ __align__(16) float in[kTailS * 128];
-    __shared__ __align__(16) float pj[kTailS * 128];
-    __shared__ __align__(16) float dn[kTailS * 256];
-    __shared__ float lg[kTailS * 24];
+    extern __shared__ __align__(16) float tsm[];
+    float* in = tsm;                         // [32][128]   (later: logits [32][24])
+    float* dn = in + kTailS * 128;           // [32][256]
     int64_t n = n_max;
     if (n_dev) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
     const int64_t site0 = (int64_t)blockIdx.x * kTailS;
@@ -177,11 +193,29 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ blo
         reinterpret_cast<float4*>(in)[i] = __ldg(reinterpret_cast<const float4*>(h16 + site * 128) + j);
     }
     __syncthreads();
-    dense_layer<128, 128, 8, false>(in, blob + kOffProjW, blob + kOffProjB, pj, kTailS);      // output_proj, model.py:37
+    dense_tile<128, 256, true>(in, blob + kOffDenseW, blob + kOffDenseB, dn);       // (dense o output_proj) + tanh
     __syncthreads();
-    dense_layer<128, 256, 8, true>(pj, blob + kOffDenseW, blob + kOffDenseB, dn, kTailS);     // dense + tanh, model.py:67
-    __syncthreads();
-    dense_layer<256, 24, 8, false>(dn, blob + kOffHeadW, blob + kOffHeadB, lg, kTailS);       // genotype + zygosity heads
+    // heads: 24 logits per site (21 genotype + 3 zygosity), thread = (site, 3 logits)
+    float* lg = in;
+    {
+        const int s = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 3;
+        float acc[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[j] = __ldg(blob + kOffHeadB + c0 + j);
+        const float* drow = dn + s * 256;
+#pragma unroll 4
+        for (int k = 0; k < 256; k += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(drow + k);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float* wr = blob + kOffHeadW + (size_t)(k + kk) * 24 + c0;
+                acc[0] = fmaf(__ldg(wr), av[kk], acc[0]); acc[1] = fmaf(__ldg(wr + 1), av[kk], acc[1]); acc[2] = fmaf(__ldg(wr + 2), av[kk], acc[2]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) lg[s * 24 + c0 + j] = acc[j];
+    }
     __syncthreads();
     if (threadIdx.x < kTailS) {
         const int s = threadIdx.x;
@@ -200,8 +234,9 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ blo
         }
     }
 }
+constexpr size_t kTailSmem = (size_t)kTailS * (128 + 256) * sizeof(float);
 
-constexpr int64_t kChunkSites = 1 << 16;
+constexpr int64_t kChunkSites = 148 * 128 * 4;     // 75,776 sites: whole waves of 128-site CTAs on 148 SMs (both LSTM kernels)
 
 }  // namespace
 }  // namespace nsnp
@@ -241,7 +276,17 @@ int nsnp_model_pack_weights(const nsnp_model_weights_t* w, void* host_blob, size
     if (!w->proj_w || !w->proj_b || !w->dense_w || !w->dense_b || !w->gt_w || !w->gt_b || !w->zy_w || !w->zy_b)
         return set_error(NSNP_E_INVALID, "missing head weights");
     for (int o = 0; o < 128; ++o) { for (int k = 0; k < 128; ++k) b[kOffProjW + k * 128 + o] = w->proj_w[o * 128 + k]; b[kOffProjB + o] = w->proj_b[o]; }
-    for (int o = 0; o < 256; ++o) { for (int k = 0; k < 128; ++k) b[kOffDenseW + k * 256 + o] = w->dense_w[o * 128 + k]; b[kOffDenseB + o] = w->dense_b[o]; }
+    // dense o output_proj folded in double precision: W'[o][k] = sum_j Wd[o][j] Wp[j][k], b'[o] = sum_j Wd[o][j] bp[j] + bd[o]
+    for (int o = 0; o < 256; ++o) {
+        for (int k = 0; k < 128; ++k) {
+            double acc = 0.0;
+            for (int j = 0; j < 128; ++j) acc += (double)w->dense_w[o * 128 + j] * (double)w->proj_w[j * 128 + k];
+            b[kOffDenseW + k * 256 + o] = (float)acc;
+        }
+        double bacc = (double)w->dense_b[o];
+        for (int j = 0; j < 128; ++j) bacc += (double)w->dense_w[o * 128 + j] * (double)w->proj_b[j];
+        b[kOffDenseB + o] = (float)bacc;
+    }
     for (int o = 0; o < 21; ++o) { for (int k = 0; k < 256; ++k) b[kOffHeadW + k * 24 + o] = w->gt_w[o * 256 + k]; b[kOffHeadB + o] = w->gt_b[o]; }
     for (int o = 0; o < 3; ++o) { for (int k = 0; k < 256; ++k) b[kOffHeadW + k * 24 + 21 + o] = w->zy_w[o * 256 + k]; b[kOffHeadB + 21 + o] = w->zy_b[o]; }
     return pack_tc_weights(w, (unsigned char*)host_blob);
@@ -271,7 +316,8 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(lstm_dir_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0) != cudaSuccess ||
-            cudaFuncSetAttribute(lstm_dir_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1) != cudaSuccess)
+            cudaFuncSetAttribute(lstm_dir_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1) != cudaSuccess ||
+            cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmem) != cudaSuccess)
             return cuda_status("cudaFuncSetAttribute(lstm_dir_kernel)");
         attr_done = true;
     }
@@ -291,7 +337,7 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
             lstm_dir_kernel<0><<<g0, 256, smem0, stream>>>(blob, xi, xf, nullptr, h0, m, nd);
             lstm_dir_kernel<1><<<g1, 256, smem1, stream>>>(blob, nullptr, nullptr, h0, h16, m, nd);
         }
-        tail_kernel<<<(unsigned)((m + kTailS - 1) / kTailS), 256, 0, stream>>>(blob, h16, m, nd, gt_prob_dev + off * 21, zy_prob_dev + off * 3);
+        tail_kernel<<<(unsigned)((m + kTailS - 1) / kTailS), 256, kTailSmem, stream>>>(blob, h16, m, nd, gt_prob_dev + off * 21, zy_prob_dev + off * 3);
         if (int e = cuda_status("pileup model kernels")) return e;
     }
     return NSNP_OK;

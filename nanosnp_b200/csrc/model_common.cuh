@@ -29,7 +29,8 @@ constexpr size_t kBlobFloats = kOffHeadB + 24 + 8;
 
 
 // ---- tensor-core section of the blob (fp16 hi/lo split weights in the UMMA K-major no-swizzle layout) ----
-//   B[k/8][n][k%8] halfs, n = unit_block*32 + gate*8 + unit_in_block  (TMEM column order of the epilogue)
+//   B[k/8][n][k%8] halfs, n = unit_block*32 + unit_half*16 + gate*4 + unit_in_half  (TMEM column order: every
+//   16 columns hold i,f,g,o of 4 hidden units, so the epilogue can pipeline 16-column TMEM loads)
 //   layer 0: K = 96  = [x 0..17 | bias column 18 | pad ..31 | h 32..95]; lo part of k < 32 is pre-scaled by 2^10
 //   layer 1: K = 208 = [l0 out 0..127 | bias column 128 | pad ..143 | h 144..207]
 constexpr int kTcK0 = 96, kTcIn0 = 32, kTcK1 = 208, kTcIn1 = 144;

@@ -105,6 +105,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 consecutive fp32 columns, no wait: pair with tmem_wait_ld() before the registers are read
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ int2 ldg_nc_volatile(const int2* p) {      // stays where it is written: issued before the MMA wait
+    int2 v;
+    asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -192,8 +207,8 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     if (!live) site = n - 1;                                     // clamp loads, skip stores
 
     // ---- one-time setup ----
-    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-    if (warp == 0) tmem_alloc<CG>(tmem_slot, 256);
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<CG>(tmem_slot, LAYER == 1 ? 512 : 256);
     {   // this CTA's weight rows: global [K/8][256][8] halfs -> shared [K/8][RB][8]
         const uint4* ghi = reinterpret_cast<const uint4*>(blob + tc_off(LAYER, dir, 0));
         const uint4* glo = reinterpret_cast<const uint4*>(blob + tc_off(LAYER, dir, 1));
@@ -226,9 +241,9 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
         const int2* g = reinterpret_cast<const int2*>(xi ? (const void*)(xi + (site * kT + t) * kF) : (const void*)(xf + (site * kT + t) * kF));
         if (sub == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xraw[j] = __ldg(g + j);
+            for (int j = 0; j < 8; ++j) xraw[j] = ldg_nc_volatile(g + j);
         } else if (sub == NWQ - 1) {
-            xraw[0] = __ldg(g + 8);
+            xraw[0] = ldg_nc_volatile(g + 8);
         }
     };
     auto xval = [&](int j) -> float {
@@ -269,9 +284,15 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
             cp_async16(sAlo + ch * LBO_A + row * 16, glo + ch * 8);
         }
     };
+    constexpr int XB = IN / 16;                                  // k-blocks of the input part; the rest is the h part
+    constexpr uint32_t kTmemCols = LAYER == 1 ? 512 : 256;       // layer 1 double-buffers the accumulator
+    uint64_t* barH = bar;                                        // "gates of this step are complete"
+    uint64_t* barX = bar + 1;                                    // layer 1: "input part of the NEXT step is accumulated"
     {
         const int t0 = dir == 0 ? 0 : kT - 1;
         load_x(t0); store_x(); stage_h0_async(t0);
+        if (LAYER == 1) cp_async_wait_all();
+        fence_async_smem();
     }
 
     tc_fence_before();
@@ -280,83 +301,117 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), a_sc = smem_u32(sAsc), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
     constexpr uint32_t idesc = make_idesc(128 * CG, 256);
-    uint32_t phase = 0;
+    const bool issuer = cta_rank == 0 && tid == 0;
+    // k-blocks [kb0, kb1) x three hi/lo passes into the accumulator at tmem_d
+    auto issue = [&](int kb0, int kb1, uint32_t tmem_d, uint32_t acc) {
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll 1
+            for (int kb = kb0; kb < kb1; ++kb) {
+                // pass 0: a_hi.w_hi   pass 1: a_hi.w_lo (layer-0 counts: scaled copy)   pass 2: a_lo.w_hi
+                uint32_t aa = pass == 2 ? a_lo : a_hi;
+                if (LAYER == 0 && pass == 1 && kb < kTcIn0 / 16) aa = a_sc;
+                const uint32_t bb = pass == 1 ? b_lo : b_hi;
+                umma_f16<CG>(tmem_d, make_desc(aa + kb * 2 * LBO_A, LBO_A, SBO), make_desc(bb + kb * 2 * LBO_B, LBO_B, SBO), idesc, acc);
+                acc = 1;
+            }
+        }
+    };
+    uint32_t phaseH = 0, phaseX = 0;
+    if (LAYER == 1) {
+        // software pipeline: the input part of step t+1 (27 of 39 MMAs, independent of h_t) runs on the tensor core
+        // while the epilogue of step t runs on the SM; only the 12 h-part MMAs stay on the per-step critical path
+        if (issuer) { tc_fence_after(); issue(0, XB, tmem_base, 0); umma_commit<CG>(barX); }
+        mbar_wait(barX, phaseX); phaseX ^= 1;
+        tc_fence_after();
+        if (C::STEPS > 1) stage_h0_async(dir == 0 ? 1 : kT - 2);
+    }
 
     for (int step = 0; step < C::STEPS; ++step) {
         const int t = dir == 0 ? step : (kT - 1 - step);
         const int tn = dir == 0 ? step + 1 : (kT - 2 - step);
         const bool more = step + 1 < C::STEPS;
+        const uint32_t acc_cols = LAYER == 1 ? (uint32_t)(step & 1) * 256u : 0u;
         // ---- operands written by the generic proxy -> visible to the tensor core; TMEM reads of the last step retired ----
         if (LAYER == 1) cp_async_wait_all();
         fence_async_smem();
         tc_fence_before();
         if (CG == 2) cluster_sync_exec(); else __syncthreads();
-        if (cta_rank == 0 && tid == 0) {
+        if (issuer) {
             tc_fence_after();
-            uint32_t acc = 0;
-#pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {
-#pragma unroll 1
-                for (int kb = 0; kb < KB; ++kb) {
-                    // pass 0: a_hi.w_hi   pass 1: a_hi.w_lo (layer-0 counts: scaled copy)   pass 2: a_lo.w_hi
-                    uint32_t aa = pass == 2 ? a_lo : a_hi;
-                    if (LAYER == 0 && pass == 1 && kb < kTcIn0 / 16) aa = a_sc;
-                    const uint32_t bb = pass == 1 ? b_lo : b_hi;
-                    umma_f16<CG>(tmem_base, make_desc(aa + kb * 2 * LBO_A, LBO_A, SBO), make_desc(bb + kb * 2 * LBO_B, LBO_B, SBO), idesc, acc);
-                    acc = 1;
-                }
+            if (LAYER == 1) {
+                issue(XB, KB, tmem_base + acc_cols, 1);                       // += W_hh . h_{t-1}
+                umma_commit<CG>(barH);
+                if (more) { issue(0, XB, tmem_base + (acc_cols ^ 256u), 0); umma_commit<CG>(barX); }
+            } else {
+                issue(0, KB, tmem_base, 0);
+                umma_commit<CG>(barH);
             }
-            umma_commit<CG>(bar);
         }
         if (more) load_x(tn);                                       // global latency hides under the MMAs
-        mbar_wait(bar, phase);
-        phase ^= 1;
+        mbar_wait(barH, phaseH);
+        phaseH ^= 1;
         tc_fence_after();
-        if (more) stage_h0_async(tn);                               // the MMAs are done reading the input part of A
 
         if (DEBUG) {
 #pragma unroll 1
             for (int jb = sub * UB; jb < sub * UB + UB; ++jb) {
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + jb * 32, v);
+                tmem_ld32(tmem_base + acc_cols + ((uint32_t)(quad * 32) << 16) + jb * 32, v);
                 if (live) for (int i = 0; i < 32; ++i) dbg[(site0 + row) * 256 + jb * 32 + i] = v[i];
             }
+            if (LAYER == 1 && more) { mbar_wait(barX, phaseX); phaseX ^= 1; }
             break;
         }
 
-        // ---- epilogue: UB blocks of 8 hidden units per thread ----
+        // ---- epilogue: UB blocks of 8 hidden units per thread, as 2*UB half blocks of 4 units whose TMEM loads are
+        //      software pipelined (the 16 columns of a half block are i,f,g,o of its 4 units) ----
+        uint32_t vb[2][16];
+        const uint32_t tacc = tmem_base + acc_cols + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * UB) * 32u;
+        tmem_ld16_nowait(tacc, vb[0]);
+        tmem_wait_ld();
+        float hv[8];
 #pragma unroll
-        for (int jl = 0; jl < UB; ++jl) {
-            const int jb = sub * UB + jl;
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + jb * 32, v);
-            float hv[8];
+        for (int hb = 0; hb < 2 * UB; ++hb) {
+            const int jl = hb >> 1, uh = hb & 1, jb = sub * UB + jl;
+            if (hb + 1 < 2 * UB) tmem_ld16_nowait(tacc + (hb + 1) * 16, vb[(hb + 1) & 1]);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float gi = fminf(fmaxf(v[u], -25.f), 25.f), gf = fminf(fmaxf(v[8 + u], -25.f), 25.f);
-                const float gg = fminf(fmaxf(v[16 + u], -12.5f), 12.5f), go = fminf(fmaxf(v[24 + u], -25.f), 25.f);
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t* v = vb[hb & 1];
+                const float gi = fminf(fmaxf(__uint_as_float(v[u]), -25.f), 25.f), gf = fminf(fmaxf(__uint_as_float(v[4 + u]), -25.f), 25.f);
+                const float gg = fminf(fmaxf(__uint_as_float(v[8 + u]), -12.5f), 12.5f), go = fminf(fmaxf(__uint_as_float(v[12 + u]), -25.f), 25.f);
                 const float ei = ex2_approx(-kLog2e * gi), ef = ex2_approx(-kLog2e * gf), eg = ex2_approx(-2.f * kLog2e * gg);
                 const float pi = 1.f + ei, pf = 1.f + ef, pg = 1.f + eg;
                 // c' = sigmoid(f) c + sigmoid(i) tanh(g) over one common denominator
                 const float pig = pi * pg;
-                const float num = fmaf(c[jl][u], pig, (1.f - eg) * pf);
+                const float num = fmaf(c[jl][uh * 4 + u], pig, (1.f - eg) * pf);
                 const float cn = num * rcp_approx(pf * pig);
-                c[jl][u] = cn;
+                c[jl][uh * 4 + u] = cn;
                 const float cc = fminf(fmaxf(cn, -12.5f), 12.5f);
                 const float ec = ex2_approx(-2.f * kLog2e * cc), eo = ex2_approx(-kLog2e * go);
-                hv[u] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));        // sigmoid(o) tanh(c')
+                hv[uh * 4 + u] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));        // sigmoid(o) tanh(c')
             }
-            const HiLo8 s = split8(hv);
-            reinterpret_cast<uint4*>(sAhi + (IN / 8 + jb) * LBO_A)[row] = s.hi;
-            reinterpret_cast<uint4*>(sAlo + (IN / 8 + jb) * LBO_A)[row] = s.lo;
-            if (live) {
-                if (LAYER == 0) {
-                    __half* o = h0_out + ((site * kT + t) * 2) * 128 + dir * kH + jb * 8;
-                    *reinterpret_cast<uint4*>(o) = s.hi;
-                    *reinterpret_cast<uint4*>(o + 128) = s.lo;
-                } else if (step == C::STEPS - 1) {
-                    float4* o = reinterpret_cast<float4*>(h16 + site * 128 + dir * kH + jb * 8);
-                    o[0] = make_float4(hv[0], hv[1], hv[2], hv[3]); o[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+            if (hb + 1 < 2 * UB) tmem_wait_ld();
+            if (uh == 1) {
+                const HiLo8 s = split8(hv);
+                reinterpret_cast<uint4*>(sAhi + (IN / 8 + jb) * LBO_A)[row] = s.hi;
+                reinterpret_cast<uint4*>(sAlo + (IN / 8 + jb) * LBO_A)[row] = s.lo;
+                if (live) {
+                    if (LAYER == 0) {
+                        __half* o = h0_out + ((site * kT + t) * 2) * 128 + dir * kH + jb * 8;
+                        *reinterpret_cast<uint4*>(o) = s.hi;
+                        *reinterpret_cast<uint4*>(o + 128) = s.lo;
+                    } else if (step == C::STEPS - 1) {
+                        float4* o = reinterpret_cast<float4*>(h16 + site * 128 + dir * kH + jb * 8);
+                        o[0] = make_float4(hv[0], hv[1], hv[2], hv[3]); o[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                    }
+                }
+                if (LAYER == 1 && more && jl == 0) {
+                    // half of this thread's epilogue is done and the input-part MMAs of step t+1 (issued ~3.5k cycles
+                    // ago) have finished: their operand region may take the inputs of step t+2 now, so the copies
+                    // land while the second half of the epilogue runs
+                    mbar_wait(barX, phaseX); phaseX ^= 1;
+                    if (step + 2 < C::STEPS) stage_h0_async(dir == 0 ? step + 2 : kT - 3 - step);
                 }
             }
         }
@@ -366,7 +421,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     // ---- teardown: nobody may still be reading TMEM / the peer's shared memory ----
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
-    if (warp == 0) tmem_dealloc<CG>(tmem_base, 256);
+    if (warp == 0) tmem_dealloc<CG>(tmem_base, kTmemCols);
 }
 
 template <int LAYER, int CG, int NWQ, bool DEBUG>
@@ -421,8 +476,8 @@ int pack_tc_weights(const nsnp_model_weights_t* w, unsigned char* blob) {
             __half* lo = reinterpret_cast<__half*>(blob + tc_off(layer, d, 1));
             const float *wih = w->w_ih[layer][d], *whh = w->w_hh[layer][d], *bi = w->b_ih[layer][d], *bh = w->b_hh[layer][d];
             for (int n = 0; n < 256; ++n) {
-                const int jb = n >> 5, gate = (n >> 3) & 3, u = n & 7;
-                const int rowi = gate * kH + jb * 8 + u;                 // PyTorch gate-major row
+                const int jb = n >> 5, uh = (n >> 4) & 1, gate = (n >> 2) & 3, u4 = n & 3;
+                const int rowi = gate * kH + jb * 8 + uh * 4 + u4;       // PyTorch gate-major row
                 for (int k = 0; k < K; ++k) {
                     float v = 0.f;
                     if (k < nin) v = wih[rowi * nin + k];

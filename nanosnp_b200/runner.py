@@ -109,7 +109,7 @@ class RegionRunner:
             timer.start("model")
             self.model(x, gt=gt, zy=zy)
             timer.stop()
-            self.launches += 1 + 3 * (-(-n // 65536))
+            self.launches += 1 + 3 * (-(-n // 75776))
         cov8 = x[:, 16, COV_CHANNELS].to(torch.float32) if n else torch.empty((0, 8), dtype=torch.float32, device=self.device)
         return RegionOutput(n, pos[:n], refbase, cov8, gt, zy, x if self.keep_windows else None)
 

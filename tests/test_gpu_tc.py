@@ -17,7 +17,7 @@ def weights(golden_weights):
 
 def _col_order():
     n = np.arange(256)
-    return ((n >> 3) & 3) * 64 + (n >> 5) * 8 + (n & 7)
+    return ((n >> 2) & 3) * 64 + (n >> 5) * 8 + ((n >> 4) & 1) * 4 + (n & 3)
 
 
 @pytest.mark.parametrize("layer,cg", [(0, 1), (0, 2), (1, 2)])

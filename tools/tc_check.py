@@ -20,8 +20,8 @@ stream = torch.cuda.current_stream().cuda_stream
 
 
 def col_order():
-    n = np.arange(256); jb, gate, u = n >> 5, (n >> 3) & 3, n & 7
-    return gate * 64 + jb * 8 + u
+    n = np.arange(256)
+    return ((n >> 2) & 3) * 64 + (n >> 5) * 8 + ((n >> 4) & 1) * 4 + (n & 3)
 
 
 def gates_ref(layer, d, inp):

@@ -294,6 +294,7 @@ int nsnp_model_pack_weights(const nsnp_model_weights_t* w, void* host_blob, size
 
 size_t nsnp_model_workspace_bytes(int64_t n_sites) {
     int64_t ch = n_sites < kChunkSites ? n_sites : kChunkSites; if (ch < 1) ch = 1;
+    ch = (ch + 127) / 128 * 128;                      // the tensor-core path stores layer-0 output in whole 128-site tiles
     return (size_t)ch * (kT * 128 + 128) * sizeof(float) + 256;
 }
 
@@ -323,7 +324,7 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
     }
     float* h0 = (float*)workspace_dev;
     const int64_t ch = n < kChunkSites ? n : kChunkSites;
-    float* h16 = h0 + ch * kT * 128;
+    float* h16 = h0 + ((ch + 127) / 128 * 128) * kT * 128;
     // n_dev (device-side site count) only makes sense for a single chunk; larger batches are chunked by the host count
     for (int64_t off = 0; off < n; off += ch) {
         const int64_t m = (n - off) < ch ? (n - off) : ch;

@@ -159,6 +159,15 @@ __device__ __forceinline__ uint4 scale_hi(const uint4& hi) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (UBLKCP): one instruction moves a contiguous block, completion is counted on an mbarrier,
+// and the data lands through the async proxy (no generic->async proxy fence needed before the MMAs read it)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
 template <int LAYER> struct TcCfg;
@@ -178,7 +187,7 @@ template <int LAYER, int CG> struct TcSmem {
 // NWQ warps share each TMEM lane quadrant (each thread = one site row x 64/NWQ hidden units).
 // DEBUG: dump the raw accumulators of the first step and return.
 template <int LAYER, int CG, int NWQ, bool DEBUG>
-__global__ void __launch_bounds__(128 * NWQ, (LAYER == 0 && CG == 2 && NWQ == 2) ? 2 : 1)
+__global__ void __launch_bounds__(128 * NWQ + (LAYER == 1 ? 32 : 0), (LAYER == 0 && CG == 2 && NWQ == 2) ? 2 : 1)
 lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict__ xi, const float* __restrict__ xf,
                const __half* __restrict__ h0_in, __half* __restrict__ h0_out, float* __restrict__ h16, float* __restrict__ dbg,
                int64_t n, int dir_override)
@@ -187,17 +196,19 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     using S = TcSmem<LAYER, CG>;
     constexpr int K = C::K, IN = C::IN, RB = S::RB;
     constexpr int KB = K / 16;                                   // MMA k-blocks per pass
-    constexpr int kThreads = 128 * NWQ;
+    constexpr int kThreads = 128 * NWQ + (LAYER == 1 ? 32 : 0);     // layer 1: + one producer warp (bulk copies of the next input)
+    constexpr int kEpiWarps = 4 * NWQ;
     constexpr int UB = 8 / NWQ;                                  // blocks of 8 hidden units per thread
     constexpr uint32_t LBO_A = kRows * 16, LBO_B = RB * 16, SBO = 128;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sBhi = smem + S::off_bhi; unsigned char* sBlo = smem + S::off_blo;
     unsigned char* sAhi = smem + S::off_ahi; unsigned char* sAlo = smem + S::off_alo; unsigned char* sAsc = smem + S::off_asc;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::off_bar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_bar + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_bar + 32);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int quad = warp & 3, sub = warp >> 2;
+    const bool producer = LAYER == 1 && warp == kEpiWarps;       // warp-uniform
+    const int quad = warp & 3, sub = producer ? 0 : (warp >> 2);
     const int row = quad * 32 + lane;                            // site row = TMEM lane
     const int dir = DEBUG ? dir_override : (int)blockIdx.y;
     const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -207,7 +218,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     if (!live) site = n - 1;                                     // clamp loads, skip stores
 
     // ---- one-time setup ----
-    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc<CG>(tmem_slot, LAYER == 1 ? 512 : 256);
     {   // this CTA's weight rows: global [K/8][256][8] halfs -> shared [K/8][RB][8]
         const uint4* ghi = reinterpret_cast<const uint4*>(blob + tc_off(LAYER, dir, 0));
@@ -224,7 +235,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     }
     __syncthreads();
     // constant chunk holding the bias column (1.0) -- layer 0: chunk 2 is rewritten every step with x16, x17
-    if (LAYER == 1 && sub == 0) reinterpret_cast<uint4*>(sAhi + (size_t)(kIn1 / 8) * LBO_A)[row] = make_uint4(0x3C00u, 0, 0, 0);
+    if (LAYER == 1 && sub == 0 && !producer) reinterpret_cast<uint4*>(sAhi + (size_t)(kIn1 / 8) * LBO_A)[row] = make_uint4(0x3C00u, 0, 0, 0);
 
     float c[UB][8];
 #pragma unroll
@@ -272,17 +283,15 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
             reinterpret_cast<uint4*>(sAsc + 2 * LBO_A)[row] = scale_hi(s.hi);
         }
     };
-    auto stage_h0_async = [&](int t) {                               // layer 1: fp16 [site][33][hi|lo][128]
-        if (LAYER != 1) return;
-        const __half* ghi = h0_in + ((site * kT + t) * 2 + 0) * 128;
-        const __half* glo = ghi + 128;
-        constexpr int CH = 16 / NWQ;
-#pragma unroll
-        for (int q = 0; q < CH; ++q) {
-            const int ch = sub * CH + q;
-            cp_async16(sAhi + ch * LBO_A + row * 16, ghi + ch * 8);
-            cp_async16(sAlo + ch * LBO_A + row * 16, glo + ch * 8);
-        }
+    // layer 1: the layer-0 output of one (tile, t) is stored exactly in operand layout, hi part then lo part, 32 KB each:
+    //     h0[tile][t][hi|lo][chunk 16][row 128][8 halfs]
+    uint64_t* barS = bar + 2;                                        // "input part of A for the next step has landed"
+    constexpr uint32_t kPartBytes = 16u * kRows * 16u;               // 32 KB
+    auto stage_h0_bulk = [&](int t) {                                // one thread
+        const __half* src = h0_in + ((size_t)blockIdx.x * kT + t) * (2 * kPartBytes / 2);
+        mbar_expect_tx(barS, 2 * kPartBytes);
+        bulk_g2s(sAhi, src, kPartBytes, barS);
+        bulk_g2s(sAlo, src + kPartBytes / 2, kPartBytes, barS);
     };
     constexpr int XB = IN / 16;                                  // k-blocks of the input part; the rest is the h part
     constexpr uint32_t kTmemCols = LAYER == 1 ? 512 : 256;       // layer 1 double-buffers the accumulator
@@ -290,14 +299,21 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     uint64_t* barX = bar + 1;                                    // layer 1: "input part of the NEXT step is accumulated"
     {
         const int t0 = dir == 0 ? 0 : kT - 1;
-        load_x(t0); store_x(); stage_h0_async(t0);
-        if (LAYER == 1) cp_async_wait_all();
+        load_x(t0); store_x();
         fence_async_smem();
     }
 
     tc_fence_before();
-    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();         // barriers initialised, operands zeroed, TMEM allocated
     tc_fence_after();
+    uint32_t phaseH = 0, phaseX = 0, phaseS = 0;
+    if (LAYER == 1) {
+        if (producer && lane == 0) stage_h0_bulk(dir == 0 ? 0 : kT - 1);
+        mbar_wait(barS, phaseS); phaseS ^= 1;
+        tc_fence_before();
+        if (CG == 2) cluster_sync_all(); else __syncthreads();     // both CTAs of the pair have their first input
+        tc_fence_after();
+    }
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), a_sc = smem_u32(sAsc), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
     constexpr uint32_t idesc = make_idesc(128 * CG, 256);
@@ -317,23 +333,23 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
             }
         }
     };
-    uint32_t phaseH = 0, phaseX = 0;
     if (LAYER == 1) {
         // software pipeline: the input part of step t+1 (27 of 39 MMAs, independent of h_t) runs on the tensor core
         // while the epilogue of step t runs on the SM; only the 12 h-part MMAs stay on the per-step critical path
         if (issuer) { tc_fence_after(); issue(0, XB, tmem_base, 0); umma_commit<CG>(barX); }
-        mbar_wait(barX, phaseX); phaseX ^= 1;
-        tc_fence_after();
-        if (C::STEPS > 1) stage_h0_async(dir == 0 ? 1 : kT - 2);
+        if (producer) {
+            mbar_wait(barX, phaseX); phaseX ^= 1;
+            if (lane == 0 && C::STEPS > 1 && !DEBUG) stage_h0_bulk(dir == 0 ? 1 : kT - 2);
+        }
     }
 
     for (int step = 0; step < C::STEPS; ++step) {
         const int t = dir == 0 ? step : (kT - 1 - step);
         const int tn = dir == 0 ? step + 1 : (kT - 2 - step);
-        const bool more = step + 1 < C::STEPS;
+        const bool more = !DEBUG && step + 1 < C::STEPS;
         const uint32_t acc_cols = LAYER == 1 ? (uint32_t)(step & 1) * 256u : 0u;
         // ---- operands written by the generic proxy -> visible to the tensor core; TMEM reads of the last step retired ----
-        if (LAYER == 1) cp_async_wait_all();
+        if (LAYER == 1 && more) { mbar_wait(barS, phaseS); phaseS ^= 1; }      // the input rows of step t+1 have landed (their MMAs are issued below)
         fence_async_smem();
         tc_fence_before();
         if (CG == 2) cluster_sync_exec(); else __syncthreads();
@@ -348,6 +364,16 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
                 umma_commit<CG>(barH);
             }
         }
+        if (producer) {
+            // producer warp: once the input-part MMAs of step t+1 have completed, their operand region takes the rows of
+            // step t+2 (two 32 KB bulk copies); it never touches TMEM and skips the epilogue
+            if (more) {
+                mbar_wait(barX, phaseX); phaseX ^= 1;
+                if (lane == 0 && step + 2 < C::STEPS) stage_h0_bulk(dir == 0 ? step + 2 : kT - 3 - step);
+            }
+            if (DEBUG) break;
+            continue;
+        }
         if (more) load_x(tn);                                       // global latency hides under the MMAs
         mbar_wait(barH, phaseH);
         phaseH ^= 1;
@@ -360,7 +386,6 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
                 tmem_ld32(tmem_base + acc_cols + ((uint32_t)(quad * 32) << 16) + jb * 32, v);
                 if (live) for (int i = 0; i < 32; ++i) dbg[(site0 + row) * 256 + jb * 32 + i] = v[i];
             }
-            if (LAYER == 1 && more) { mbar_wait(barX, phaseX); phaseX ^= 1; }
             break;
         }
 
@@ -378,8 +403,12 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t* v = vb[hb & 1];
-                const float gi = fminf(fmaxf(__uint_as_float(v[u]), -25.f), 25.f), gf = fminf(fmaxf(__uint_as_float(v[4 + u]), -25.f), 25.f);
-                const float gg = fminf(fmaxf(__uint_as_float(v[8 + u]), -12.5f), 12.5f), go = fminf(fmaxf(__uint_as_float(v[12 + u]), -25.f), 25.f);
+                // only the lower clamps are needed: a very negative gate would give ex2 = +inf and inf * 0 below, a very
+                // positive one gives ex2 = 0, which is exact.  With the clamps every (1 + e) factor is <= 2^36 + 1, so the
+                // triple product stays below 2^108 and its reciprocal stays a normal float.  |c'| <= 33 after 33 steps, so
+                // ex2(-2 c' log2e) <= 2^96 needs no clamp; an overflowing (1 + eo) makes rcp return 0 = the exact limit.
+                const float gi = fmaxf(__uint_as_float(v[u]), -25.f), gf = fmaxf(__uint_as_float(v[4 + u]), -25.f);
+                const float gg = fmaxf(__uint_as_float(v[8 + u]), -12.5f), go = __uint_as_float(v[12 + u]);
                 const float ei = ex2_approx(-kLog2e * gi), ef = ex2_approx(-kLog2e * gf), eg = ex2_approx(-2.f * kLog2e * gg);
                 const float pi = 1.f + ei, pf = 1.f + ef, pg = 1.f + eg;
                 // c' = sigmoid(f) c + sigmoid(i) tanh(g) over one common denominator
@@ -387,8 +416,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
                 const float num = fmaf(c[jl][uh * 4 + u], pig, (1.f - eg) * pf);
                 const float cn = num * rcp_approx(pf * pig);
                 c[jl][uh * 4 + u] = cn;
-                const float cc = fminf(fmaxf(cn, -12.5f), 12.5f);
-                const float ec = ex2_approx(-2.f * kLog2e * cc), eo = ex2_approx(-kLog2e * go);
+                const float ec = ex2_approx(-2.f * kLog2e * cn), eo = ex2_approx(-kLog2e * go);
                 hv[uh * 4 + u] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));        // sigmoid(o) tanh(c')
             }
             if (hb + 1 < 2 * UB) tmem_wait_ld();
@@ -398,20 +426,14 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
                 reinterpret_cast<uint4*>(sAlo + (IN / 8 + jb) * LBO_A)[row] = s.lo;
                 if (live) {
                     if (LAYER == 0) {
-                        __half* o = h0_out + ((site * kT + t) * 2) * 128 + dir * kH + jb * 8;
+                        // layer-1 operand layout h0[tile][t][hi|lo][chunk][row][8]: a warp writes 512 contiguous bytes
+                        __half* o = h0_out + ((((size_t)blockIdx.x * kT + t) * 2) * 16 + (dir * 8 + jb)) * (kRows * 8) + row * 8;
                         *reinterpret_cast<uint4*>(o) = s.hi;
-                        *reinterpret_cast<uint4*>(o + 128) = s.lo;
+                        *reinterpret_cast<uint4*>(o + 16 * kRows * 8) = s.lo;
                     } else if (step == C::STEPS - 1) {
                         float4* o = reinterpret_cast<float4*>(h16 + site * 128 + dir * kH + jb * 8);
                         o[0] = make_float4(hv[0], hv[1], hv[2], hv[3]); o[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
                     }
-                }
-                if (LAYER == 1 && more && jl == 0) {
-                    // half of this thread's epilogue is done and the input-part MMAs of step t+1 (issued ~3.5k cycles
-                    // ago) have finished: their operand region may take the inputs of step t+2 now, so the copies
-                    // land while the second half of the epilogue runs
-                    mbar_wait(barX, phaseX); phaseX ^= 1;
-                    if (step + 2 < C::STEPS) stage_h0_async(dir == 0 ? step + 2 : kT - 3 - step);
                 }
             }
         }
@@ -439,7 +461,7 @@ int launch_one(const void* blob, const int32_t* xi, const float* xf, const void*
     if (CG == 2 && (gx & 1)) ++gx;                               // whole clusters; the padding CTA works on clamped rows
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(gx, DEBUG ? 1 : 2, 1);
-    cfg.blockDim = dim3(128 * NWQ, 1, 1);
+    cfg.blockDim = dim3(128 * NWQ + (LAYER == 1 ? 32 : 0), 1, 1);
     cfg.dynamicSmemBytes = S::total;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];

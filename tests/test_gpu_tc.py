@@ -15,6 +15,16 @@ def weights(golden_weights):
     return PileupModelWeights(*golden_weights, device="cuda:0")
 
 
+def _tile_layout(hi, lo):
+    """[m][33][128] hi / lo -> layer-1 operand layout [tile][33][hi|lo][chunk 16][row 128][8]"""
+    m = hi.shape[0]; tiles = (m + 127) // 128
+    out = np.zeros((tiles, 33, 2, 16, 128, 8), np.float16)
+    for part, a in enumerate((hi, lo)):
+        pad = np.zeros((tiles * 128, 33, 128), np.float16); pad[:m] = a
+        out[:, :, part] = pad.reshape(tiles, 128, 33, 16, 8).transpose(0, 2, 3, 1, 4)
+    return out
+
+
 def _col_order():
     n = np.arange(256)
     return ((n >> 2) & 3) * 64 + (n >> 5) * 8 + ((n >> 4) & 1) * 4 + (n & 3)
@@ -35,7 +45,7 @@ def test_umma_operand_layout_first_step_gates(weights, golden_weights, small_cas
     else:
         h = rng.uniform(-1, 1, size=(m, 33, 128)).astype(np.float32)
         hi = h.astype(np.float16); lo = (h - hi.astype(np.float32)).astype(np.float16)
-        h0 = torch.from_numpy(np.stack([hi, lo], axis=2).copy()).cuda(); xi = None
+        h0 = torch.from_numpy(_tile_layout(hi, lo)).cuda(); xi = None
         xin = hi.astype(np.float64) + lo.astype(np.float64)
     for d in (0, 1):
         sfx = "_reverse" if d else ""

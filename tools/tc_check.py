@@ -19,6 +19,15 @@ W = PileupModelWeights(enc, fwd, device="cuda:0")
 stream = torch.cuda.current_stream().cuda_stream
 
 
+def _tile_layout(hi, lo):
+    m = hi.shape[0]; tiles = (m + 127) // 128
+    out = np.zeros((tiles, 33, 2, 16, 128, 8), np.float16)
+    for part, a in enumerate((hi, lo)):
+        pad = np.zeros((tiles * 128, 33, 128), np.float16); pad[:m] = a
+        out[:, :, part] = pad.reshape(tiles, 128, 33, 16, 8).transpose(0, 2, 3, 1, 4)
+    return out
+
+
 def col_order():
     n = np.arange(256)
     return ((n >> 2) & 3) * 64 + (n >> 5) * 8 + ((n >> 4) & 1) * 4 + (n & 3)
@@ -56,7 +65,7 @@ elif what == "gates1_cg2":
     m = 300
     h = rng.uniform(-1, 1, size=(m, 33, 128)).astype(np.float32)
     hi = h.astype(np.float16); lo = (h - hi.astype(np.float32)).astype(np.float16)
-    h0 = torch.from_numpy(np.stack([hi, lo], axis=2).copy()).cuda()          # [m][33][2][128]
+    h0 = torch.from_numpy(_tile_layout(hi, lo)).cuda()
     for d in (0, 1):
         t = 0 if d == 0 else 32
         got = run_gates(1, d, 2, None, h0, m)

@@ -161,6 +161,15 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
 int nsnp_debug_lstm_tc_gates(const void* blob_dev, const int32_t* x_i32_dev, int layer, int dir, int cg, const void* h0_dev,
                              float* gates_out_dev, int64_t m, void* stream);
 
+/* ---- per-kernel timing (bench.py) ---------------------------------------------------------------
+ * When enabled, every kernel launch of this library is bracketed by cudaEventRecord on the launching stream.
+ * nsnp_profile_read synchronises, adds the elapsed times per kernel slot into ms_out[NSNP_PROF_SLOTS] and
+ * launches_out[NSNP_PROF_SLOTS], and clears the pending events.  Slots: */
+enum { NSNP_PROF_READ_SCAN = 0, NSNP_PROF_PILEUP_TILE, NSNP_PROF_SELECT, NSNP_PROF_GATHER, NSNP_PROF_LSTM0, NSNP_PROF_LSTM1,
+       NSNP_PROF_TAIL, NSNP_PROF_SLOTS };
+void nsnp_profile_enable(int on);
+int  nsnp_profile_read(double* ms_out, int64_t* launches_out);
+
 /* ---- status / utilities ----------------------------------------------------------------------- */
 /* copies status_dev[0..3] to the host (synchronises the stream) and maps it to an NSNP_E_* code */
 int nsnp_check_status(const int32_t* status_dev, void* stream);

@@ -17,6 +17,7 @@ CHANNELS, FLANK, WINDOW = 18, 16, 33
 GT_CLASSES, ZY_CLASSES = 21, 3
 F_COVERED, F_GATE = 1, 2
 PREC_FP32, PREC_F16X3 = 0, 1
+PROF_SLOTS = ("read_scan_kernel", "pileup_tile_kernel", "select_kernels", "gather_kernel", "lstm_layer0", "lstm_layer1", "tail_kernel")
 
 
 class NsnpError(RuntimeError):
@@ -85,6 +86,8 @@ SYMBOLS = {
     "nsnp_model_workspace_bytes": (_SZ, [_I64]),
     "nsnp_pileup_model_forward": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _SZ, C.c_int, _P]),
     "nsnp_debug_lstm_tc_gates": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _I64, _P]),
+    "nsnp_profile_enable": (None, [C.c_int]),
+    "nsnp_profile_read": (C.c_int, [_P, _P]),
     "nsnp_check_status": (C.c_int, [_P, _P]),
     "nsnp_vcf_format_batch": (_I64, [C.c_char_p, _I64, _P, _P, _P, _P, _P, _P, _I64]),
     "nsnp_synth_ref_host": (C.c_int, [C.POINTER(SynthCfg), _P]),

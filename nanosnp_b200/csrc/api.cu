@@ -1,5 +1,7 @@
 // C-ABI plumbing: error reporting, defaults, device-side status decoding.
 #include <stdarg.h>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace nsnp {
@@ -20,9 +22,54 @@ int cuda_status(const char* what) {
     return set_error(NSNP_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
+// ---- per-kernel timing ----------------------------------------------------------------------------
+struct ProfPending { int slot; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfPending> g_prof_pending;
+static std::vector<cudaEvent_t> g_prof_pool;
+static std::mutex g_prof_mu;
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+ProfScope::ProfScope(int slot_, cudaStream_t s) : slot(slot_), stream(s), pending(nullptr) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfPending* p = new ProfPending{slot, prof_event(), prof_event()};
+    cudaEventRecord(p->a, stream);
+    pending = p;
+}
+ProfScope::~ProfScope() {
+    if (!pending) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfPending* p = (ProfPending*)pending;
+    cudaEventRecord(p->b, stream);
+    g_prof_pending.push_back(*p);
+    delete p;
+}
+
 }  // namespace nsnp
 
 extern "C" {
+
+void nsnp_profile_enable(int on) { nsnp::g_prof_on = on != 0; }
+
+int nsnp_profile_read(double* ms_out, int64_t* launches_out) {
+    std::lock_guard<std::mutex> lk(nsnp::g_prof_mu);
+    for (int i = 0; i < NSNP_PROF_SLOTS; ++i) { if (ms_out) ms_out[i] = 0.0; if (launches_out) launches_out[i] = 0; }
+    for (auto& p : nsnp::g_prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) != cudaSuccess || cudaEventElapsedTime(&ms, p.a, p.b) != cudaSuccess)
+            return nsnp::set_error(NSNP_E_CUDA, "nsnp_profile_read: %s", cudaGetErrorString(cudaGetLastError()));
+        if (ms_out) ms_out[p.slot] += ms;
+        if (launches_out) launches_out[p.slot] += 1;
+        nsnp::g_prof_pool.push_back(p.a); nsnp::g_prof_pool.push_back(p.b);
+    }
+    nsnp::g_prof_pending.clear();
+    return NSNP_OK;
+}
+
 
 int nsnp_abi_version(void) { return NSNP_ABI_VERSION; }
 const char* nsnp_last_error(void) { return nsnp::g_err; }

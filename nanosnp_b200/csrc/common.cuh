@@ -11,6 +11,13 @@ namespace nsnp {
 int set_error(int code, const char* fmt, ...);   // records a thread-local message, returns code
 int cuda_status(const char* what);               // maps cudaGetLastError() to NSNP_E_CUDA / NSNP_OK
 
+// RAII bracket around one kernel launch when profiling is on (api.cu)
+struct ProfScope {
+    int slot; cudaStream_t stream; void* pending;
+    ProfScope(int slot_, cudaStream_t s);
+    ~ProfScope();
+};
+
 constexpr int kNumSMs = 148;                     // B200: 2 dies x 74 SMs
 
 // device-side status words (status_dev[4])

@@ -335,9 +335,10 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
         if (precision == NSNP_PREC_F16X3) {
             if (int e = launch_lstm_tc(blob_dev, xi, xf, h0, h16, m, stream)) return e;
         } else {
-            lstm_dir_kernel<0><<<g0, 256, smem0, stream>>>(blob, xi, xf, nullptr, h0, m, nd);
-            lstm_dir_kernel<1><<<g1, 256, smem1, stream>>>(blob, nullptr, nullptr, h0, h16, m, nd);
+            { ProfScope prof(NSNP_PROF_LSTM0, stream); lstm_dir_kernel<0><<<g0, 256, smem0, stream>>>(blob, xi, xf, nullptr, h0, m, nd); }
+            { ProfScope prof(NSNP_PROF_LSTM1, stream); lstm_dir_kernel<1><<<g1, 256, smem1, stream>>>(blob, nullptr, nullptr, h0, h16, m, nd); }
         }
+        ProfScope prof(NSNP_PROF_TAIL, stream);
         tail_kernel<<<(unsigned)((m + kTailS - 1) / kTailS), 256, kTailSmem, stream>>>(blob, h16, m, nd, gt_prob_dev + off * 21, zy_prob_dev + off * 3);
         if (int e = cuda_status("pileup model kernels")) return e;
     }

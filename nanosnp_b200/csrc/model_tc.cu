@@ -477,8 +477,9 @@ int launch_one(const void* blob, const int32_t* xi, const float* xf, const void*
 
 int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, cudaStream_t stream) {
     // layer 0: CTA pairs share W (53 KB each) so two CTAs fit per SM and one CTA's MMAs overlap the other's epilogue
-    if (int e = launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e;
+    { ProfScope prof(NSNP_PROF_LSTM0, stream); if (int e = launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e; }
     // layer 1: W only fits split across a CTA pair (2 x 104 KB); one CTA per SM, 16 warps for the epilogue
+    ProfScope prof(NSNP_PROF_LSTM1, stream);
     return launch_one<1, 2, 4, false>(blob, nullptr, nullptr, h0, nullptr, h16, nullptr, m, 0, stream);
 }
 

@@ -536,6 +536,7 @@ int nsnp_pileup_counts(const nsnp_reads_t* reads, const uint8_t* ref_dev, int64_
     if (reads->n_reads > 0) {
         const int64_t warps = reads->n_reads;
         int blocks = (int)((warps + 7) / 8); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        ProfScope prof(NSNP_PROF_READ_SCAN, stream);
         read_scan_kernel<<<blocks, 256, 0, stream>>>(*reads, *params, region_start, region_start + region_len, tile_shift, w);
         if (int e = cuda_status("read_scan_kernel")) return e;
     }
@@ -552,6 +553,7 @@ int nsnp_pileup_counts(const nsnp_reads_t* reads, const uint8_t* ref_dev, int64_
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pileup_tile_kernel<T>, kThreads, smem);
         if (occ < 1) occ = 1; if (occ > 4) occ = 4;
         int grid = kNumSMs * occ; if (grid > n_tiles) grid = n_tiles; if (grid > kMaxCtas) grid = kMaxCtas;
+        ProfScope prof(NSNP_PROF_PILEUP_TILE, stream);
         pileup_tile_kernel<T><<<grid, kThreads, smem, stream>>>(*reads, *params, ref_dev, region_start, region_len, n_tiles, w,
                                                               counts_dev, flags_dev, status_dev);
         if (int e = cuda_status("pileup_tile_kernel")) return e;

@@ -238,6 +238,7 @@ int nsnp_select_candidates(const int32_t* counts_dev, uint8_t* flags_dev, const 
         regate_kernel<<<blocks, 256, 0, stream>>>(counts_dev, flags_dev, ref_dev, region_start, region_len, *params);
         if (int e = cuda_status("regate_kernel")) return e;
     }
+    ProfScope prof(NSNP_PROF_SELECT, stream);
     SelArgs a{flags_dev, region_start, region_len, emit_start, emit_end};
     const int n_seg = (int)((region_len + kSeg - 1) / kSeg);
     int32_t* seg = (int32_t*)workspace_dev;
@@ -259,6 +260,7 @@ int nsnp_gather_windows(const int32_t* counts_dev, const uint8_t* ref_dev, int64
     if (nsnp_device_count() == 0) return set_error(NSNP_E_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
     if (n_max <= 0) return NSNP_OK;
     int64_t blocks = (n_max + 7) / 8; if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    ProfScope prof(NSNP_PROF_GATHER, stream);
     gather_kernel<<<(int)blocks, 256, 0, stream>>>(counts_dev, ref_dev, region_start, region_len, pos_dev, n_dev, n_max, x_i32_dev, x_f32_dev, refbase_dev);
     return cuda_status("gather_kernel");
 }

@@ -157,6 +157,7 @@ def main_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line (NCCL prints its version at INFO/VERSION)
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic workload: one contig per rank, generated on the GPU, cut into regions with 16-bp halos ----

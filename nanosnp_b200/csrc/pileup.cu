@@ -174,62 +174,79 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
         R += __shfl_sync(0xffffffffu, ri, 31);
         Q += __shfl_sync(0xffffffffu, qi, 31);
 
-        if (op_aligned(op)) {
-            const int64_t a = rs > ts ? rs : ts, b = (rs + len) < te ? (rs + len) : te;
-            if (a < b) {
-                const int pa = (int)(a - ts), n = (int)(b - a);
-                atomicAdd(&sm.ms[pa], sinc);
-                if (b < te) atomicAdd(&sm.me[pa + n], sinc);
-                const int64_t g = sbase + qs + (a - rs);
-                for (int o = 0; o < n; o += 16) {
-                    const int m = min(16, n - o);
-                    const uint32_t sw = bases16_g(seqw, g + o);
-                    const uint32_t rw = bases16(sm.ref2, pa + o);
-                    uint32_t x = sw ^ rw;
-                    uint32_t mm = (x | (x >> 1)) & 0x55555555u;
-                    if (ref_has_x) mm |= bases16(sm.refx, pa + o);
-                    if (m < 16) mm &= (1u << (2 * m)) - 1u;
-                    if (nmw) {
-                        uint32_t nb = bits16_g(nmw, g + o);
-                        if (m < 16) nb &= (1u << m) - 1u;
-                        if (nb) {
-                            mm &= ~spread16(nb);
-                            while (nb) { const int j = __ffs(nb) - 1; nb &= nb - 1; atomicAdd(&sm.nn[pa + o + j], sinc); }
-                        }
-                    }
-                    while (mm) {
-                        const int j2 = __ffs(mm) - 1; mm &= mm - 1;
-                        const int bcode = (sw >> j2) & 3;
-                        atomicAdd(&sm.base[strand * 2 + (bcode >> 1)][pa + o + (j2 >> 1)], 1u << (16 * (bcode & 1)));
-                    }
-                }
+        // ---- phase 1: one lane per CIGAR op, straight-line predicated bookkeeping ----
+        const bool aligned = op_aligned(op), isdel = op == 2;
+        const int64_t a = rs > ts ? rs : ts, b = (rs + len) < te ? (rs + len) : te;      // clipped reference span
+        const bool span = (aligned || isdel) && a < b;
+        if (span) {                                                                      // run boundaries (depth = prefix sum later)
+            uint32_t* st = aligned ? sm.ms : sm.ds;
+            uint32_t* en = aligned ? sm.me : sm.de;
+            atomicAdd(&st[(int)(a - ts)], sinc);
+            if (b < te) atomicAdd(&en[(int)(b - ts)], sinc);
+        }
+        // indel event anchored at the preceding reference position (appendix A.8 iii/iv); leading ops are never reported
+        const int64_t anchor = rs - 1;
+        if ((op == 1 || isdel) && len <= NSNP_MAX_INDEL && rs > rpos && anchor >= ts && anchor < te) {
+            const int cls = (isdel ? 2 : 0) + strand;
+            const int e = atomicAdd(&sm.n_events, 1);
+            atomicAdd(&sm.cnt4[(int)(anchor - ts)], 1u << (8 * cls));
+            if (e < ws.slab_cap) {
+                Event ev;
+                ev.next = atomicExch(&sm.head[(int)(anchor - ts)], (uint32_t)e);
+                ev.info = (uint32_t)len | ((uint32_t)cls << 8);
+                ev.seq = (uint64_t)(sbase + qs);
+                slab[e] = ev;
+            } else {
+                dev_fail(status, DEV_E_INDEL_SLAB, sm.tile);
             }
-        } else if (op == 2 || op == 1) {
-            if (op == 2) {
-                const int64_t a = rs > ts ? rs : ts, b = (rs + len) < te ? (rs + len) : te;
-                if (a < b) {
-                    atomicAdd(&sm.ds[(int)(a - ts)], sinc);
-                    if (b < te) atomicAdd(&sm.de[(int)(b - ts)], sinc);
-                }
-            }
-            // indel event anchored at the preceding reference position (appendix A.8 iii/iv); leading ops are never reported
-            const int64_t anchor = rs - 1;
-            if (len <= NSNP_MAX_INDEL && rs > rpos && anchor >= ts && anchor < te) {
-                const int e = atomicAdd(&sm.n_events, 1);
-                atomicAdd(&sm.cnt4[(int)(anchor - ts)], 1u << (8 * ((op == 2 ? 2 : 0) + strand)));
-                if (e < ws.slab_cap) {
-                    Event ev;
-                    ev.next = atomicExch(&sm.head[(int)(anchor - ts)], (uint32_t)e);
-                    ev.info = (uint32_t)len | ((uint32_t)((op == 2 ? 2 : 0) + strand) << 8);
-                    ev.seq = (uint64_t)(sbase + qs);
-                    slab[e] = ev;
-                } else {
-                    dev_fail(status, DEV_E_INDEL_SLAB, sm.tile);
-                }
-            }
-        } else if (op == 3) {
-            const int64_t a = rs > ts ? rs : ts, b = (rs + len) < te ? (rs + len) : te;
+        }
+        if (op == 3) {                                                                   // reference skip: covered, nothing counted
             for (int64_t p = a; p < b; ++p) atomicOr(&sm.skipcov[(int)(p - ts) >> 5], 1u << ((int)(p - ts) & 31));
+        }
+
+        // ---- phase 2: mismatch detection, one lane per 16-base word of any aligned run of this chunk.  The words of
+        //      all 32 ops are flattened (warp scan) so long runs do not leave the other lanes idle. ----
+        const int n = (aligned && a < b) ? (int)(b - a) : 0;
+        const int nw = (n + 15) >> 4;
+        const int winc = warp_incl_scan(nw);
+        const int W = __shfl_sync(0xffffffffu, winc, 31);
+        const int pa = (int)(a - ts);
+        const int64_t g = sbase + qs + (a - rs);
+        for (int wb = 0; wb < W; wb += 32) {
+            const int f = wb + lane;
+            // owner = number of lanes whose inclusive word count is <= f (binary search across lanes)
+            int j = 0;
+#pragma unroll
+            for (int stp = 16; stp >= 1; stp >>= 1) { const int v = __shfl_sync(0xffffffffu, winc, j + stp - 1); if (v <= f) j += stp; }
+            const int ex_j = __shfl_sync(0xffffffffu, winc - nw, j);
+            const int pa_j = __shfl_sync(0xffffffffu, pa, j);
+            const int n_j = __shfl_sync(0xffffffffu, n, j);
+            const uint32_t glo = __shfl_sync(0xffffffffu, (uint32_t)g, j), ghi = __shfl_sync(0xffffffffu, (uint32_t)((uint64_t)g >> 32), j);
+            if (f < W) {
+                const int o = (f - ex_j) << 4;
+                const int m = min(16, n_j - o);
+                const int64_t gw = (int64_t)(((uint64_t)ghi << 32) | glo) + o;
+                const int pw = pa_j + o;
+                const uint32_t sw = bases16_g(seqw, gw);
+                const uint32_t rw = bases16(sm.ref2, pw);
+                uint32_t x = sw ^ rw;
+                uint32_t mm = (x | (x >> 1)) & 0x55555555u;
+                if (ref_has_x) mm |= bases16(sm.refx, pw);
+                if (m < 16) mm &= (1u << (2 * m)) - 1u;
+                if (nmw) {
+                    uint32_t nb = bits16_g(nmw, gw);
+                    if (m < 16) nb &= (1u << m) - 1u;
+                    if (nb) {
+                        mm &= ~spread16(nb);
+                        while (nb) { const int q = __ffs(nb) - 1; nb &= nb - 1; atomicAdd(&sm.nn[pw + q], sinc); }
+                    }
+                }
+                while (mm) {
+                    const int j2 = __ffs(mm) - 1; mm &= mm - 1;
+                    const int bcode = (sw >> j2) & 3;
+                    atomicAdd(&sm.base[strand * 2 + (bcode >> 1)][pw + (j2 >> 1)], 1u << (16 * (bcode & 1)));
+                }
+            }
         }
     }
 }

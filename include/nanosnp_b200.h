@@ -184,6 +184,12 @@ int64_t nsnp_vcf_format_batch(const char* contig, int64_t n, const int32_t* pos1
                               const float* gt_prob, const float* zy_prob, const float* cov8,
                               char* out, int64_t out_capacity);
 
+/* Whole contig file: consecutive batches of batch_size sites (predict.py:43 DataLoader(batch_size, shuffle=False)),
+ * formatted on n_threads host threads with hand-rolled number formatting (same bytes as nsnp_vcf_format_batch). */
+int64_t nsnp_vcf_format_contig(const char* contig, int64_t n, const int32_t* pos1, const uint8_t* refbase,
+                               const float* gt_prob, const float* zy_prob, const float* cov8, int64_t batch_size,
+                               int n_threads, char* out, int64_t out_capacity);
+
 /* ---- synthetic inputs (bench / tests) --------------------------------------- */
 typedef struct nsnp_synth_cfg {
     uint64_t seed_ref, seed_var, seed_reads;

@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     (objdir / "ptxas.log").write_text("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart", "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart", "-lcuda", "-lpthread"]
     subprocess.run(cmd, check=True)
     return LIB
 

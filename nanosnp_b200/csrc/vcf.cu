@@ -150,3 +150,202 @@ extern "C" int64_t nsnp_vcf_format_batch(const char* contig, int64_t n, const in
     if (o.n > o.cap) return -o.n;
     return o.n;
 }
+
+
+// ===================================================================================================
+// Fast path: same records, hand-rolled number formatting, batches formatted on host threads.
+// Every shortcut falls back to the libc path above whenever its exactness argument does not hold.
+// ===================================================================================================
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+inline char* put_uint(char* p, unsigned long long v) {
+    char tmp[24]; int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+// QUAL: str(float(round(v, 2))) and int(...) of it.  v >= 0.  round() is correct rounding of the exact binary value
+// to 2 decimals (half-even on exact ties); v*100 is inexact, so anything within 1e-6 of a tie goes the libc way.
+inline char* put_qual(char* p, double v, long long* int_part) {
+    const double t = v * 100.0;
+    const double fl = floor(t);
+    const double fr = t - fl;
+    long long q100;
+    if (fabs(fr - 0.5) < 1e-6 || !(t < 9.0e15)) {
+        char buf[64]; snprintf(buf, sizeof buf, "%.2f", v);
+        const double r = strtod(buf, nullptr);
+        q100 = (long long)floor(r * 100.0 + 0.5);
+    } else {
+        q100 = (long long)fl + (fr > 0.5 ? 1 : 0);
+    }
+    const long long ip = q100 / 100; const int f2 = (int)(q100 % 100);
+    *int_part = ip;
+    p = put_uint(p, (unsigned long long)ip);
+    *p++ = '.';
+    *p++ = (char)('0' + f2 / 10);
+    if (f2 % 10) *p++ = (char)('0' + f2 % 10);
+    return p;
+}
+
+// '%f' % af: af is a float32 quotient in [0, 1] (or nan); float32 * 1e6 is exact in double, so the correctly rounded
+// 6-decimal value (half-even on exact ties, as printf does) follows from the exact product.
+inline char* put_af(char* p, float af, bool af_one) {
+    if (af_one) { memcpy(p, "1.000000", 8); return p + 8; }
+    if (af != af) { memcpy(p, "nan", 3); return p + 3; }
+    const double r = (double)af * 1.0e6;
+    if (!(r >= 0.0) || r > 1.0e6) { const int n = snprintf(p, 32, "%f", (double)af); return p + n; }
+    double q = floor(r); const double fr = r - q;
+    if (fr > 0.5 || (fr == 0.5 && fmod(q, 2.0) == 1.0)) q += 1.0;
+    const unsigned long long u = (unsigned long long)q;
+    p = put_uint(p, u / 1000000ull);
+    *p++ = '.';
+    unsigned long long f = u % 1000000ull;
+    char d[6]; for (int i = 5; i >= 0; --i) { d[i] = (char)('0' + f % 10); f /= 10; }
+    memcpy(p, d, 6);
+    return p + 6;
+}
+
+inline bool calc_score_fast(float p, double* out) {
+    const float a = 1.0f - p;
+    const float r = a / p;
+    const double x = (double)r;
+    if (!(x > 0.0)) return false;
+    static const double kScale = -10.0 * (1.0 / log(10.0));
+    volatile double t = kScale * log(x);
+    t = t + 10.0;
+    *out = t > 0.0 ? t : 0.0;          // unrounded: put_qual rounds
+    return true;
+}
+
+inline char* put_record(char* p, const char* contig, size_t clen, long long pos, char ref, const char* alt, double q, const char* filter,
+                        const char* zy, float depth, float af, bool af_one)
+{
+    memcpy(p, contig, clen); p += clen; *p++ = '\t';
+    p = put_uint(p, (unsigned long long)pos);
+    *p++ = '\t'; *p++ = '.'; *p++ = '\t'; *p++ = ref; *p++ = '\t';
+    for (const char* a = alt; *a; ++a) *p++ = *a;
+    *p++ = '\t';
+    long long qi = 0;
+    p = put_qual(p, q, &qi);
+    *p++ = '\t';
+    for (const char* a = filter; *a; ++a) *p++ = *a;
+    memcpy(p, "\t.\tGT:GQ:DP:AF\t", 15); p += 15;
+    for (const char* a = zy; *a; ++a) *p++ = *a;
+    *p++ = ':';
+    p = put_uint(p, (unsigned long long)qi);
+    *p++ = ':';
+    const long long dp = (long long)depth;
+    if (dp < 0) { *p++ = '-'; p = put_uint(p, (unsigned long long)(-dp)); } else p = put_uint(p, (unsigned long long)dp);
+    *p++ = ':';
+    p = put_af(p, af, af_one);
+    *p++ = '\n';
+    return p;
+}
+
+// one batch (predict.py:54-194), appended to `o`
+void format_batch_fast(std::string& o, const char* contig, size_t clen, int64_t n, const int32_t* pos1, const uint8_t* refbase,
+                       const float* gt_prob, const float* zy_prob, const float* cov8)
+{
+    int head_gt[10];
+    const int nhead = n < 10 ? (int)n : 10;
+    auto argmax = [](const float* v, int m) { int b = 0; for (int i = 1; i < m; ++i) if (v[i] > v[b]) b = i; return b; };
+    for (int i = 0; i < nhead; ++i) head_gt[i] = argmax(gt_prob + (size_t)i * 21, 21);
+    char line[256 + 64];
+    for (int64_t j = 0; j < n; ++j) {
+        const float* gp = gt_prob + j * 21; const float* zp = zy_prob + j * 3;
+        const int gt = argmax(gp, 21), zyo = argmax(zp, 3);
+        if (gt >= 10) continue;
+        const char sref = (char)refbase[j];
+        const char* label = kGt[gt];
+        const char* zy = kZy[zyo];
+        const float* cov = cov8 + j * 8;
+        float neg = 0.f; for (int k = 0; k < 8; ++k) if (cov[k] < 0.f) neg += cov[k];
+        const float depth = -1.0f * neg;
+        char alt[4]; int na = 0;
+        for (int k = 0; k < 2; ++k) if (label[k] != sref) alt[na++] = label[k];
+        alt[na] = 0;
+        float support = 0.f; bool bad = false;
+        for (int k = 0; k < na; ++k) { const int b = base_idx(alt[k]); if (b < 0) { bad = true; break; } support += cov[b]; support += cov[b + 4]; }
+        if (bad) continue;
+        const float af = support / depth;
+        const bool af_one = af > 1.0f;
+        double gt_q, zy_q;
+        if (!calc_score_fast(gp[gt], &gt_q)) continue;
+        if (!calc_score_fast(zp[zyo], &zy_q)) continue;
+        // min() of the ROUNDED values in Python; rounding is monotone, so the smaller unrounded value rounds to the minimum
+        const double qual = gt_q < zy_q ? gt_q : zy_q;
+        char* e = nullptr;
+        if (na == 0) {
+            if (zyo == 0) {
+                const char a1[2] = {sref, 0};
+                e = put_record(line, contig, clen, pos1[j], sref, a1, qual, "RefCall", zy, depth, af, af_one);
+            } else {
+                static const int tis_hom[4] = {0, 4, 7, 9};
+                static const int tis_het[6] = {1, 2, 3, 5, 6, 8};
+                const int* tis = zyo == 1 ? tis_hom : tis_het; const int nt = zyo == 1 ? 4 : 6;
+                int max_ti = -1, max_v = -1; bool raised = false;
+                for (int q = 0; q < nt; ++q) {
+                    const int ti = tis[q];
+                    if (zyo == 1 && kGt[ti][0] == sref) continue;
+                    if (ti >= n) { raised = true; break; }
+                    if (head_gt[ti] > max_v) { max_v = head_gt[ti]; max_ti = ti; }
+                }
+                if (raised) continue;
+                char a1[2] = {0, 0};
+                if (zyo == 1) a1[0] = kGt[max_ti][0]; else a1[0] = kGt[max_ti][0] == sref ? kGt[max_ti][1] : kGt[max_ti][0];
+                e = put_record(line, contig, clen, pos1[j], sref, a1, zy_q, "PASS", zy, depth, af, af_one);
+            }
+        } else {
+            char alts[8];
+            if (na == 1) { alts[0] = alt[0]; alts[1] = 0; }
+            else if (alt[0] == alt[1]) { alts[0] = alt[0]; alts[1] = 0; }
+            else { alts[0] = alt[0]; alts[1] = ','; alts[2] = alt[1]; alts[3] = 0; }
+            if (alts[1] == ',' && zyo != 2) zy = "1/2";
+            e = put_record(line, contig, clen, pos1[j], sref, alts, zyo == 0 ? gt_q : qual, "PASS", zy, depth, af, af_one);
+        }
+        o.append(line, (size_t)(e - line));
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t nsnp_vcf_format_contig(const char* contig, int64_t n, const int32_t* pos1, const uint8_t* refbase,
+                                          const float* gt_prob, const float* zy_prob, const float* cov8, int64_t batch_size,
+                                          int n_threads, char* out, int64_t out_capacity)
+{
+    if (!contig || n < 0 || batch_size <= 0 || (n > 0 && (!pos1 || !refbase || !gt_prob || !zy_prob || !cov8))) return 0;
+    const size_t clen = strlen(contig);
+    if (clen > 200) return 0;
+    const int64_t n_batches = (n + batch_size - 1) / batch_size;
+    int nt = n_threads < 1 ? 1 : n_threads;
+    if ((int64_t)nt > n_batches) nt = (int)(n_batches > 0 ? n_batches : 1);
+    std::vector<std::string> parts((size_t)nt);
+    auto work = [&](int t) {
+        const int64_t b0 = n_batches * t / nt, b1 = n_batches * (t + 1) / nt;
+        std::string o;                      // thread-local: the string headers in `parts` share cache lines
+        o.reserve((size_t)((b1 - b0) * batch_size) * (72 + clen));
+        for (int64_t b = b0; b < b1; ++b) {
+            const int64_t s = b * batch_size, m = (n - s) < batch_size ? (n - s) : batch_size;
+            format_batch_fast(o, contig, clen, m, pos1 + s, refbase + s, gt_prob + s * 21, zy_prob + s * 3, cov8 + s * 8);
+        }
+        parts[(size_t)t] = std::move(o);
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    int64_t total = 0;
+    for (auto& s2 : parts) total += (int64_t)s2.size();
+    if (!out || total > out_capacity) return -total;
+    char* p = out;
+    for (auto& s2 : parts) { memcpy(p, s2.data(), s2.size()); p += s2.size(); }
+    return total;
+}

@@ -37,28 +37,76 @@ def write_head(reference_index_file, fwriter):                     # predict.py:
     fwriter.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tSample\n")
 
 
-def format_records(contig: str, positions, reference_bases, gt: np.ndarray, zy: np.ndarray, cov8: np.ndarray, batch_size: int) -> str:
-    """All records of one contig file, batch by batch (host arrays)."""
+def format_records(contig: str, positions, reference_bases, gt: np.ndarray, zy: np.ndarray, cov8: np.ndarray, batch_size: int,
+                   n_threads: int = 0) -> bytes:
+    """All records of one contig file, consecutive batches of batch_size sites (host arrays) -> VCF text bytes."""
     lib = _lib.load()
     n = len(positions)
+    if n == 0:
+        return b""
     pos = np.ascontiguousarray(positions, np.int32); refb = np.ascontiguousarray(reference_bases, np.uint8)
     gt = np.ascontiguousarray(gt, np.float32); zy = np.ascontiguousarray(zy, np.float32); cov8 = np.ascontiguousarray(cov8, np.float32)
-    out = []
-    cap = batch_size * (128 + len(contig)) + 64
-    buf = C.create_string_buffer(cap)
-    for b in range(0, n, batch_size):
-        m = min(n, b + batch_size) - b
-        w = lib.nsnp_vcf_format_batch(contig.encode(), m, pos[b:].ctypes.data, refb[b:].ctypes.data, gt[b:].ctypes.data,
-                                      zy[b:].ctypes.data, cov8[b:].ctypes.data, C.addressof(buf), cap)
-        if w < 0:
-            raise _lib.NsnpError(_lib.E_WORKSPACE, "VCF batch buffer too small")
-        out.append(buf.raw[:w].decode())
-    return "".join(out)
+    cap = n * (80 + len(contig)) + 64
+    buf = np.empty(cap, np.uint8)
+    w = lib.nsnp_vcf_format_contig(contig.encode(), n, pos.ctypes.data, refb.ctypes.data, gt.ctypes.data, zy.ctypes.data,
+                                   cov8.ctypes.data, batch_size, n_threads or (os.cpu_count() or 1), buf.ctypes.data, cap)
+    if w < 0:
+        raise _lib.NsnpError(_lib.E_WORKSPACE, "VCF buffer too small")
+    return buf[:w].tobytes()
+
+
+class ContigVcfAssembler:
+    """Streams one contig's sites region by region into VCF text while keeping the reference's batch composition:
+    records are formatted in consecutive batches of `batch_size` sites counted from the contig's first site
+    (predict.py:43), so a region boundary in the middle of a batch carries the partial batch over to the next region."""
+
+    def __init__(self, contig: str, batch_size: int = 1000, n_threads: int = 0, sink=None):
+        self.contig, self.batch, self.threads, self.sink = contig, batch_size, n_threads, sink
+        self.carry = None
+        self.n_bytes = 0
+        self.n_sites = 0
+
+    def _emit(self, pos1, refb, gt, zy, cov8):
+        text = format_records(self.contig, pos1, refb, gt, zy, cov8, self.batch, self.threads)
+        self.n_bytes += len(text)
+        if self.sink is not None:
+            self.sink.write(text)
+
+    def add(self, pos0, refbase, gt, zy, cov8):
+        """Host arrays of one region, ascending positions (0-based)."""
+        n = len(pos0)
+        self.n_sites += n
+        pos1 = np.asarray(pos0, np.int32) + 1
+        arrs = [pos1, np.asarray(refbase), np.asarray(gt), np.asarray(zy), np.asarray(cov8)]
+        start = 0
+        if self.carry is not None:
+            need = self.batch - len(self.carry[0])
+            take = min(need, n)
+            merged = [np.concatenate([c, a[:take]]) for c, a in zip(self.carry, arrs)]
+            start = take
+            if len(merged[0]) == self.batch:
+                self._emit(*merged)
+                self.carry = None
+            else:
+                self.carry = merged
+                return
+        full = (n - start) // self.batch * self.batch
+        if full:
+            self._emit(*[a[start:start + full] for a in arrs])
+        if start + full < n:
+            self.carry = [np.array(a[start + full:]) for a in arrs]        # copy: the caller reuses its buffers
+
+    def close(self):
+        if self.carry is not None:
+            self._emit(*self.carry)
+            self.carry = None
+        return self.n_bytes
 
 
 def predict(model: LSTMNetwork, testing_paths, reference_index_file, batch_size, output_file, device, reference=None):
     with open(output_file, "w") as fwriter:
         write_head(reference_index_file, fwriter)
+        fwriter.flush()
         model.eval()
         for testing_file in testing_paths:
             dataset = PredictDataset(datapath=testing_file, reference=reference, device=device)
@@ -76,7 +124,7 @@ def predict(model: LSTMNetwork, testing_paths, reference_index_file, batch_size,
                 while end < len(names) and names[end] == names[start]:
                     end += 1
                 if start == 0 and end == len(names):
-                    fwriter.write(format_records(names[0], dataset.positions, dataset.reference_bases, gt_h, zy_h, cov_h, batch_size))
+                    fwriter.write(format_records(names[0], dataset.positions, dataset.reference_bases, gt_h, zy_h, cov_h, batch_size).decode())
                 else:
                     raise NotImplementedError("one predict-data file must hold one contig (as make_predict_data.sh writes them)")
                 start = end

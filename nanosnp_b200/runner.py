@@ -137,10 +137,17 @@ class RegionRunner:
                 dev_reads[k] = self.upload(host_regions[k], key=f"reads{k % 2}")
                 ev = torch.cuda.Event(); ev.record(up_s); up_done[k] = ev
 
+        handles = [None] * n_reg
+
         def finish(k):
             down_done[k].synchronize()
             if consume is not None:
-                consume(k, results[k])
+                handles[k] = consume(k, results[k])             # may return a future (background host work on the pinned buffers)
+
+        def release(k):
+            if k >= 0 and handles[k] is not None and hasattr(handles[k], "result"):
+                handles[k].result()
+                handles[k] = None
 
         up_s.wait_stream(main)
         start_upload(0)
@@ -155,6 +162,7 @@ class RegionRunner:
             ev = torch.cuda.Event(); ev.record(main); comp_done[k] = ev
             # results: device -> device staging (so the next region can reuse the work buffers) -> pinned host
             ho = host_outs[k % 2]
+            release(k - 2)                                        # the consumer of region k-2 is done with this pinned buffer set
             with torch.cuda.stream(down_s):
                 down_s.wait_event(ev)
                 res = {"n": out.n}
@@ -172,6 +180,7 @@ class RegionRunner:
             if k >= 1:
                 finish(k - 1)                                     # host-side consumer of the previous region
         finish(n_reg - 1)
+        release(n_reg - 2); release(n_reg - 1)
         return total
 
     # ---- host-buffer mode: what a caller holding decoded reads in (pinned) host memory pays -------------

@@ -76,6 +76,57 @@ def test_native_vcf_formatter_matches_reference_python(golden, small_case):
     assert hdr + body == (golden / "s2_tiny_b7.vcf").read_text()
 
 
+def test_fast_threaded_formatter_is_byte_identical_to_the_libc_one(golden, small_case):
+    from nanosnp_b200.predict import format_records
+    z = np.load(golden / "s2_small.npz")
+    x = small_case["windows"]; cov = x[:, 16, [0, 1, 2, 3, 9, 10, 11, 12]].astype(np.float32)
+    for batch, threads in ((1000, 1), (1000, 5), (7, 3), (64, 16)):
+        slow = _native_vcf("ctg1", small_case["site_pos"], small_case["site_refbase"], z["gt"], z["zy"], x, batch)
+        fast = format_records("ctg1", small_case["site_pos"], small_case["site_refbase"], z["gt"], z["zy"], cov, batch, threads).decode()
+        assert fast == slow, (batch, threads)
+    # adversarial numerics: probabilities on a dense grid (QUAL rounding ties), AF ties (n/128), p == 1, zero depth
+    rng = np.random.default_rng(11)
+    n = 20000
+    gt = np.full((n, 21), 1e-9, np.float32); zy = np.full((n, 3), 1e-9, np.float32)
+    pmax = np.linspace(0.05, 0.99999, n).astype(np.float32)
+    k = rng.integers(0, 10, n); gt[np.arange(n), k] = pmax; gt[::501, :] = 0; gt[::501, 3] = 1.0
+    kz = rng.integers(0, 3, n); zy[np.arange(n), kz] = rng.uniform(0.34, 1.0, n).astype(np.float32)
+    xx = np.zeros((n, 33, 18), np.float32)
+    refb = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)]
+    for i in range(n):
+        r = "ACGT".index(chr(refb[i])); d = int(rng.choice([0, 6, 64, 128, 100]))
+        alt = (r + 1) % 4; s = int(rng.integers(0, d + 1)) if d else 0
+        xx[i, 16, alt] = s; xx[i, 16, r] = -d
+    cov = np.ascontiguousarray(xx[:, 16, [0, 1, 2, 3, 9, 10, 11, 12]])
+    pos = np.arange(1, n + 1).astype(np.int32)
+    slow = _native_vcf("chr7", pos, refb, gt, zy, xx, 1000)
+    fast = format_records("chr7", pos, refb, gt, zy, cov, 1000, 4).decode()
+    assert fast == slow
+    assert "nan" in fast and ":1.000000" in fast
+
+
+def test_contig_assembler_keeps_batch_composition(golden, small_case):
+    """Region-by-region streaming must give the same text as formatting the whole contig at once."""
+    import io
+    from nanosnp_b200.predict import ContigVcfAssembler, format_records
+    z = np.load(golden / "s2_small.npz")
+    x = small_case["windows"]; cov = np.ascontiguousarray(x[:, 16, [0, 1, 2, 3, 9, 10, 11, 12]].astype(np.float32))
+    pos0 = (small_case["site_pos"] - 1).astype(np.int32)
+    whole = format_records("ctg1", small_case["site_pos"], small_case["site_refbase"], z["gt"], z["zy"], cov, 1000, 2)
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        cuts = np.sort(rng.choice(np.arange(1, len(pos0)), size=6, replace=False)).tolist()
+        if trial == 0:
+            cuts = [1, 2, 999, 1000, 1001, 3000]
+        sink = io.BytesIO()
+        asm = ContigVcfAssembler("ctg1", 1000, 2, sink)
+        for a, b in zip([0] + cuts, cuts + [len(pos0)]):
+            asm.add(pos0[a:b], small_case["site_refbase"][a:b], z["gt"][a:b], z["zy"][a:b], cov[a:b])
+        asm.close()
+        assert sink.getvalue() == whole
+    assert whole.decode() == "".join(l + "\n" for l in (golden / "s2_small.vcf").read_text().splitlines() if not l.startswith("#"))
+
+
 def test_native_vcf_formatter_quirks_vs_oracle():
     """Randomised probabilities (incl. p == 1.0, tiny batches, zero depth) against the Python restatement."""
     from oracle.s2_restate import vcf_records

@@ -156,6 +156,7 @@ extern "C" int64_t nsnp_vcf_format_batch(const char* contig, int64_t n, const in
 // Fast path: same records, hand-rolled number formatting, batches formatted on host threads.
 // Every shortcut falls back to the libc path above whenever its exactness argument does not hold.
 // ===================================================================================================
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -324,10 +325,19 @@ extern "C" int64_t nsnp_vcf_format_contig(const char* contig, int64_t n, const i
     const int64_t n_batches = (n + batch_size - 1) / batch_size;
     int nt = n_threads < 1 ? 1 : n_threads;
     if ((int64_t)nt > n_batches) nt = (int)(n_batches > 0 ? n_batches : 1);
+    // per-thread text buffers are kept between calls (fresh 40 MB allocations page-fault under the process-wide mm lock
+    // and stop the threads from scaling); the pool is guarded for concurrent callers
+    static std::mutex pool_mu;
+    static std::vector<std::string> pool;
     std::vector<std::string> parts((size_t)nt);
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        for (int t = 0; t < nt && !pool.empty(); ++t) { parts[(size_t)t] = std::move(pool.back()); pool.pop_back(); }
+    }
     auto work = [&](int t) {
         const int64_t b0 = n_batches * t / nt, b1 = n_batches * (t + 1) / nt;
-        std::string o;                      // thread-local: the string headers in `parts` share cache lines
+        std::string o = std::move(parts[(size_t)t]);      // worked on locally: the headers in `parts` share cache lines
+        o.clear();
         o.reserve((size_t)((b1 - b0) * batch_size) * (72 + clen));
         for (int64_t b = b0; b < b1; ++b) {
             const int64_t s = b * batch_size, m = (n - s) < batch_size ? (n - s) : batch_size;
@@ -344,8 +354,14 @@ extern "C" int64_t nsnp_vcf_format_contig(const char* contig, int64_t n, const i
     }
     int64_t total = 0;
     for (auto& s2 : parts) total += (int64_t)s2.size();
-    if (!out || total > out_capacity) return -total;
-    char* p = out;
-    for (auto& s2 : parts) { memcpy(p, s2.data(), s2.size()); p += s2.size(); }
-    return total;
+    const bool fits = out && total <= out_capacity;
+    if (fits) {
+        char* p = out;
+        for (auto& s2 : parts) { memcpy(p, s2.data(), s2.size()); p += s2.size(); }
+    }
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        for (auto& s2 : parts) if (pool.size() < 256) pool.push_back(std::move(s2));
+    }
+    return fits ? total : -total;
 }

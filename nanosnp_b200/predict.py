@@ -37,21 +37,31 @@ def write_head(reference_index_file, fwriter):                     # predict.py:
     fwriter.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tSample\n")
 
 
-def format_records(contig: str, positions, reference_bases, gt: np.ndarray, zy: np.ndarray, cov8: np.ndarray, batch_size: int,
-                   n_threads: int = 0) -> bytes:
-    """All records of one contig file, consecutive batches of batch_size sites (host arrays) -> VCF text bytes."""
+def format_records_into(buf: np.ndarray, contig: str, positions, reference_bases, gt, zy, cov8, batch_size: int, n_threads: int = 0) -> int:
+    """Formats all records of consecutive batch_size-site batches into the uint8 array `buf`; returns the byte count
+    (raises if buf is too small).  No copies of the inputs when they are already contiguous and typed."""
     lib = _lib.load()
     n = len(positions)
     if n == 0:
-        return b""
+        return 0
     pos = np.ascontiguousarray(positions, np.int32); refb = np.ascontiguousarray(reference_bases, np.uint8)
     gt = np.ascontiguousarray(gt, np.float32); zy = np.ascontiguousarray(zy, np.float32); cov8 = np.ascontiguousarray(cov8, np.float32)
-    cap = n * (80 + len(contig)) + 64
-    buf = np.empty(cap, np.uint8)
     w = lib.nsnp_vcf_format_contig(contig.encode(), n, pos.ctypes.data, refb.ctypes.data, gt.ctypes.data, zy.ctypes.data,
-                                   cov8.ctypes.data, batch_size, n_threads or (os.cpu_count() or 1), buf.ctypes.data, cap)
+                                   cov8.ctypes.data, batch_size, n_threads or (os.cpu_count() or 1), buf.ctypes.data, buf.shape[0])
     if w < 0:
-        raise _lib.NsnpError(_lib.E_WORKSPACE, "VCF buffer too small")
+        raise _lib.NsnpError(_lib.E_WORKSPACE, f"VCF buffer too small: need {-w} bytes")
+    return int(w)
+
+
+def vcf_buffer_bytes(n: int, contig: str) -> int:
+    return n * (80 + len(contig)) + 64
+
+
+def format_records(contig: str, positions, reference_bases, gt: np.ndarray, zy: np.ndarray, cov8: np.ndarray, batch_size: int,
+                   n_threads: int = 0) -> bytes:
+    """All records of one contig file, consecutive batches of batch_size sites (host arrays) -> VCF text bytes."""
+    buf = np.empty(vcf_buffer_bytes(len(positions), contig), np.uint8)
+    w = format_records_into(buf, contig, positions, reference_bases, gt, zy, cov8, batch_size, n_threads)
     return buf[:w].tobytes()
 
 
@@ -67,10 +77,13 @@ class ContigVcfAssembler:
         self.n_sites = 0
 
     def _emit(self, pos1, refb, gt, zy, cov8):
-        text = format_records(self.contig, pos1, refb, gt, zy, cov8, self.batch, self.threads)
-        self.n_bytes += len(text)
+        need = vcf_buffer_bytes(len(pos1), self.contig)
+        if getattr(self, "_buf", None) is None or self._buf.shape[0] < need:
+            self._buf = np.empty(int(need * 1.1), np.uint8)          # reused across regions
+        w = format_records_into(self._buf, self.contig, pos1, refb, gt, zy, cov8, self.batch, self.threads)
+        self.n_bytes += w
         if self.sink is not None:
-            self.sink.write(text)
+            self.sink.write(self._buf[:w].tobytes())
 
     def add(self, pos0, refbase, gt, zy, cov8):
         """Host arrays of one region, ascending positions (0-based)."""

@@ -190,6 +190,15 @@ int64_t nsnp_vcf_format_contig(const char* contig, int64_t n, const int32_t* pos
                                const float* gt_prob, const float* zy_prob, const float* cov8, int64_t batch_size,
                                int n_threads, char* out, int64_t out_capacity);
 
+/* ---- host: BAM records -> flat packed arrays (replaces the BAM reading samtools does for mpileup) ------------
+ * `data` is the UNCOMPRESSED BAM stream (the caller inflates BGZF with zlib); first_record_offset points past the
+ * header and reference list.  Two passes: count, then fill caller-allocated arrays.  Return the read count or -1. */
+int64_t nsnp_bam_count(const uint8_t* data, int64_t n_bytes, int64_t first_record_offset, int32_t ref_id,
+                       int64_t* n_cigar, int64_t* n_bases_padded);
+int64_t nsnp_bam_fill(const uint8_t* data, int64_t n_bytes, int64_t first_record_offset, int32_t ref_id,
+                      int32_t* pos, uint16_t* flag, uint8_t* mapq, int64_t* cigar_off, uint32_t* cigar, int64_t* seq_off,
+                      uint8_t* seq2, uint8_t* nmask);
+
 /* ---- synthetic inputs (bench / tests) --------------------------------------- */
 typedef struct nsnp_synth_cfg {
     uint64_t seed_ref, seed_var, seed_reads;

@@ -91,6 +91,8 @@ SYMBOLS = {
     "nsnp_check_status": (C.c_int, [_P, _P]),
     "nsnp_vcf_format_batch": (_I64, [C.c_char_p, _I64, _P, _P, _P, _P, _P, _P, _I64]),
     "nsnp_vcf_format_contig": (_I64, [C.c_char_p, _I64, _P, _P, _P, _P, _P, _I64, C.c_int, _P, _I64]),
+    "nsnp_bam_count": (_I64, [_P, _I64, _I64, _I32, _P, _P]),
+    "nsnp_bam_fill": (_I64, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nsnp_synth_ref_host": (C.c_int, [C.POINTER(SynthCfg), _P]),
     "nsnp_synth_count_host": (C.c_int, [C.POINTER(SynthCfg), _P, _P, _P, _P, _P]),
     "nsnp_synth_fill_host": (C.c_int, [C.POINTER(SynthCfg), _P, _P, _P, _P, _P]),

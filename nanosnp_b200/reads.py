@@ -111,6 +111,31 @@ class PackedReads:
                            self.seq_off[:n], self.seq2[:nb4], None if self.nmask is None else self.nmask[: (nb + 7) // 8])
 
 
+def slice_reads(reads: "PackedReads", lo: int, hi: int) -> "PackedReads":
+    """Reads [lo, hi) as a self-contained PackedReads (numpy): offsets rebased, arrays padded for the kernels' look-ahead."""
+    assert isinstance(reads.pos, np.ndarray)
+    n = reads.n_reads
+    c0, c1 = int(reads.cigar_off[lo]), int(reads.cigar_off[hi])
+    nb_total = reads.n_bases
+    b0 = int(reads.seq_off[lo]) if lo < n else nb_total
+    b1 = int(reads.seq_off[hi]) if hi < n else nb_total
+    b0 -= b0 % 16                                   # keep 4-byte alignment of the sliced seq2 / nmask
+    pad = np.zeros(16, np.uint8)
+    seq2 = np.concatenate([reads.seq2[b0 // 4:(b1 + 3) // 4], pad])
+    nmask = None if reads.nmask is None else np.concatenate([reads.nmask[b0 // 8:(b1 + 7) // 8], pad])
+    return PackedReads(np.ascontiguousarray(reads.pos[lo:hi]), np.ascontiguousarray(reads.flag[lo:hi]), np.ascontiguousarray(reads.mapq[lo:hi]),
+                       reads.cigar_off[lo:hi + 1] - c0, np.ascontiguousarray(reads.cigar[c0:c1]), reads.seq_off[lo:hi] - b0, seq2, nmask)
+
+
+def max_reference_span(reads: "PackedReads") -> int:
+    """Longest reference span of any read (host arrays): bounds how far back a region must look for overlapping reads."""
+    ops = reads.cigar & 15
+    rl = np.where((ops == 0) | (ops == 2) | (ops == 3) | (ops == 7) | (ops == 8), reads.cigar >> 4, 0).astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(rl)])
+    spans = cs[reads.cigar_off[1:]] - cs[reads.cigar_off[:-1]]
+    return int(spans.max()) if len(spans) else 0
+
+
 def reference_span(cigar: np.ndarray) -> int:
     ops = cigar & 15
     lens = cigar >> 4

@@ -49,8 +49,36 @@ def test_predict_cli_from_pd_text_and_from_reads(tmp_path, golden, small_case, p
     P.main(["-config", cfg, "-model_path", str(golden / "ont_pileup_weights.npz"), "-data", str(d2), "-reference", fa, "-output", out2,
             "--precision", precision])
     assert open(out2).read() == open(out1).read()
+    # (c) a BAM file: BGZF + BAM decode on the host, then the same GPU path
+    from nanosnp_b200.bam import write_bam
+    bam = str(tmp_path / "reads.bam")
+    write_bam(bam, [("ctg1", len(small_case["ref"]))], {"ctg1": small_case["reads"]})
+    out3 = str(tmp_path / "c.vcf")
+    P.main(["-config", cfg, "-model_path", str(golden / "ont_pileup_weights.npz"), "-data", bam, "-reference", fa, "-output", out3,
+            "--precision", precision])
+    assert open(out3).read() == open(out1).read()
     with pytest.raises(SystemExit):
         P.main(["-config", cfg, "-model_path", "x", "-data", str(d2), "-reference", fa, "-output", out2, "--no_cuda"])
+
+
+def test_region_sharded_contig_equals_single_region(tmp_path, golden, golden_weights, small_case):
+    """Many small regions (16-bp halos, batches carried across region boundaries) give the same VCF bytes as one region."""
+    import io
+    from nanosnp_b200.caller import call_contig
+    from nanosnp_b200.pipeline import PileupEngine, PileupModelForward, PileupModelWeights
+    from nanosnp_b200.runner import RegionRunner
+    w = PileupModelWeights(*golden_weights, device="cuda:0")
+    runner = RegionRunner(PileupEngine("cuda:0"), PileupModelForward(w, 0))
+    outs = []
+    for region_len in (1 << 30, 6_500, 1_111):
+        sink = io.BytesIO()
+        info = call_contig(runner, small_case["reads"], small_case["ref"], "ctg1", sink, 1000, region_len)
+        outs.append(sink.getvalue())
+        assert info["sites"] == len(small_case["site_pos"])
+    assert outs[0] == outs[1] == outs[2]
+    ref_lines = [l for l in (golden / "s2_small.vcf").read_text().splitlines() if not l.startswith("#")]
+    got = outs[0].decode().splitlines()
+    assert len(got) == len(ref_lines) and all(a.split("\t")[:5] == b.split("\t")[:5] for a, b in zip(got, ref_lines))
 
 
 def test_lstmnetwork_seam(golden_weights, small_case, golden):

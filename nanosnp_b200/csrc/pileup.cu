@@ -388,9 +388,11 @@ __global__ void __launch_bounds__(kThreads, 3) pileup_tile_kernel(nsnp_reads_t r
         }
         __syncthreads();
 
-        // ---- epilogue: 18 channels + gate per position, staged, then coalesced stores ----
-        for (int sb = 0; sb < tn; sb += kStageRows) {
-            const int p = sb + tid;
+        // ---- epilogue: 18 channels + gate per position, staged, then coalesced stores.  Every warp owns 32 consecutive
+        //      positions at a time and its own 2304-byte slice of the staging buffer, so the loop needs no block-wide
+        //      barrier: a warp with a long indel chain to walk only delays itself. ----
+        for (int sb = warp * 32; sb < tn; sb += kThreads) {
+            const int p = sb + lane;
             if (p < tn) {
                 // indel channels: totals from the class counters; the chain is walked only where a class holds >= 2
                 // events (multiplicity of the most frequent identical indel, I1/D1) or the counters may have wrapped
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 3) pileup_tile_kernel(nsnp_reads_t r
                 const bool covered = (int)(md & 0xFFFF) + (int)(md >> 16) + df + dr > 0 || ((sm.skipcov[p >> 5] >> (p & 31)) & 1u);
                 const bool gate = covered && rc4 < 4 && pass && depth >= prm.min_coverage;       // main.cpp:196
                 flags[(ts - region_start) + p] = (uint8_t)((covered ? NSNP_F_COVERED : 0) | (gate ? NSNP_F_GATE : 0));
-                int2* row = reinterpret_cast<int2*>(sm.stage + tid * 18);
+                int2* row = reinterpret_cast<int2*>(sm.stage + tid * 18);            // = warp slice + lane row
                 row[0] = make_int2(chr == 0 ? -mf : cf[0], chr == 1 ? -mf : cf[1]);
                 row[1] = make_int2(chr == 2 ? -mf : cf[2], chr == 3 ? -mf : cf[3]);
                 row[2] = make_int2(tot0, mx0); row[3] = make_int2(tot2, mx2);
@@ -472,17 +474,18 @@ __global__ void __launch_bounds__(kThreads, 3) pileup_tile_kernel(nsnp_reads_t r
                 row[6] = make_int2(chr == 3 ? -mr : cr[3], tot1);
                 row[7] = make_int2(mx1, tot3); row[8] = make_int2(mx3, dr);
             }
-            __syncthreads();
+            __syncwarp();
             {
-                const int rows = min(kStageRows, tn - sb);
-                const int n_int = rows * 18;
+                const int rows = min(32, tn - sb);
+                const int n_int = rows * 18;                       // 32 rows = 576 ints = 144 int4 (16-byte aligned: sb % 32 == 0)
                 int32_t* out = counts + ((ts - region_start) + sb) * 18;
                 const int n4 = n_int >> 2;
-                const int4* st4 = reinterpret_cast<const int4*>(sm.stage);
-                for (int q = tid; q < n4; q += kThreads) st_stream(reinterpret_cast<int4*>(out) + q, st4[q]);
-                for (int e = (n4 << 2) + tid; e < n_int; e += kThreads) out[e] = sm.stage[e];
+                const int32_t* wst = sm.stage + warp * 32 * 18;
+                const int4* st4 = reinterpret_cast<const int4*>(wst);
+                for (int q = lane; q < n4; q += 32) st_stream(reinterpret_cast<int4*>(out) + q, st4[q]);
+                for (int e = (n4 << 2) + lane; e < n_int; e += 32) out[e] = wst[e];
             }
-            __syncthreads();
+            __syncwarp();
         }
     }
 }

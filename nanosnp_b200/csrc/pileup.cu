@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(kThreads, 3) pileup_tile_kernel(nsnp_reads_t r
 
         // ---- accumulate: reads [lo, hi) that overlap the tile, one warp per read ----
         const int rlo = ws.tile_lo[tile], rhi = ws.tile_hi[tile];
+        int n_overlap = 0;                                  // reads that really overlap the tile (block-uniform)
         for (int rb = rlo; rb < rhi; rb += kReadList) {
             __syncthreads();
             if (tid == 0) { sm.n_rlist = 0; sm.next_task = 0; }
@@ -348,6 +349,7 @@ __global__ void __launch_bounds__(kThreads, 3) pileup_tile_kernel(nsnp_reads_t r
             }
             __syncthreads();
             const int nr = sm.n_rlist;
+            n_overlap += nr;
             for (;;) {
                 int t = 0;
                 if (lane == 0) t = atomicAdd(&sm.next_task, 1);
@@ -357,8 +359,8 @@ __global__ void __launch_bounds__(kThreads, 3) pileup_tile_kernel(nsnp_reads_t r
             }
         }
         __syncthreads();
-        const bool deep = rhi - rlo > 255;                  // class counters are bytes: exact only below 256 overlapping reads
-        if (tid == 0 && rhi - rlo > 65535) dev_fail(status, DEV_E_DEPTH, (int)(ts & 0x7fffffff));
+        const bool deep = n_overlap > 255;                  // class counters are bytes: exact only below 256 overlapping reads
+        if (tid == 0 && n_overlap > 65535) dev_fail(status, DEV_E_DEPTH, (int)(ts & 0x7fffffff));
 
         // ---- prefix sums: run starts/ends -> depths (fwd | rev << 16 stays valid: depths are < 65536) ----
         {

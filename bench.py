@@ -254,7 +254,7 @@ def main_ours(args):
         def step_host(with_vcf=True):
             # H2D of region k+1 and D2H of region k-1 overlap the kernels of region k (copy streams + double buffers);
             # the VCF text of region k-1 is formatted on host threads (nsnp_vcf_format_contig) meanwhile
-            asm = ContigVcfAssembler(cfg.contig, 1000, os.cpu_count() or 1, None)
+            asm = ContigVcfAssembler(cfg.contig, 1000, max(1, (os.cpu_count() or 1) // world), None)     # host cores are shared by the ranks
 
             def consume(k, res):
                 if not with_vcf:

@@ -191,6 +191,7 @@ def main_ours(args):
     prec = _lib.PREC_FP32 if args.precision == "fp32" else _lib.PREC_F16X3
     model = PileupModelForward(PileupModelWeights(enc, fwd, device=dev), precision=prec)
     runner = RegionRunner(eng, model)
+    runner_e2e = RegionRunner(eng, model, records=True)      # e2e: numeric record logic on the GPU, 32 B/site D2H
 
     def step_device(timer=None):
         n = 0
@@ -241,9 +242,7 @@ def main_ours(args):
         capn = max(1024, max(rg.emit_end - rg.emit_start for rg in regions) // 3)
 
         def pinned_out():
-            return {"pos0": torch.empty(capn, dtype=torch.int32).pin_memory(), "refbase": torch.empty(capn, dtype=torch.uint8).pin_memory(),
-                    "cov8": torch.empty((capn, 8), dtype=torch.float32).pin_memory(), "gt": torch.empty((capn, 21), dtype=torch.float32).pin_memory(),
-                    "zy": torch.empty((capn, 3), dtype=torch.float32).pin_memory()}
+            return {"rec": torch.empty((capn, 32), dtype=torch.uint8).pin_memory()}
         host_outs = (pinned_out(), pinned_out())
 
         from concurrent.futures import ThreadPoolExecutor
@@ -259,8 +258,8 @@ def main_ours(args):
             def consume(k, res):
                 if not with_vcf:
                     return None
-                return pool.submit(asm.add, res["pos0"].numpy(), res["refbase"].numpy(), res["gt"].numpy(), res["zy"].numpy(), res["cov8"].numpy())
-            n = runner.run_host_many(host_regions, regions, ref, host_outs, consume)
+                return pool.submit(asm.add_records, res["rec"].numpy())
+            n = runner_e2e.run_host_many(host_regions, regions, ref, host_outs, consume)
             vcf_bytes[0] = pool.submit(asm.close).result()
             return n
         step_host()
@@ -274,7 +273,7 @@ def main_ours(args):
         barrier()
         wall = time.perf_counter() - t0
         e2e_ms = max(f0.elapsed_time(f1), wall * 1e3)
-        d2h_bytes = n_e2e * (4 + 1 + 32 + 84 + 12)
+        d2h_bytes = n_e2e * 32
         e2e = {"ms": e2e_ms, "sites": n_e2e, "h2d": h2d_bytes, "d2h": d2h_bytes, "vcf_bytes": vcf_bytes[0]}
 
     # ---- reduce over ranks: max time, total sites ----
@@ -369,9 +368,10 @@ def main_ours(args):
     if e2e:
         line["e2e"] = {"value": e2e_sites / (e2e_ms * 1e-3) * K, "unit": "sites/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                        "ms_per_step": e2e_ms / K, "vcf_bytes_per_step": e2e["vcf_bytes"],
-                       "note": "pinned host read arrays -> H2D -> kernels -> D2H of (pos, refbase, centre counts, gt[21], zy[3]) -> VCF record text "
-                               "(native multi-threaded formatter, 1000-site batches per contig as predict.py) through RegionRunner.run_host_many; copies and "
-                               "formatting overlap the kernels of the neighbouring regions; reference FASTA and weights resident"}
+                       "note": "pinned host read arrays -> H2D -> kernels (incl. site_record_kernel: argmax/QUAL/DP/AF per site) -> D2H of 32-byte site "
+                               "records -> VCF record text (native multi-threaded text assembly, 1000-site batches per contig as predict.py) through "
+                               "RegionRunner.run_host_many; copies and formatting overlap the kernels of the neighbouring regions; reference FASTA and "
+                               "weights resident"}
     else:
         line["e2e"] = None
     if world == 1 and not args.no_cpu_baseline:

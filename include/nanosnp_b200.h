@@ -166,7 +166,7 @@ int nsnp_debug_lstm_tc_gates(const void* blob_dev, const int32_t* x_i32_dev, int
  * nsnp_profile_read synchronises, adds the elapsed times per kernel slot into ms_out[NSNP_PROF_SLOTS] and
  * launches_out[NSNP_PROF_SLOTS], and clears the pending events.  Slots: */
 enum { NSNP_PROF_READ_SCAN = 0, NSNP_PROF_PILEUP_TILE, NSNP_PROF_SELECT, NSNP_PROF_GATHER, NSNP_PROF_LSTM0, NSNP_PROF_LSTM1,
-       NSNP_PROF_TAIL, NSNP_PROF_SLOTS };
+       NSNP_PROF_TAIL, NSNP_PROF_RECORDS, NSNP_PROF_SLOTS };
 void nsnp_profile_enable(int on);
 int  nsnp_profile_read(double* ms_out, int64_t* launches_out);
 
@@ -183,6 +183,26 @@ int nsnp_check_status(const int32_t* status_dev, void* stream);
 int64_t nsnp_vcf_format_batch(const char* contig, int64_t n, const int32_t* pos1, const uint8_t* refbase,
                               const float* gt_prob, const float* zy_prob, const float* cov8,
                               char* out, int64_t out_capacity);
+
+/* ---- s2: compact site records (numeric half of predict.py:54-88 on the GPU) ---------------------------------- */
+typedef struct nsnp_site_record {        /* 32 bytes */
+    uint8_t gt, zy, flags, ref;          /* argmax of the two heads, NSNP_REC_* flags, centre reference base */
+    int32_t pos1;                        /* 1-based position */
+    int32_t q100_gt, q100_zy;            /* round(QUAL * 100) of the genotype / zygosity probability */
+    int32_t depth;                       /* DP */
+    int32_t af_q;                        /* AF * 1e6 rounded like '%f', or NSNP_AF_ONE / NSNP_AF_NAN */
+    float   p_gt, p_zy;                  /* the max probabilities (host recomputes flagged rounding ties) */
+} nsnp_site_record_t;
+#define NSNP_REC_DROP    1               /* predict.py would raise for this site: no record */
+#define NSNP_REC_TIE_GT  2               /* QUAL within 1e-6 of a rounding tie: recompute on the host */
+#define NSNP_REC_TIE_ZY  4
+#define NSNP_AF_ONE      1000001
+#define NSNP_AF_NAN      (-1)
+int nsnp_site_records(const float* gt_prob_dev, const float* zy_prob_dev, const int32_t* x_i32_dev, const uint8_t* refbase_dev,
+                      const int32_t* pos_dev, int64_t n, const int32_t* n_dev, nsnp_site_record_t* rec_dev, void* stream);
+/* host: text of all records of consecutive batch_size-site batches from compact records (same bytes as the two below) */
+int64_t nsnp_vcf_format_contig_records(const char* contig, int64_t n, const nsnp_site_record_t* rec, int64_t batch_size,
+                                       int n_threads, char* out, int64_t out_capacity);
 
 /* Whole contig file: consecutive batches of batch_size sites (predict.py:43 DataLoader(batch_size, shuffle=False)),
  * formatted on n_threads host threads with hand-rolled number formatting (same bytes as nsnp_vcf_format_batch). */

@@ -17,7 +17,7 @@ CHANNELS, FLANK, WINDOW = 18, 16, 33
 GT_CLASSES, ZY_CLASSES = 21, 3
 F_COVERED, F_GATE = 1, 2
 PREC_FP32, PREC_F16X3 = 0, 1
-PROF_SLOTS = ("read_scan_kernel", "pileup_tile_kernel", "select_kernels", "gather_kernel", "lstm_layer0", "lstm_layer1", "tail_kernel")
+PROF_SLOTS = ("read_scan_kernel", "pileup_tile_kernel", "select_kernels", "gather_kernel", "lstm_layer0", "lstm_layer1", "tail_kernel", "site_record_kernel")
 
 
 class NsnpError(RuntimeError):
@@ -90,6 +90,8 @@ SYMBOLS = {
     "nsnp_profile_read": (C.c_int, [_P, _P]),
     "nsnp_check_status": (C.c_int, [_P, _P]),
     "nsnp_vcf_format_batch": (_I64, [C.c_char_p, _I64, _P, _P, _P, _P, _P, _P, _I64]),
+    "nsnp_site_records": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "nsnp_vcf_format_contig_records": (_I64, [C.c_char_p, _I64, _P, _I64, C.c_int, _P, _I64]),
     "nsnp_vcf_format_contig": (_I64, [C.c_char_p, _I64, _P, _P, _P, _P, _P, _I64, C.c_int, _P, _I64]),
     "nsnp_bam_count": (_I64, [_P, _I64, _I64, _I32, _P, _P]),
     "nsnp_bam_fill": (_I64, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -14,7 +14,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = ROOT / "libnanosnp_b200.so"
-SOURCES = ["api.cu", "synth.cu", "pileup.cu", "select.cu", "model.cu", "model_tc.cu", "vcf.cu", "bam.cu"]
+SOURCES = ["api.cu", "synth.cu", "pileup.cu", "select.cu", "model.cu", "model_tc.cu", "vcf.cu", "bam.cu", "record.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

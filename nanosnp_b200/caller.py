@@ -34,6 +34,8 @@ def call_contig(runner: RegionRunner, reads: PackedReads, ref: np.ndarray, conti
     cap = max(4096, max(rg.emit_end - rg.emit_start for rg in regions))
 
     def pinned_out():
+        if runner.records:
+            return {"rec": torch.empty((cap, 32), dtype=torch.uint8).pin_memory()}
         return {"pos0": torch.empty(cap, dtype=torch.int32).pin_memory(), "refbase": torch.empty(cap, dtype=torch.uint8).pin_memory(),
                 "cov8": torch.empty((cap, 8), dtype=torch.float32).pin_memory(), "gt": torch.empty((cap, 21), dtype=torch.float32).pin_memory(),
                 "zy": torch.empty((cap, 3), dtype=torch.float32).pin_memory()}
@@ -41,7 +43,10 @@ def call_contig(runner: RegionRunner, reads: PackedReads, ref: np.ndarray, conti
     asm = ContigVcfAssembler(contig, batch_size, n_threads, sink)
 
     def consume(k, res):
-        asm.add(res["pos0"].numpy(), res["refbase"].numpy(), res["gt"].numpy(), res["zy"].numpy(), res["cov8"].numpy())
+        if runner.records:
+            asm.add_records(res["rec"].numpy())
+        else:
+            asm.add(res["pos0"].numpy(), res["refbase"].numpy(), res["gt"].numpy(), res["zy"].numpy(), res["cov8"].numpy())
         return None
     n = runner.run_host_many(host_regions, regions, ref_dev, host_outs, consume)
     nbytes = asm.close()

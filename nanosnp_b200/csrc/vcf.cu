@@ -365,3 +365,160 @@ extern "C" int64_t nsnp_vcf_format_contig(const char* contig, int64_t n, const i
     }
     return fits ? total : -total;
 }
+
+
+// ---- text from compact GPU records (record.cu) -------------------------------------------------------------------
+namespace {
+
+inline char* put_q100(char* p, long long q100, long long* int_part) {
+    const long long ip = q100 / 100; const int f2 = (int)(q100 % 100);
+    *int_part = ip;
+    p = put_uint(p, (unsigned long long)ip);
+    *p++ = '.';
+    *p++ = (char)('0' + f2 / 10);
+    if (f2 % 10) *p++ = (char)('0' + f2 % 10);
+    return p;
+}
+
+// QUAL*100 of a record field; rounding ties flagged by the device are redone with the libc path
+inline bool rec_q100(float p, int32_t q_dev, bool tie, long long* q100) {
+    if (!tie) { *q100 = q_dev; return true; }
+    double v;
+    if (!calc_score(p, &v)) return false;                  // rounded to 2 decimals by calc_score
+    *q100 = (long long)floor(v * 100.0 + 0.5);
+    return true;
+}
+
+inline char* put_record_q(char* p, const char* contig, size_t clen, long long pos, char ref, const char* alt, long long q100,
+                          const char* filter, const char* zy, long long depth, int32_t af_q)
+{
+    memcpy(p, contig, clen); p += clen; *p++ = '\t';
+    p = put_uint(p, (unsigned long long)pos);
+    *p++ = '\t'; *p++ = '.'; *p++ = '\t'; *p++ = ref; *p++ = '\t';
+    for (const char* a = alt; *a; ++a) *p++ = *a;
+    *p++ = '\t';
+    long long qi = 0;
+    p = put_q100(p, q100, &qi);
+    *p++ = '\t';
+    for (const char* a = filter; *a; ++a) *p++ = *a;
+    memcpy(p, "\t.\tGT:GQ:DP:AF\t", 15); p += 15;
+    for (const char* a = zy; *a; ++a) *p++ = *a;
+    *p++ = ':';
+    p = put_uint(p, (unsigned long long)qi);
+    *p++ = ':';
+    if (depth < 0) { *p++ = '-'; p = put_uint(p, (unsigned long long)(-depth)); } else p = put_uint(p, (unsigned long long)depth);
+    *p++ = ':';
+    if (af_q == NSNP_AF_ONE) { memcpy(p, "1.000000", 8); p += 8; }
+    else if (af_q == NSNP_AF_NAN) { memcpy(p, "nan", 3); p += 3; }
+    else {
+        const unsigned long long u = (unsigned long long)af_q;
+        p = put_uint(p, u / 1000000ull);
+        *p++ = '.';
+        unsigned long long f = u % 1000000ull;
+        char d[6]; for (int i = 5; i >= 0; --i) { d[i] = (char)('0' + f % 10); f /= 10; }
+        memcpy(p, d, 6); p += 6;
+    }
+    *p++ = '\n';
+    return p;
+}
+
+void format_batch_records(std::string& o, const char* contig, size_t clen, int64_t n, const nsnp_site_record_t* rec) {
+    char line[256 + 64];
+    for (int64_t j = 0; j < n; ++j) {
+        const nsnp_site_record_t& r = rec[j];
+        const int gt = r.gt, zyo = r.zy;
+        if (gt >= 10) continue;                                               // predict.py:68
+        if (r.flags & NSNP_REC_DROP) continue;                                // calculate_score raised
+        const char sref = (char)r.ref;
+        const char* label = kGt[gt];
+        const char* zy = kZy[zyo];
+        char alt[4]; int na = 0;
+        for (int k = 0; k < 2; ++k) if (label[k] != sref) alt[na++] = label[k];
+        alt[na] = 0;
+        long long gt_q, zy_q;
+        if (!rec_q100(r.p_gt, r.q100_gt, (r.flags & NSNP_REC_TIE_GT) != 0, &gt_q)) continue;
+        if (!rec_q100(r.p_zy, r.q100_zy, (r.flags & NSNP_REC_TIE_ZY) != 0, &zy_q)) continue;
+        const long long qual = gt_q < zy_q ? gt_q : zy_q;
+        char* e = nullptr;
+        if (na == 0) {
+            if (zyo == 0) {
+                const char a1[2] = {sref, 0};
+                e = put_record_q(line, contig, clen, r.pos1, sref, a1, qual, "RefCall", zy, r.depth, r.af_q);
+            } else {
+                static const int tis_hom[4] = {0, 4, 7, 9};
+                static const int tis_het[6] = {1, 2, 3, 5, 6, 8};
+                const int* tis = zyo == 1 ? tis_hom : tis_het; const int nt = zyo == 1 ? 4 : 6;
+                int max_ti = -1, max_v = -1; bool raised = false;
+                for (int q = 0; q < nt; ++q) {
+                    const int ti = tis[q];
+                    if (zyo == 1 && kGt[ti][0] == sref) continue;
+                    if (ti >= n) { raised = true; break; }                    // IndexError on the batch argmax array
+                    const int v = rec[ti].gt;                                 // gt_output[ti]: the batch array indexed by a class index
+                    if (v > max_v) { max_v = v; max_ti = ti; }
+                }
+                if (raised) continue;
+                char a1[2] = {0, 0};
+                if (zyo == 1) a1[0] = kGt[max_ti][0]; else a1[0] = kGt[max_ti][0] == sref ? kGt[max_ti][1] : kGt[max_ti][0];
+                e = put_record_q(line, contig, clen, r.pos1, sref, a1, zy_q, "PASS", zy, r.depth, r.af_q);
+            }
+        } else {
+            char alts[8];
+            if (na == 1) { alts[0] = alt[0]; alts[1] = 0; }
+            else if (alt[0] == alt[1]) { alts[0] = alt[0]; alts[1] = 0; }
+            else { alts[0] = alt[0]; alts[1] = ','; alts[2] = alt[1]; alts[3] = 0; }
+            if (alts[1] == ',' && zyo != 2) zy = "1/2";
+            e = put_record_q(line, contig, clen, r.pos1, sref, alts, zyo == 0 ? gt_q : qual, "PASS", zy, r.depth, r.af_q);
+        }
+        o.append(line, (size_t)(e - line));
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t nsnp_vcf_format_contig_records(const char* contig, int64_t n, const nsnp_site_record_t* rec, int64_t batch_size,
+                                                  int n_threads, char* out, int64_t out_capacity)
+{
+    if (!contig || n < 0 || batch_size <= 0 || (n > 0 && !rec)) return 0;
+    const size_t clen = strlen(contig);
+    if (clen > 200) return 0;
+    const int64_t n_batches = (n + batch_size - 1) / batch_size;
+    int nt = n_threads < 1 ? 1 : n_threads;
+    if ((int64_t)nt > n_batches) nt = (int)(n_batches > 0 ? n_batches : 1);
+    static std::mutex pool_mu;
+    static std::vector<std::string> pool;
+    std::vector<std::string> parts((size_t)nt);
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        for (int t = 0; t < nt && !pool.empty(); ++t) { parts[(size_t)t] = std::move(pool.back()); pool.pop_back(); }
+    }
+    auto work = [&](int t) {
+        const int64_t b0 = n_batches * t / nt, b1 = n_batches * (t + 1) / nt;
+        std::string o = std::move(parts[(size_t)t]);
+        o.clear();
+        o.reserve((size_t)((b1 - b0) * batch_size) * (72 + clen));
+        for (int64_t b = b0; b < b1; ++b) {
+            const int64_t s = b * batch_size, m = (n - s) < batch_size ? (n - s) : batch_size;
+            format_batch_records(o, contig, clen, m, rec + s);
+        }
+        parts[(size_t)t] = std::move(o);
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    int64_t total = 0;
+    for (auto& s2 : parts) total += (int64_t)s2.size();
+    const bool fits = out && total <= out_capacity;
+    if (fits) {
+        char* p = out;
+        for (auto& s2 : parts) { memcpy(p, s2.data(), s2.size()); p += s2.size(); }
+    }
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        for (auto& s2 : parts) if (pool.size() < 256) pool.push_back(std::move(s2));
+    }
+    return fits ? total : -total;
+}

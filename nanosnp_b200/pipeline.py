@@ -116,6 +116,16 @@ class PileupEngine:
                                                     refbase.data_ptr(), _stream(self.device)))
         return x_i32, x_f32, refbase
 
+    # -- s2 numeric record logic ------------------------------------------------------------------
+    def site_records(self, gt: torch.Tensor, zy: torch.Tensor, x: torch.Tensor, refbase: torch.Tensor, pos: torch.Tensor, n: int,
+                     rec: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if rec is None:
+            rec = torch.empty((max(n, 1), 32), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nsnp_site_records(gt.data_ptr(), zy.data_ptr(), x.data_ptr(), refbase.data_ptr(), pos.data_ptr(), n, 0,
+                                                  rec.data_ptr(), _stream(self.device)))
+        return rec[:n]
+
     # -- s1 for a whole region ---------------------------------------------------------------------
     def candidate_windows(self, reads: PackedReads, ref: torch.Tensor, region_start: int = 0, region_len: Optional[int] = None,
                           emit_start: Optional[int] = None, emit_end: Optional[int] = None, capacity: Optional[int] = None):

@@ -36,6 +36,80 @@ def format_records(contig: str, positions, reference_bases, gt: np.ndarray, zy: 
     return buf[:w].tobytes()
 
 
+RECORD_DTYPE = np.dtype([("gt", np.uint8), ("zy", np.uint8), ("flags", np.uint8), ("ref", np.uint8), ("pos1", np.int32),
+                         ("q100_gt", np.int32), ("q100_zy", np.int32), ("depth", np.int32), ("af_q", np.int32),
+                         ("p_gt", np.float32), ("p_zy", np.float32)])          # struct nsnp_site_record (32 bytes)
+assert RECORD_DTYPE.itemsize == 32
+REC_DROP, REC_TIE_GT, REC_TIE_ZY, AF_ONE, AF_NAN = 1, 2, 4, 1000001, -1
+
+
+def format_compact_records_into(buf: np.ndarray, contig: str, rec: np.ndarray, batch_size: int, n_threads: int = 0) -> int:
+    """Text of compact GPU site records (nsnp_site_records) -> buf; returns the byte count."""
+    lib = _lib.load()
+    n = len(rec)
+    if n == 0:
+        return 0
+    rec = np.ascontiguousarray(rec)
+    assert rec.dtype == RECORD_DTYPE or (rec.dtype == np.uint8 and rec.ndim == 2 and rec.shape[1] == 32)
+    w = lib.nsnp_vcf_format_contig_records(contig.encode(), n, rec.ctypes.data, batch_size, n_threads or (os.cpu_count() or 1),
+                                           buf.ctypes.data, buf.shape[0])
+    if w < 0:
+        raise _lib.NsnpError(_lib.E_WORKSPACE, f"VCF buffer too small: need {-w} bytes")
+    return int(w)
+
+
+def records_reference(positions1, reference_bases, gt, zy, cov8) -> np.ndarray:
+    """NumPy statement of what site_record_kernel computes (tests; not used by the product path)."""
+    from math import log
+    n = len(positions1)
+    rec = np.zeros(n, RECORD_DTYPE)
+    gt = np.asarray(gt, np.float32); zy = np.asarray(zy, np.float32); cov8 = np.asarray(cov8, np.float32)
+    rec["gt"] = gt.argmax(1); rec["zy"] = zy.argmax(1); rec["ref"] = reference_bases; rec["pos1"] = positions1
+    rec["p_gt"] = gt.max(1); rec["p_zy"] = zy.max(1)
+    kscale = -10.0 * (1.0 / log(10.0))
+    labels = ["AA", "AC", "AG", "AT", "CC", "CG", "CT", "GG", "GT", "TT"]
+    with np.errstate(all="ignore"):
+        for j in range(n):
+            cov = cov8[j]
+            depth = np.float32(-1.0) * cov[cov < 0].sum(dtype=np.float32)
+            rec["depth"][j] = int(depth)
+            if rec["gt"][j] >= 10:
+                continue
+            sref = chr(int(reference_bases[j]))
+            support = np.float32(0.0)
+            for ch in labels[rec["gt"][j]]:
+                if ch != sref:
+                    b = "ACGT".index(ch)
+                    support = np.float32(support + cov[b]); support = np.float32(support + cov[b + 4])
+            af = np.float32(support) / np.float32(depth)
+            if af > 1.0:
+                rec["af_q"][j] = AF_ONE
+            elif af != af:
+                rec["af_q"][j] = AF_NAN
+            else:
+                m = float(af) * 1.0e6
+                q = np.floor(m); fr = m - q
+                if fr > 0.5 or (fr == 0.5 and q % 2 == 1):
+                    q += 1
+                rec["af_q"][j] = int(q)
+            flags = 0
+            for name, p, tiebit in (("q100_gt", rec["p_gt"][j], REC_TIE_GT), ("q100_zy", rec["p_zy"][j], REC_TIE_ZY)):
+                r = np.float32(np.float32(1.0) - p) / np.float32(p)
+                x = float(r)
+                if not x > 0.0:
+                    flags |= REC_DROP
+                    continue
+                t = kscale * log(x) + 10.0
+                t = t if t > 0.0 else 0.0
+                h = t * 100.0
+                fl = np.floor(h); fr = h - fl
+                if abs(fr - 0.5) < 1e-6:
+                    flags |= tiebit
+                rec[name][j] = int(fl) + (1 if fr > 0.5 else 0)
+            rec["flags"][j] = flags
+    return rec
+
+
 class ContigVcfAssembler:
     """Streams one contig's sites region by region into VCF text while keeping the reference's batch composition:
     records are formatted in consecutive batches of `batch_size` sites counted from the contig's first site
@@ -47,21 +121,34 @@ class ContigVcfAssembler:
         self.n_bytes = 0
         self.n_sites = 0
 
-    def _emit(self, pos1, refb, gt, zy, cov8):
-        need = vcf_buffer_bytes(len(pos1), self.contig)
+    def _emit(self, *arrs):
+        need = vcf_buffer_bytes(len(arrs[0]), self.contig)
         if getattr(self, "_buf", None) is None or self._buf.shape[0] < need:
             self._buf = np.empty(int(need * 1.1), np.uint8)          # reused across regions
-        w = format_records_into(self._buf, self.contig, pos1, refb, gt, zy, cov8, self.batch, self.threads)
+        if len(arrs) == 1:
+            w = format_compact_records_into(self._buf, self.contig, arrs[0], self.batch, self.threads)
+        else:
+            w = format_records_into(self._buf, self.contig, *arrs, self.batch, self.threads)
         self.n_bytes += w
         if self.sink is not None:
             self.sink.write(self._buf[:w].tobytes())
 
+    def add_records(self, rec):
+        """Compact GPU records of one region (RECORD_DTYPE or uint8 [n,32]), ascending positions."""
+        rec = np.asarray(rec)
+        if rec.dtype != RECORD_DTYPE:
+            rec = np.ascontiguousarray(rec).view(RECORD_DTYPE).reshape(-1)
+        self.n_sites += len(rec)
+        self._add_arrays([rec])
+
     def add(self, pos0, refbase, gt, zy, cov8):
         """Host arrays of one region, ascending positions (0-based)."""
-        n = len(pos0)
-        self.n_sites += n
+        self.n_sites += len(pos0)
         pos1 = np.asarray(pos0, np.int32) + 1
-        arrs = [pos1, np.asarray(refbase), np.asarray(gt), np.asarray(zy), np.asarray(cov8)]
+        self._add_arrays([pos1, np.asarray(refbase), np.asarray(gt), np.asarray(zy), np.asarray(cov8)])
+
+    def _add_arrays(self, arrs):
+        n = len(arrs[0])
         start = 0
         if self.carry is not None:
             need = self.batch - len(self.carry[0])

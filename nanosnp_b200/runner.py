@@ -28,6 +28,7 @@ class RegionOutput:
     gt: torch.Tensor          # float32 [n,21]
     zy: torch.Tensor          # float32 [n,3]
     x: Optional[torch.Tensor] = None
+    rec: Optional[torch.Tensor] = None    # uint8 [n,32] compact site records (records mode)
 
 
 class StageTimer:
@@ -63,11 +64,12 @@ class StageTimer:
 
 
 class RegionRunner:
-    def __init__(self, engine: PileupEngine, model: PileupModelForward, keep_windows: bool = False):
+    def __init__(self, engine: PileupEngine, model: PileupModelForward, keep_windows: bool = False, records: bool = False):
         self.eng = engine
         self.model = model
         self.device = engine.device
         self.keep_windows = keep_windows
+        self.records = records            # numeric record logic on the GPU: 32 bytes/site leave the device instead of 133
         self._bufs: Dict[str, torch.Tensor] = {}
         self.launches = 0          # kernels of this library launched so far
 
@@ -110,6 +112,12 @@ class RegionRunner:
             self.model(x, gt=gt, zy=zy)
             timer.stop()
             self.launches += 1 + 3 * (-(-n // 75776))
+        if self.records:
+            rec = self._buf("rec", (max(n, 1), 32), torch.uint8)[:n]
+            if n:
+                eng.site_records(gt, zy, x, refbase, pos, n, rec=rec)
+                self.launches += 1
+            return RegionOutput(n, pos[:n], refbase, None, gt, zy, x if self.keep_windows else None, rec)
         cov8 = x[:, 16, COV_CHANNELS].to(torch.float32) if n else torch.empty((0, 8), dtype=torch.float32, device=self.device)
         return RegionOutput(n, pos[:n], refbase, cov8, gt, zy, x if self.keep_windows else None)
 
@@ -166,7 +174,7 @@ class RegionRunner:
             with torch.cuda.stream(down_s):
                 down_s.wait_event(ev)
                 res = {"n": out.n}
-                for name in ("pos0", "refbase", "cov8", "gt", "zy"):
+                for name in (("rec",) if self.records else ("pos0", "refbase", "cov8", "gt", "zy")):
                     t = getattr(out, name)
                     if ho[name].shape[0] < out.n:
                         raise _lib.NsnpError(_lib.E_WORKSPACE, f"host result buffer '{name}' too small for {out.n} sites")

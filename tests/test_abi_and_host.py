@@ -105,6 +105,42 @@ def test_fast_threaded_formatter_is_byte_identical_to_the_libc_one(golden, small
     assert "nan" in fast and ":1.000000" in fast
 
 
+def test_compact_record_formatter_matches_the_array_formatter(golden, small_case):
+    """Host half of the GPU record path: records computed by the NumPy statement of site_record_kernel must give the same
+    bytes as the array formatter (golden set, tiny batches, adversarial ties / nan / p == 1)."""
+    from nanosnp_b200.predict_io import (ContigVcfAssembler, format_compact_records_into, format_records, records_reference, vcf_buffer_bytes)
+    z = np.load(golden / "s2_small.npz")
+    x = small_case["windows"]; cov = np.ascontiguousarray(x[:, 16, [0, 1, 2, 3, 9, 10, 11, 12]].astype(np.float32))
+    n = 2500
+    rec = records_reference(small_case["site_pos"][:n], small_case["site_refbase"][:n], z["gt"][:n], z["zy"][:n], cov[:n])
+    buf = np.empty(vcf_buffer_bytes(n, "ctg1"), np.uint8)
+    for batch, th in ((1000, 3), (7, 2)):
+        w = format_compact_records_into(buf, "ctg1", rec, batch, th)
+        assert buf[:w].tobytes() == format_records("ctg1", small_case["site_pos"][:n], small_case["site_refbase"][:n], z["gt"][:n], z["zy"][:n], cov[:n], batch, th)
+    rng = np.random.default_rng(12)
+    m = 3000
+    gt = np.full((m, 21), 1e-9, np.float32); zy = np.full((m, 3), 1e-9, np.float32)
+    gt[np.arange(m), rng.integers(0, 12, m)] = np.linspace(0.05, 0.99999, m).astype(np.float32); gt[::301, :] = 0; gt[::301, 2] = 1.0
+    zy[np.arange(m), rng.integers(0, 3, m)] = rng.uniform(0.34, 1.0, m).astype(np.float32)
+    refb = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, m)]
+    c8 = np.zeros((m, 8), np.float32)
+    for i in range(m):
+        r = "ACGT".index(chr(refb[i])); d = int(rng.choice([0, 6, 64, 128, 100])); a = (r + 1) % 4
+        c8[i, a] = int(rng.integers(0, d + 1)) if d else 0; c8[i, r] = -d
+    pos = np.arange(1, m + 1).astype(np.int32)
+    rec = records_reference(pos, refb, gt, zy, c8)
+    buf = np.empty(vcf_buffer_bytes(m, "chrQ"), np.uint8)
+    w = format_compact_records_into(buf, "chrQ", rec, 1000, 4)
+    assert buf[:w].tobytes() == format_records("chrQ", pos, refb, gt, zy, c8, 1000, 4)
+    # streaming assembler in records mode
+    import io
+    sink = io.BytesIO(); asm = ContigVcfAssembler("chrQ", 1000, 2, sink)
+    for a, b in ((0, 999), (999, 1001), (1001, 3000)):
+        asm.add_records(rec[a:b])
+    asm.close()
+    assert sink.getvalue() == buf[:w].tobytes()
+
+
 def test_contig_assembler_keeps_batch_composition(golden, small_case):
     """Region-by-region streaming must give the same text as formatting the whole contig at once."""
     import io

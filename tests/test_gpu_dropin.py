@@ -95,3 +95,20 @@ def test_lstmnetwork_seam(golden_weights, small_case, golden):
     z = np.load(golden / "s2_small.npz")
     assert gt.shape == (1000, 21) and zy.shape == (1000, 3) and gt.is_cuda
     assert np.abs(gt.detach().cpu().numpy() - z["gt"][:1000]).max() < 2e-5
+
+
+def test_gpu_site_records_give_identical_vcf_bytes(golden_weights, small_case):
+    """site_record_kernel + compact formatter == array formatter on the same GPU probabilities."""
+    import io
+    import torch
+    from nanosnp_b200.caller import call_contig
+    from nanosnp_b200.pipeline import PileupEngine, PileupModelForward, PileupModelWeights
+    from nanosnp_b200.runner import RegionRunner
+    w = PileupModelWeights(*golden_weights, device="cuda:0")
+    outs = []
+    for records in (False, True):
+        runner = RegionRunner(PileupEngine("cuda:0"), PileupModelForward(w, 1), records=records)
+        sink = io.BytesIO()
+        call_contig(runner, small_case["reads"], small_case["ref"], "ctg1", sink, 1000, 9_000)
+        outs.append(sink.getvalue())
+    assert outs[0] == outs[1] and len(outs[0]) > 100_000

@@ -53,7 +53,7 @@ def predict(model: LSTMNetwork, testing_paths, reference_index_file, batch_size,
     def get_runner():
         nonlocal runner
         if runner is None:
-            runner = RegionRunner(PileupEngine(device), model._forward())
+            runner = RegionRunner(PileupEngine(device), model._forward(), records=True)
         return runner
 
     with open(output_file, "wb") as fwriter:

@@ -126,7 +126,6 @@ struct TileSmem {
     uint32_t refx[T / 16 + 2];    // 01 at non-ACGT reference positions (forces a "mismatch" event)
     uint32_t skipcov[T / 32];     // positions inside a reference skip (N op)
     uint8_t  refc[T];
-    int32_t  stage[kStageRows * 18];
     int32_t  thr_snp[kGateTab], thr_indel[kGateTab];   // smallest count c with (double)c / den >= min_af
     int32_t  rlist[kReadList];
     int32_t  warp_tot[kWarps][4];
@@ -164,9 +163,12 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
     const uint32_t* seqw = reinterpret_cast<const uint32_t*>(rd.seq2);
     const uint32_t* nmw = reinterpret_cast<const uint32_t*>(rd.nmask);
 
-    for (int64_t k = c0 + ((int64_t)chunk << kCkShift); k < c1 && R <= te; k += 32) {
-        int op = 6, len = 0;                                            // pad: consumes nothing
-        if (k + lane < c1) { const uint32_t cg = __ldg(rd.cigar + k + lane); op = cg & 15; len = cg >> 4; }
+    const int64_t k0 = c0 + ((int64_t)chunk << kCkShift);
+    uint32_t cg_next = (k0 + lane < c1) ? __ldg(rd.cigar + k0 + lane) : 6u;     // software-pipelined CIGAR loads
+    for (int64_t k = k0; k < c1 && R <= te; k += 32) {
+        const uint32_t cg = cg_next;
+        cg_next = (k + 32 + lane < c1) ? __ldg(rd.cigar + k + 32 + lane) : 6u;
+        const int op = cg & 15, len = cg >> 4;                          // 6 = pad: consumes nothing
         const int rl = op_ref(op) ? len : 0, ql = op_query(op) ? len : 0;
         const int ri = warp_incl_scan(rl), qi = warp_incl_scan(ql);
         const int64_t rs = R + ri - rl;                                 // reference start of this lane's op
@@ -279,7 +281,7 @@ __device__ __forceinline__ int min_count_for_af(double af, int den) {
 }
 
 template <int T>
-__global__ void __launch_bounds__(kThreads, 3) pileup_tile_kernel(nsnp_reads_t rd, nsnp_params_t prm, const uint8_t* __restrict__ ref,
+__global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t rd, nsnp_params_t prm, const uint8_t* __restrict__ ref,
                                                                int64_t region_start, int64_t region_len, int n_tiles,
                                                                Workspace ws, int32_t* __restrict__ counts,
                                                                uint8_t* __restrict__ flags, int32_t* status)
@@ -403,24 +405,56 @@ __global__ void __launch_bounds__(kThreads, 3) pileup_tile_kernel(nsnp_reads_t r
                 tot0 = c4 & 0xFF; tot1 = (c4 >> 8) & 0xFF; tot2 = (c4 >> 16) & 0xFF; tot3 = c4 >> 24;
                 mx0 = tot0; mx1 = tot1; mx2 = tot2; mx3 = tot3;
                 if (deep || ((c4 + 0x7E7E7E7Eu) & 0x80808080u)) {             // some byte >= 2
-                    tot0 = tot1 = tot2 = tot3 = 0; mx0 = mx1 = mx2 = mx3 = 0;
+                    // pass 1 over the chain: totals per class and how many events equal the FIRST event seen of their
+                    // class.  All equal -> multiplicity = total; a class of two unequal events -> 1.  Only a class with
+                    // >= 3 events that are not all identical needs the quadratic pass below (rare).
+                    int tt[4] = {0, 0, 0, 0}, same[4] = {0, 0, 0, 0};
+                    uint32_t finfo[4] = {0, 0, 0, 0};
+                    uint64_t fseq[4] = {0, 0, 0, 0};
                     for (uint32_t e = sm.head[p]; e != 0xFFFFFFFFu;) {
                         const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(slab + e));
                         const int cls = (raw.y >> 8) & 3, len = raw.y & 0xFF;
                         const uint64_t g = (uint64_t)raw.z | ((uint64_t)raw.w << 32);
-                        // multiplicity = this event + identical events further down the chain: the group member
-                        // nearest the head sees the whole group
-                        int mult = 1;
-                        for (uint32_t f = raw.x; f != 0xFFFFFFFFu;) {
-                            const uint4 o = __ldcg(reinterpret_cast<const uint4*>(slab + f));
-                            if ((o.y & 0x3FF) == (raw.y & 0x3FF) &&
-                                (cls >= 2 || same_insert(seqw, nmw, g, (uint64_t)o.z | ((uint64_t)o.w << 32), len))) ++mult;
-                            f = o.x;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (cls == c) {
+                                if (tt[c] == 0) { finfo[c] = raw.y & 0x3FF; fseq[c] = g; }
+                                else if ((raw.y & 0x3FF) == finfo[c] && (c >= 2 || same_insert(seqw, nmw, g, fseq[c], len))) ++same[c];
+                                ++tt[c];
+                            }
                         }
-                        if (cls == 0) { ++tot0; mx0 = max(mx0, mult); } else if (cls == 1) { ++tot1; mx1 = max(mx1, mult); }
-                        else if (cls == 2) { ++tot2; mx2 = max(mx2, mult); } else { ++tot3; mx3 = max(mx3, mult); }
                         e = raw.x;
                     }
+                    int mxs[4]; uint32_t need_full = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (tt[c] <= 1 || same[c] == tt[c] - 1) mxs[c] = tt[c];
+                        else if (tt[c] == 2) mxs[c] = 1;
+                        else { mxs[c] = 0; need_full |= 1u << c; }
+                    }
+                    if (need_full) {
+                        for (uint32_t e = sm.head[p]; e != 0xFFFFFFFFu;) {
+                            const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(slab + e));
+                            const int cls = (raw.y >> 8) & 3, len = raw.y & 0xFF;
+                            if ((need_full >> cls) & 1u) {
+                                const uint64_t g = (uint64_t)raw.z | ((uint64_t)raw.w << 32);
+                                // multiplicity = this event + identical events further down the chain: the group member
+                                // nearest the head sees the whole group
+                                int mult = 1;
+                                for (uint32_t f = raw.x; f != 0xFFFFFFFFu;) {
+                                    const uint4 o = __ldcg(reinterpret_cast<const uint4*>(slab + f));
+                                    if ((o.y & 0x3FF) == (raw.y & 0x3FF) &&
+                                        (cls >= 2 || same_insert(seqw, nmw, g, (uint64_t)o.z | ((uint64_t)o.w << 32), len))) ++mult;
+                                    f = o.x;
+                                }
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) if (cls == c) mxs[c] = max(mxs[c], mult);
+                            }
+                            e = raw.x;
+                        }
+                    }
+                    tot0 = tt[0]; tot1 = tt[1]; tot2 = tt[2]; tot3 = tt[3];
+                    mx0 = mxs[0]; mx1 = mxs[1]; mx2 = mxs[2]; mx3 = mxs[3];
                 }
                 const uint32_t md = sm.ms[p], dd = sm.ds[p], nnv = sm.nn[p];
                 const int mf = (int)(md & 0xFFFF) - (int)(nnv & 0xFFFF), mr = (int)(md >> 16) - (int)(nnv >> 16);
@@ -467,27 +501,22 @@ __global__ void __launch_bounds__(kThreads, 3) pileup_tile_kernel(nsnp_reads_t r
                 const bool covered = (int)(md & 0xFFFF) + (int)(md >> 16) + df + dr > 0 || ((sm.skipcov[p >> 5] >> (p & 31)) & 1u);
                 const bool gate = covered && rc4 < 4 && pass && depth >= prm.min_coverage;       // main.cpp:196
                 flags[(ts - region_start) + p] = (uint8_t)((covered ? NSNP_F_COVERED : 0) | (gate ? NSNP_F_GATE : 0));
-                int2* row = reinterpret_cast<int2*>(sm.stage + tid * 18);            // = warp slice + lane row
-                row[0] = make_int2(chr == 0 ? -mf : cf[0], chr == 1 ? -mf : cf[1]);
-                row[1] = make_int2(chr == 2 ? -mf : cf[2], chr == 3 ? -mf : cf[3]);
-                row[2] = make_int2(tot0, mx0); row[3] = make_int2(tot2, mx2);
-                row[4] = make_int2(df, chr == 0 ? -mr : cr[0]);
-                row[5] = make_int2(chr == 1 ? -mr : cr[1], chr == 2 ? -mr : cr[2]);
-                row[6] = make_int2(chr == 3 ? -mr : cr[3], tot1);
-                row[7] = make_int2(mx1, tot3); row[8] = make_int2(mx3, dr);
+                // the row is 72 contiguous bytes at 72*p: 16-byte vector stores plus one 8-byte store (rows of odd positions
+                // start 8 bytes off a 16-byte boundary); neighbouring lanes complete each other's 32-byte sectors in L2
+                const int v0 = chr == 0 ? -mf : cf[0], v1 = chr == 1 ? -mf : cf[1], v2 = chr == 2 ? -mf : cf[2], v3 = chr == 3 ? -mf : cf[3];
+                const int v9 = chr == 0 ? -mr : cr[0], v10 = chr == 1 ? -mr : cr[1], v11 = chr == 2 ? -mr : cr[2], v12 = chr == 3 ? -mr : cr[3];
+                const int r[18] = {v0, v1, v2, v3, tot0, mx0, tot2, mx2, df, v9, v10, v11, v12, tot1, mx1, tot3, mx3, dr};
+                int32_t* orow = counts + ((ts - region_start) + p) * 18;
+                if ((p & 1) == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) st_stream(reinterpret_cast<int4*>(orow) + q, make_int4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]));
+                    st_stream(reinterpret_cast<int2*>(orow + 16), make_int2(r[16], r[17]));
+                } else {
+                    st_stream(reinterpret_cast<int2*>(orow), make_int2(r[0], r[1]));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) st_stream(reinterpret_cast<int4*>(orow + 2) + q, make_int4(r[2 + 4 * q], r[3 + 4 * q], r[4 + 4 * q], r[5 + 4 * q]));
+                }
             }
-            __syncwarp();
-            {
-                const int rows = min(32, tn - sb);
-                const int n_int = rows * 18;                       // 32 rows = 576 ints = 144 int4 (16-byte aligned: sb % 32 == 0)
-                int32_t* out = counts + ((ts - region_start) + sb) * 18;
-                const int n4 = n_int >> 2;
-                const int32_t* wst = sm.stage + warp * 32 * 18;
-                const int4* st4 = reinterpret_cast<const int4*>(wst);
-                for (int q = lane; q < n4; q += 32) st_stream(reinterpret_cast<int4*>(out) + q, st4[q]);
-                for (int e = (n4 << 2) + lane; e < n_int; e += 32) out[e] = wst[e];
-            }
-            __syncwarp();
         }
     }
 }

@@ -132,15 +132,23 @@ struct TileSmem {
     int32_t  n_rlist, next_task, n_events, tile, ref_has_x;
 };
 
+struct ReadMeta { int32_t rpos; int32_t strand; int64_t c0, c1, sbase; };
+__device__ __forceinline__ ReadMeta load_meta(const nsnp_reads_t& rd, int r) {
+    ReadMeta m;
+    m.rpos = __ldg(rd.pos + r); m.c0 = __ldg(rd.cigar_off + r); m.c1 = __ldg(rd.cigar_off + r + 1);
+    m.sbase = __ldg(rd.seq_off + r); m.strand = (__ldg(rd.flag + r) >> 4) & 1;
+    return m;
+}
+
 template <int T>
 __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t& rd, const Workspace& ws, Event* slab,
-                                             int r, int64_t ts, int64_t te, int32_t* status)
+                                             int r, const ReadMeta& meta, int64_t ts, int64_t te, int32_t* status)
 {
     const int lane = lane_id();
-    const int32_t rpos = rd.pos[r];
-    const int64_t c0 = rd.cigar_off[r], c1 = rd.cigar_off[r + 1];
-    const int64_t sbase = rd.seq_off[r];
-    const int strand = (rd.flag[r] >> 4) & 1;
+    const int32_t rpos = meta.rpos;
+    const int64_t c0 = meta.c0, c1 = meta.c1;
+    const int64_t sbase = meta.sbase;
+    const int strand = meta.strand;
     const uint32_t sinc = 1u << (16 * strand);
     const int nchunks = (int)((c1 - c0 + 31) >> kCkShift);
     const bool ref_has_x = sm.ref_has_x != 0;                       // tile-uniform
@@ -352,12 +360,19 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
             __syncthreads();
             const int nr = sm.n_rlist;
             n_overlap += nr;
-            for (;;) {
-                int t = 0;
-                if (lane == 0) t = atomicAdd(&sm.next_task, 1);
-                t = __shfl_sync(0xffffffffu, t, 0);
-                if (t >= nr) break;
-                process_read<T>(sm, rd, ws, slab, sm.rlist[t], ts, te, status);
+            // dynamic read -> warp assignment; the NEXT read's metadata is fetched before the current one is processed
+            auto grab = [&]() { int t = 0; if (lane == 0) t = atomicAdd(&sm.next_task, 1); return __shfl_sync(0xffffffffu, t, 0); };
+            int t = grab();
+            ReadMeta meta = {};
+            int r = 0;
+            if (t < nr) { r = sm.rlist[t]; meta = load_meta(rd, r); }
+            while (t < nr) {
+                const int tn = grab();
+                ReadMeta mnext = {};
+                int rn = 0;
+                if (tn < nr) { rn = sm.rlist[tn]; mnext = load_meta(rd, rn); }
+                process_read<T>(sm, rd, ws, slab, r, meta, ts, te, status);
+                t = tn; r = rn; meta = mnext;
             }
         }
         __syncthreads();

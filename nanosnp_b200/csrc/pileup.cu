@@ -132,20 +132,22 @@ struct TileSmem {
     int32_t  n_rlist, next_task, n_events, tile, ref_has_x;
 };
 
-struct ReadMeta { int32_t rpos; int32_t strand; int64_t c0, c1, sbase; };
-__device__ __forceinline__ ReadMeta load_meta(const nsnp_reads_t& rd, int r) {
+struct ReadMeta { int32_t rpos; int32_t rend; int32_t strand; int64_t c0, c1, sbase; };
+__device__ __forceinline__ ReadMeta load_meta(const nsnp_reads_t& rd, const Workspace& ws, int r) {
     ReadMeta m;
-    m.rpos = __ldg(rd.pos + r); m.c0 = __ldg(rd.cigar_off + r); m.c1 = __ldg(rd.cigar_off + r + 1);
+    m.rpos = __ldg(rd.pos + r); m.rend = ws.rend[r]; m.c0 = __ldg(rd.cigar_off + r); m.c1 = __ldg(rd.cigar_off + r + 1);
     m.sbase = __ldg(rd.seq_off + r); m.strand = (__ldg(rd.flag + r) >> 4) & 1;
     return m;
 }
 
+// All coordinates are 32-bit: contig positions are int32 (BAM), query offsets are < 2^31; only the absolute base index
+// of the packed sequence array needs 64 bits (added last).
 template <int T>
 __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t& rd, const Workspace& ws, Event* slab,
-                                             int r, const ReadMeta& meta, int64_t ts, int64_t te, int32_t* status)
+                                             int r, const ReadMeta& meta, int ts, int te, int32_t* status)
 {
     const int lane = lane_id();
-    const int32_t rpos = meta.rpos;
+    const int rpos = meta.rpos;
     const int64_t c0 = meta.c0, c1 = meta.c1;
     const int64_t sbase = meta.sbase;
     const int strand = meta.strand;
@@ -154,55 +156,57 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
     const bool ref_has_x = sm.ref_has_x != 0;                       // tile-uniform
     const int32_t* ckr = ws.ck_ref + ((c0 >> kCkShift) + r);
     const int32_t* ckq = ws.ck_q + ((c0 >> kCkShift) + r);
+    // the read's reference span [rpos, rend): two boundary increments per read and tile.  Aligned depth = span depth
+    // minus deletion depth (minus reference skips, which close and reopen the span below): prefix sums in the epilogue.
+    if (lane == 0) atomicAdd(&sm.ms[max(rpos - ts, 0)], sinc);
+    if (lane == 1 && meta.rend < te) atomicAdd(&sm.me[meta.rend - ts], sinc);
     // last chunk whose first op starts at or before the tile start (32-ary search over the checkpoints)
     int lo = 0, hi = nchunks;
     if (rpos < ts) {
         while (hi - lo > 1) {
             const int step = (hi - lo + 31) >> 5;
             const int c = lo + lane * step;
-            const bool le = c < hi && (int64_t)__ldg(ckr + c) <= ts;
+            const bool le = c < hi && __ldg(ckr + c) <= ts;
             const int cnt = __popc(__ballot_sync(0xffffffffu, le));      // monotone: lanes 0..cnt-1 are true, cnt >= 1
             lo = lo + (cnt - 1) * step;
             hi = min(hi, lo + step);
         }
     }
-    int chunk = lo;
-    int64_t R = __ldg(ckr + chunk), Q = __ldg(ckq + chunk);
+    const int chunk = lo;
+    int R = __ldg(ckr + chunk), Q = __ldg(ckq + chunk);
     const uint32_t* seqw = reinterpret_cast<const uint32_t*>(rd.seq2);
     const uint32_t* nmw = reinterpret_cast<const uint32_t*>(rd.nmask);
 
-    const int64_t k0 = c0 + ((int64_t)chunk << kCkShift);
-    uint32_t cg_next = (k0 + lane < c1) ? __ldg(rd.cigar + k0 + lane) : 6u;     // software-pipelined CIGAR loads
-    for (int64_t k = k0; k < c1 && R <= te; k += 32) {
+    const uint32_t* cgp = rd.cigar + c0 + ((int64_t)chunk << kCkShift);
+    int left = (int)(c1 - c0) - (chunk << kCkShift);                             // ops from this chunk to the end of the read
+    uint32_t cg_next = lane < left ? __ldg(cgp + lane) : 6u;                      // software-pipelined CIGAR loads
+    for (; left > 0 && R <= te; left -= 32, cgp += 32) {
         const uint32_t cg = cg_next;
-        cg_next = (k + 32 + lane < c1) ? __ldg(rd.cigar + k + 32 + lane) : 6u;
+        cg_next = (32 + lane < left) ? __ldg(cgp + 32 + lane) : 6u;
         const int op = cg & 15, len = cg >> 4;                          // 6 = pad: consumes nothing
         const int rl = op_ref(op) ? len : 0, ql = op_query(op) ? len : 0;
         const int ri = warp_incl_scan(rl), qi = warp_incl_scan(ql);
-        const int64_t rs = R + ri - rl;                                 // reference start of this lane's op
-        const int64_t qs = Q + qi - ql;                                 // query start (relative to the read)
+        const int rs = R + ri - rl;                                     // reference start of this lane's op
+        const int qs = Q + qi - ql;                                     // query start (relative to the read)
         R += __shfl_sync(0xffffffffu, ri, 31);
         Q += __shfl_sync(0xffffffffu, qi, 31);
 
         // ---- phase 1: one lane per CIGAR op, straight-line predicated bookkeeping ----
         const bool aligned = op_aligned(op), isdel = op == 2;
-        const int64_t a = rs > ts ? rs : ts, b = (rs + len) < te ? (rs + len) : te;      // clipped reference span
-        const bool span = (aligned || isdel) && a < b;
-        if (span) {                                                                      // run boundaries (depth = prefix sum later)
-            uint32_t* st = aligned ? sm.ms : sm.ds;
-            uint32_t* en = aligned ? sm.me : sm.de;
-            atomicAdd(&st[(int)(a - ts)], sinc);
-            if (b < te) atomicAdd(&en[(int)(b - ts)], sinc);
+        const int a = max(rs, ts), b = min(rs + len, te);                               // clipped reference span
+        if (isdel && a < b) {                                                           // '*' / '#' run boundaries
+            atomicAdd(&sm.ds[a - ts], sinc);
+            if (b < te) atomicAdd(&sm.de[b - ts], sinc);
         }
         // indel event anchored at the preceding reference position (appendix A.8 iii/iv); leading ops are never reported
-        const int64_t anchor = rs - 1;
+        const int anchor = rs - 1;
         if ((op == 1 || isdel) && len <= NSNP_MAX_INDEL && rs > rpos && anchor >= ts && anchor < te) {
             const int cls = (isdel ? 2 : 0) + strand;
             const int e = atomicAdd(&sm.n_events, 1);
-            atomicAdd(&sm.cnt4[(int)(anchor - ts)], 1u << (8 * cls));
+            atomicAdd(&sm.cnt4[anchor - ts], 1u << (8 * cls));
             if (e < ws.slab_cap) {
                 Event ev;
-                ev.next = atomicExch(&sm.head[(int)(anchor - ts)], (uint32_t)e);
+                ev.next = atomicExch(&sm.head[anchor - ts], (uint32_t)e);
                 ev.info = (uint32_t)len | ((uint32_t)cls << 8);
                 ev.seq = (uint64_t)(sbase + qs);
                 slab[e] = ev;
@@ -210,18 +214,20 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
                 dev_fail(status, DEV_E_INDEL_SLAB, sm.tile);
             }
         }
-        if (op == 3) {                                                                   // reference skip: covered, nothing counted
-            for (int64_t p = a; p < b; ++p) atomicOr(&sm.skipcov[(int)(p - ts) >> 5], 1u << ((int)(p - ts) & 31));
+        if (op == 3 && a < b) {                                          // reference skip: covered, nothing counted
+            atomicAdd(&sm.me[a - ts], sinc);                             // close the span over the skip, reopen after it
+            if (b < te) atomicAdd(&sm.ms[b - ts], sinc);
+            for (int p = a; p < b; ++p) atomicOr(&sm.skipcov[(p - ts) >> 5], 1u << ((p - ts) & 31));
         }
 
         // ---- phase 2: mismatch detection, one lane per 16-base word of any aligned run of this chunk.  The words of
         //      all 32 ops are flattened (warp scan) so long runs do not leave the other lanes idle. ----
-        const int n = (aligned && a < b) ? (int)(b - a) : 0;
+        const int n = (aligned && a < b) ? (b - a) : 0;
         const int nw = (n + 15) >> 4;
         const int winc = warp_incl_scan(nw);
         const int W = __shfl_sync(0xffffffffu, winc, 31);
-        const int pa = (int)(a - ts);
-        const int64_t g = sbase + qs + (a - rs);
+        const int pa = a - ts;
+        const int qa = qs + (a - rs);                                    // query offset of the first clipped base
         for (int wb = 0; wb < W; wb += 32) {
             const int f = wb + lane;
             // owner = number of lanes whose inclusive word count is <= f (binary search across lanes)
@@ -231,11 +237,11 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
             const int ex_j = __shfl_sync(0xffffffffu, winc - nw, j);
             const int pa_j = __shfl_sync(0xffffffffu, pa, j);
             const int n_j = __shfl_sync(0xffffffffu, n, j);
-            const uint32_t glo = __shfl_sync(0xffffffffu, (uint32_t)g, j), ghi = __shfl_sync(0xffffffffu, (uint32_t)((uint64_t)g >> 32), j);
+            const int qa_j = __shfl_sync(0xffffffffu, qa, j);
             if (f < W) {
                 const int o = (f - ex_j) << 4;
                 const int m = min(16, n_j - o);
-                const int64_t gw = (int64_t)(((uint64_t)ghi << 32) | glo) + o;
+                const int64_t gw = sbase + (qa_j + o);
                 const int pw = pa_j + o;
                 const uint32_t sw = bases16_g(seqw, gw);
                 const uint32_t rw = bases16(sm.ref2, pw);
@@ -316,9 +322,9 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
         __syncthreads();
         const int tile = sm.tile;
         if (tile >= n_tiles) break;
-        const int64_t ts = region_start + (int64_t)tile * T;
-        const int64_t te = min(ts + T, region_start + region_len);
-        const int tn = (int)(te - ts);
+        const int ts = (int)region_start + tile * T;                          // contig coordinates are int32 (checked by the host)
+        const int te = (int)min((int64_t)ts + T, region_start + region_len);
+        const int tn = te - ts;
 
         // ---- clear counters, stage the reference tile ----
         {
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int pp = tid * 4 + j;
-                const uint8_t ch = pp < tn ? ref[ts + pp] : (uint8_t)'N';
+                const uint8_t ch = pp < tn ? ref[(int64_t)ts + pp] : (uint8_t)'N';
                 sm.refc[pp] = ch;
                 const int cd = nt4(ch);
                 if (cd < 4) r2 |= (uint32_t)cd << (2 * j); else rx |= 1u << (2 * j);
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
             __syncthreads();
             for (int r = rb + tid; r < min(rhi, rb + kReadList); r += kThreads) {
                 // overlap test; a read that merely starts at te has no anchor inside the tile
-                if ((int64_t)rd.pos[r] < te && (int64_t)ws.rend[r] > ts) sm.rlist[atomicAdd(&sm.n_rlist, 1)] = r;
+                if (rd.pos[r] < te && ws.rend[r] > ts) sm.rlist[atomicAdd(&sm.n_rlist, 1)] = r;
             }
             __syncthreads();
             const int nr = sm.n_rlist;
@@ -365,12 +371,12 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
             int t = grab();
             ReadMeta meta = {};
             int r = 0;
-            if (t < nr) { r = sm.rlist[t]; meta = load_meta(rd, r); }
+            if (t < nr) { r = sm.rlist[t]; meta = load_meta(rd, ws, r); }
             while (t < nr) {
                 const int tn = grab();
                 ReadMeta mnext = {};
                 int rn = 0;
-                if (tn < nr) { rn = sm.rlist[tn]; mnext = load_meta(rd, rn); }
+                if (tn < nr) { rn = sm.rlist[tn]; mnext = load_meta(rd, ws, rn); }
                 process_read<T>(sm, rd, ws, slab, r, meta, ts, te, status);
                 t = tn; r = rn; meta = mnext;
             }
@@ -382,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
         // ---- prefix sums: run starts/ends -> depths (fwd | rev << 16 stays valid: depths are < 65536) ----
         {
             constexpr int K = T / kThreads;
-            int s0 = 0, s1 = 0, s2 = 0, s3 = 0;          // aligned fwd, aligned rev, del fwd, del rev
+            int s0 = 0, s1 = 0, s2 = 0, s3 = 0;          // read span fwd, span rev, del fwd, del rev
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 const int p = tid * K + j;
@@ -401,76 +407,98 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
                 const uint32_t a = sm.ms[p], b = sm.me[p], c = sm.ds[p], d = sm.de[p];
                 e0 += (int)(a & 0xFFFF) - (int)(b & 0xFFFF); e1 += (int)(a >> 16) - (int)(b >> 16);
                 e2 += (int)(c & 0xFFFF) - (int)(d & 0xFFFF); e3 += (int)(c >> 16) - (int)(d >> 16);
-                sm.ms[p] = (uint32_t)e0 | ((uint32_t)e1 << 16);
+                sm.ms[p] = (uint32_t)(e0 - e2) | ((uint32_t)(e1 - e3) << 16);        // aligned depth = span - deletions
                 sm.ds[p] = (uint32_t)e2 | ((uint32_t)e3 << 16);
             }
         }
         __syncthreads();
 
-        // ---- epilogue: 18 channels + gate per position, staged, then coalesced stores.  Every warp owns 32 consecutive
-        //      positions at a time and its own 2304-byte slice of the staging buffer, so the loop needs no block-wide
-        //      barrier: a warp with a long indel chain to walk only delays itself. ----
-        for (int sb = warp * 32; sb < tn; sb += kThreads) {
-            const int p = sb + lane;
-            if (p < tn) {
-                // indel channels: totals from the class counters; the chain is walked only where a class holds >= 2
-                // events (multiplicity of the most frequent identical indel, I1/D1) or the counters may have wrapped
-                int tot0, tot1, tot2, tot3, mx0, mx1, mx2, mx3;
-                const uint32_t c4 = sm.cnt4[p];
-                tot0 = c4 & 0xFF; tot1 = (c4 >> 8) & 0xFF; tot2 = (c4 >> 16) & 0xFF; tot3 = c4 >> 24;
-                mx0 = tot0; mx1 = tot1; mx2 = tot2; mx3 = tot3;
-                if (deep || ((c4 + 0x7E7E7E7Eu) & 0x80808080u)) {             // some byte >= 2
-                    // pass 1 over the chain: totals per class and how many events equal the FIRST event seen of their
-                    // class.  All equal -> multiplicity = total; a class of two unequal events -> 1.  Only a class with
-                    // >= 3 events that are not all identical needs the quadratic pass below (rare).
-                    int tt[4] = {0, 0, 0, 0}, same[4] = {0, 0, 0, 0};
-                    uint32_t finfo[4] = {0, 0, 0, 0};
-                    uint64_t fseq[4] = {0, 0, 0, 0};
+        // ---- indel channels.  Totals come from the class counters; the multiplicity of the most frequent identical
+        //      indel (I1/D1) needs a chain walk only where a class holds >= 2 events (or the byte counters may have
+        //      wrapped).  Every warp owns the positions {warp*32 + lane + 256*k}: it first COMPACTS the positions that
+        //      need a walk into a list (ballot ranks), then walks them one per lane, so the walk runs with full lanes
+        //      and the channel epilogue below stays straight-line and convergent.  Results per position:
+        //      cnt4 <- tot I | i << 16,  head <- tot D | d << 16,  me <- max I | i << 16,  de <- max D | d << 16. ----
+        {
+            int32_t* wl = sm.rlist + warp * (T / kWarps);          // the read list is dead here: 128 slots per warp
+            int nlist = 0;
+            for (int sb = warp * 32; sb < T; sb += kThreads) {
+                const int p = sb + lane;
+                const uint32_t c4 = sm.cnt4[p];                    // zero beyond tn
+                const bool need = p < tn && (deep || ((c4 + 0x7E7E7E7Eu) & 0x80808080u));      // some byte >= 2
+                const uint32_t bal = __ballot_sync(0xffffffffu, need);
+                if (need) wl[nlist + __popc(bal & ((1u << lane) - 1u))] = p;
+                else {
+                    const uint32_t t01 = (c4 & 0xFFu) | ((c4 & 0xFF00u) << 8), t23 = ((c4 >> 16) & 0xFFu) | ((c4 >> 24) << 16);
+                    sm.cnt4[p] = t01; sm.head[p] = t23; sm.me[p] = t01; sm.de[p] = t23;
+                }
+                nlist += __popc(bal);
+            }
+            __syncwarp();
+            for (int i = lane; i < nlist; i += 32) {
+                const int p = wl[i];
+                // pass 1 over the chain: totals per class and how many events equal the FIRST event seen of their
+                // class.  All equal -> multiplicity = total; a class of two unequal events -> 1.  Only a class with
+                // >= 3 events that are not all identical needs the quadratic pass below (rare).
+                int tt[4] = {0, 0, 0, 0}, same[4] = {0, 0, 0, 0};
+                uint32_t finfo[4] = {0, 0, 0, 0};
+                uint64_t fseq[4] = {0, 0, 0, 0};
+                for (uint32_t e = sm.head[p]; e != 0xFFFFFFFFu;) {
+                    const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(slab + e));
+                    const int cls = (raw.y >> 8) & 3, len = raw.y & 0xFF;
+                    const uint64_t g = (uint64_t)raw.z | ((uint64_t)raw.w << 32);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (cls == c) {
+                            if (tt[c] == 0) { finfo[c] = raw.y & 0x3FF; fseq[c] = g; }
+                            else if ((raw.y & 0x3FF) == finfo[c] && (c >= 2 || same_insert(seqw, nmw, g, fseq[c], len))) ++same[c];
+                            ++tt[c];
+                        }
+                    }
+                    e = raw.x;
+                }
+                int mxs[4]; uint32_t need_full = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (tt[c] <= 1 || same[c] == tt[c] - 1) mxs[c] = tt[c];
+                    else if (tt[c] == 2) mxs[c] = 1;
+                    else { mxs[c] = 0; need_full |= 1u << c; }
+                }
+                if (need_full) {
                     for (uint32_t e = sm.head[p]; e != 0xFFFFFFFFu;) {
                         const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(slab + e));
                         const int cls = (raw.y >> 8) & 3, len = raw.y & 0xFF;
-                        const uint64_t g = (uint64_t)raw.z | ((uint64_t)raw.w << 32);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (cls == c) {
-                                if (tt[c] == 0) { finfo[c] = raw.y & 0x3FF; fseq[c] = g; }
-                                else if ((raw.y & 0x3FF) == finfo[c] && (c >= 2 || same_insert(seqw, nmw, g, fseq[c], len))) ++same[c];
-                                ++tt[c];
+                        if ((need_full >> cls) & 1u) {
+                            const uint64_t g = (uint64_t)raw.z | ((uint64_t)raw.w << 32);
+                            // multiplicity = this event + identical events further down the chain: the group member
+                            // nearest the head sees the whole group
+                            int mult = 1;
+                            for (uint32_t f = raw.x; f != 0xFFFFFFFFu;) {
+                                const uint4 o = __ldcg(reinterpret_cast<const uint4*>(slab + f));
+                                if ((o.y & 0x3FF) == (raw.y & 0x3FF) &&
+                                    (cls >= 2 || same_insert(seqw, nmw, g, (uint64_t)o.z | ((uint64_t)o.w << 32), len))) ++mult;
+                                f = o.x;
                             }
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) if (cls == c) mxs[c] = max(mxs[c], mult);
                         }
                         e = raw.x;
                     }
-                    int mxs[4]; uint32_t need_full = 0;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (tt[c] <= 1 || same[c] == tt[c] - 1) mxs[c] = tt[c];
-                        else if (tt[c] == 2) mxs[c] = 1;
-                        else { mxs[c] = 0; need_full |= 1u << c; }
-                    }
-                    if (need_full) {
-                        for (uint32_t e = sm.head[p]; e != 0xFFFFFFFFu;) {
-                            const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(slab + e));
-                            const int cls = (raw.y >> 8) & 3, len = raw.y & 0xFF;
-                            if ((need_full >> cls) & 1u) {
-                                const uint64_t g = (uint64_t)raw.z | ((uint64_t)raw.w << 32);
-                                // multiplicity = this event + identical events further down the chain: the group member
-                                // nearest the head sees the whole group
-                                int mult = 1;
-                                for (uint32_t f = raw.x; f != 0xFFFFFFFFu;) {
-                                    const uint4 o = __ldcg(reinterpret_cast<const uint4*>(slab + f));
-                                    if ((o.y & 0x3FF) == (raw.y & 0x3FF) &&
-                                        (cls >= 2 || same_insert(seqw, nmw, g, (uint64_t)o.z | ((uint64_t)o.w << 32), len))) ++mult;
-                                    f = o.x;
-                                }
-#pragma unroll
-                                for (int c = 0; c < 4; ++c) if (cls == c) mxs[c] = max(mxs[c], mult);
-                            }
-                            e = raw.x;
-                        }
-                    }
-                    tot0 = tt[0]; tot1 = tt[1]; tot2 = tt[2]; tot3 = tt[3];
-                    mx0 = mxs[0]; mx1 = mxs[1]; mx2 = mxs[2]; mx3 = mxs[3];
                 }
+                sm.cnt4[p] = (uint32_t)tt[0] | ((uint32_t)tt[1] << 16); sm.head[p] = (uint32_t)tt[2] | ((uint32_t)tt[3] << 16);
+                sm.me[p] = (uint32_t)mxs[0] | ((uint32_t)mxs[1] << 16); sm.de[p] = (uint32_t)mxs[2] | ((uint32_t)mxs[3] << 16);
+            }
+            __syncwarp();
+        }
+
+        // ---- epilogue: 18 channels + gate per position, rows stored straight from registers.  Warp-private positions:
+        //      no block-wide barrier. ----
+        for (int sb = warp * 32; sb < tn; sb += kThreads) {
+            const int p = sb + lane;
+            if (p < tn) {
+                const uint32_t t01 = sm.cnt4[p], t23 = sm.head[p], m01 = sm.me[p], m23 = sm.de[p];
+                const int tot0 = t01 & 0xFFFF, tot1 = t01 >> 16, tot2 = t23 & 0xFFFF, tot3 = t23 >> 16;
+                const int mx0 = m01 & 0xFFFF, mx1 = m01 >> 16, mx2 = m23 & 0xFFFF, mx3 = m23 >> 16;
                 const uint32_t md = sm.ms[p], dd = sm.ds[p], nnv = sm.nn[p];
                 const int mf = (int)(md & 0xFFFF) - (int)(nnv & 0xFFFF), mr = (int)(md >> 16) - (int)(nnv >> 16);
                 const int df = (int)(dd & 0xFFFF), dr = (int)(dd >> 16);
@@ -515,13 +543,13 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
                 }
                 const bool covered = (int)(md & 0xFFFF) + (int)(md >> 16) + df + dr > 0 || ((sm.skipcov[p >> 5] >> (p & 31)) & 1u);
                 const bool gate = covered && rc4 < 4 && pass && depth >= prm.min_coverage;       // main.cpp:196
-                flags[(ts - region_start) + p] = (uint8_t)((covered ? NSNP_F_COVERED : 0) | (gate ? NSNP_F_GATE : 0));
+                flags[((int64_t)ts - region_start) + p] = (uint8_t)((covered ? NSNP_F_COVERED : 0) | (gate ? NSNP_F_GATE : 0));
                 // the row is 72 contiguous bytes at 72*p: 16-byte vector stores plus one 8-byte store (rows of odd positions
                 // start 8 bytes off a 16-byte boundary); neighbouring lanes complete each other's 32-byte sectors in L2
                 const int v0 = chr == 0 ? -mf : cf[0], v1 = chr == 1 ? -mf : cf[1], v2 = chr == 2 ? -mf : cf[2], v3 = chr == 3 ? -mf : cf[3];
                 const int v9 = chr == 0 ? -mr : cr[0], v10 = chr == 1 ? -mr : cr[1], v11 = chr == 2 ? -mr : cr[2], v12 = chr == 3 ? -mr : cr[3];
                 const int r[18] = {v0, v1, v2, v3, tot0, mx0, tot2, mx2, df, v9, v10, v11, v12, tot1, mx1, tot3, mx3, dr};
-                int32_t* orow = counts + ((ts - region_start) + p) * 18;
+                int32_t* orow = counts + (((int64_t)ts - region_start) + p) * 18;
                 if ((p & 1) == 0) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) st_stream(reinterpret_cast<int4*>(orow) + q, make_int4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]));
@@ -587,6 +615,7 @@ int nsnp_pileup_counts(const nsnp_reads_t* reads, const uint8_t* ref_dev, int64_
     if (((uintptr_t)reads->seq2 & 3) || ((uintptr_t)reads->nmask & 3) || ((uintptr_t)counts_dev & 15))
         return set_error(NSNP_E_INVALID, "nsnp_pileup_counts: seq2/nmask must be 4-byte and counts 16-byte aligned");
     if (reads->n_reads > 0x7fffffff - 1) return set_error(NSNP_E_UNSUPPORTED, "more than 2^31 reads in one call");
+    if (contig_len > 0x7fffffff - 4096) return set_error(NSNP_E_UNSUPPORTED, "contig longer than 2^31 - 4096 (BAM positions are int32)");
     if (nsnp_device_count() == 0) return set_error(NSNP_E_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
     if (region_len == 0) return NSNP_OK;
 

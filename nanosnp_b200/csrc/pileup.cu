@@ -89,16 +89,22 @@ __global__ void __launch_bounds__(256) read_scan_kernel(nsnp_reads_t rd, nsnp_pa
         const int64_t c0 = rd.cigar_off[r], c1 = rd.cigar_off[r + 1];
         const int64_t slot0 = (c0 >> kCkShift) + r;
         int32_t R = pos, Q = 0;
-        for (int64_t k = c0; k < c1; k += 32) {
-            int rl = 0, ql = 0;
-            if (k + lane < c1) {
-                const uint32_t cg = __ldg(rd.cigar + k + lane);
-                const int op = cg & 15, len = cg >> 4;
-                rl = op_ref(op) ? len : 0; ql = op_query(op) ? len : 0;
+        // kUnroll chunks of 32 ops per iteration: the loads are independent, so a long read (thousands of ops: the
+        // critical path of this kernel) keeps kUnroll loads in flight instead of one
+        constexpr int kUnroll = 8;
+        for (int64_t k = c0; k < c1; k += 32 * kUnroll) {
+            uint32_t cg[kUnroll];
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) cg[j] = (k + 32 * j + lane < c1) ? __ldg(rd.cigar + k + 32 * j + lane) : 6u;   // 6 = pad
+            const int64_t s = slot0 + ((k - c0) >> kCkShift);
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                const int op = cg[j] & 15, len = cg[j] >> 4;
+                const int rl = op_ref(op) ? len : 0, ql = op_query(op) ? len : 0;
+                if (lane == j && k + 32 * j < c1) { ws.ck_ref[s + j] = R; ws.ck_q[s + j] = Q; }
+                R += __reduce_add_sync(0xffffffffu, rl);
+                Q += __reduce_add_sync(0xffffffffu, ql);
             }
-            if (lane == 0) { const int64_t s = slot0 + ((k - c0) >> kCkShift); ws.ck_ref[s] = R; ws.ck_q[s] = Q; }
-            R += __reduce_add_sync(0xffffffffu, rl);
-            Q += __reduce_add_sync(0xffffffffu, ql);
         }
         if (lane == 0) ws.rend[r] = R;
         // tiles this read overlaps
@@ -114,18 +120,26 @@ __global__ void __launch_bounds__(256) read_scan_kernel(nsnp_reads_t rd, nsnp_pa
 // ------------------------------------------------------------------------------------------------
 constexpr int kGateTab = 256;            // AF-gate thresholds are tabulated for depths below this
 
+constexpr uint32_t kBias = 0x40004000u; // packed signed boundary deltas: each u16 half carries +0x4000
+constexpr int kMaxOverlap = 16383;       // reads overlapping one tile (keeps the biased halves inside [1, 0x7FFF])
+constexpr uint32_t kNoEvent = 0xFFFFFFFFu;
+
 template <int T>
 struct TileSmem {
+    // --- cleared to zero per tile (contiguous) ---
     uint32_t base[4][T];          // mismatch counters, u16 pairs: [strand*2 + (b>>1)][p], half = b&1
     uint32_t nn[T];               // read-N bases: fwd | rev << 16
-    uint32_t ms[T], me[T];        // aligned-run starts / ends (fwd | rev << 16); after the scan: aligned depth
-    uint32_t ds[T], de[T];        // deletion-span starts / ends;                after the scan: '*' / '#' depth
     uint32_t cnt4[T];             // indel events per class (I i D d), one byte each (exact while <= 255 reads overlap)
-    uint32_t head[T];             // indel event chain heads
+    uint32_t dfast[T];            // deletions of length 1 / 2 per strand, one byte each: D1 D2 d1 d2
+    uint32_t ifast[2][T];         // 1-base insertions per strand, one byte per inserted base: A C G T
+    // --- cleared to kBias ---
+    uint32_t ms[T];               // read-span boundary deltas (fwd | rev << 16, biased); after the scan: aligned depth
+    uint32_t ds[T];               // deletion-span boundary deltas;                      after the scan: '*' / '#' depth
+    // --- cleared to kNoEvent ---
+    uint32_t head[T];             // chain heads of the indel events that have no fast counter
     uint32_t ref2[T / 16 + 2];    // 2-bit reference tile
     uint32_t refx[T / 16 + 2];    // 01 at non-ACGT reference positions (forces a "mismatch" event)
     uint32_t skipcov[T / 32];     // positions inside a reference skip (N op)
-    uint8_t  refc[T];
     int32_t  thr_snp[kGateTab], thr_indel[kGateTab];   // smallest count c with (double)c / den >= min_af
     int32_t  rlist[kReadList];
     int32_t  warp_tot[kWarps][4];
@@ -144,7 +158,7 @@ __device__ __forceinline__ ReadMeta load_meta(const nsnp_reads_t& rd, const Work
 // of the packed sequence array needs 64 bits (added last).
 template <int T>
 __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t& rd, const Workspace& ws, Event* slab,
-                                             int r, const ReadMeta& meta, int ts, int te, int32_t* status)
+                                             int r, const ReadMeta& meta, int ts, int te, bool deep, int32_t* status)
 {
     const int lane = lane_id();
     const int rpos = meta.rpos;
@@ -159,7 +173,7 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
     // the read's reference span [rpos, rend): two boundary increments per read and tile.  Aligned depth = span depth
     // minus deletion depth (minus reference skips, which close and reopen the span below): prefix sums in the epilogue.
     if (lane == 0) atomicAdd(&sm.ms[max(rpos - ts, 0)], sinc);
-    if (lane == 1 && meta.rend < te) atomicAdd(&sm.me[meta.rend - ts], sinc);
+    if (lane == 1 && meta.rend < te) atomicSub(&sm.ms[meta.rend - ts], sinc);
     // last chunk whose first op starts at or before the tile start (32-ary search over the checkpoints)
     int lo = 0, hi = nchunks;
     if (rpos < ts) {
@@ -196,26 +210,40 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
         const int a = max(rs, ts), b = min(rs + len, te);                               // clipped reference span
         if (isdel && a < b) {                                                           // '*' / '#' run boundaries
             atomicAdd(&sm.ds[a - ts], sinc);
-            if (b < te) atomicAdd(&sm.de[b - ts], sinc);
+            if (b < te) atomicSub(&sm.ds[b - ts], sinc);
         }
-        // indel event anchored at the preceding reference position (appendix A.8 iii/iv); leading ops are never reported
+        // indel event anchored at the preceding reference position (appendix A.8 iii/iv); leading ops are never reported.
+        // Totals per class go to byte counters.  The multiplicity of the most frequent IDENTICAL indel (I1/D1) needs
+        // grouping by (length, sequence): the common groups -- deletions of 1 or 2 bases, 1-base insertions of A/C/G/T --
+        // have their own byte counters; everything else is chained per position and grouped exactly in the epilogue.
         const int anchor = rs - 1;
-        if ((op == 1 || isdel) && len <= NSNP_MAX_INDEL && rs > rpos && anchor >= ts && anchor < te) {
+        const bool isins = op == 1;
+        const bool ev = (isins || isdel) && len <= NSNP_MAX_INDEL && rs > rpos && anchor >= ts && anchor < te;
+        const int64_t gq = sbase + qs;                                   // absolute base index of an inserted sequence
+        const bool ins1 = ev && isins && len == 1 && !deep;
+        uint32_t iword = 0, inbit = 0;
+        if (ins1) { iword = __ldg(seqw + (gq >> 4)); if (nmw) inbit = (__ldg(nmw + (gq >> 5)) >> (gq & 31)) & 1u; }   // consumed after phase 2
+        if (ev) {
             const int cls = (isdel ? 2 : 0) + strand;
-            const int e = atomicAdd(&sm.n_events, 1);
-            atomicAdd(&sm.cnt4[anchor - ts], 1u << (8 * cls));
-            if (e < ws.slab_cap) {
-                Event ev;
-                ev.next = atomicExch(&sm.head[anchor - ts], (uint32_t)e);
-                ev.info = (uint32_t)len | ((uint32_t)cls << 8);
-                ev.seq = (uint64_t)(sbase + qs);
-                slab[e] = ev;
-            } else {
-                dev_fail(status, DEV_E_INDEL_SLAB, sm.tile);
+            const int ap = anchor - ts;
+            atomicAdd(&sm.cnt4[ap], 1u << (8 * cls));
+            if (isdel && len <= 2 && !deep) {
+                atomicAdd(&sm.dfast[ap], 1u << (8 * (2 * strand + len - 1)));
+            } else if (!ins1) {
+                const int e = atomicAdd(&sm.n_events, 1);
+                if (e < ws.slab_cap) {
+                    Event evr;
+                    evr.next = atomicExch(&sm.head[ap], (uint32_t)e);
+                    evr.info = (uint32_t)len | ((uint32_t)cls << 8);
+                    evr.seq = (uint64_t)gq;
+                    slab[e] = evr;
+                } else {
+                    dev_fail(status, DEV_E_INDEL_SLAB, sm.tile);
+                }
             }
         }
         if (op == 3 && a < b) {                                          // reference skip: covered, nothing counted
-            atomicAdd(&sm.me[a - ts], sinc);                             // close the span over the skip, reopen after it
+            atomicSub(&sm.ms[a - ts], sinc);                             // close the span over the skip, reopen after it
             if (b < te) atomicAdd(&sm.ms[b - ts], sinc);
             for (int p = a; p < b; ++p) atomicOr(&sm.skipcov[(p - ts) >> 5], 1u << ((p - ts) & 31));
         }
@@ -261,6 +289,22 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
                     const int j2 = __ffs(mm) - 1; mm &= mm - 1;
                     const int bcode = (sw >> j2) & 3;
                     atomicAdd(&sm.base[strand * 2 + (bcode >> 1)][pw + (j2 >> 1)], 1u << (16 * (bcode & 1)));
+                }
+            }
+        }
+        if (ins1) {                                                      // 1-base insertion: fast counter, or the chain when the base is N
+            if (!inbit) {
+                atomicAdd(&sm.ifast[strand][anchor - ts], 1u << (8 * ((iword >> (2 * (int)(gq & 15))) & 3u)));
+            } else {
+                const int e = atomicAdd(&sm.n_events, 1);
+                if (e < ws.slab_cap) {
+                    Event evr;
+                    evr.next = atomicExch(&sm.head[anchor - ts], (uint32_t)e);
+                    evr.info = 1u | ((uint32_t)strand << 8);
+                    evr.seq = (uint64_t)gq;
+                    slab[e] = evr;
+                } else {
+                    dev_fail(status, DEV_E_INDEL_SLAB, sm.tile);
                 }
             }
         }
@@ -329,8 +373,11 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
         // ---- clear counters, stage the reference tile ----
         {
             uint4* z = reinterpret_cast<uint4*>(&sm.base[0][0]);
-            for (int i = tid; i < 10 * T / 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);   // base, nn, ms, me, ds, de, cnt4
-            for (int i = tid; i < T; i += kThreads) sm.head[i] = 0xFFFFFFFFu;
+            for (int i = tid; i < 9 * T / 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);    // base, nn, cnt4, dfast, ifast
+            uint4* zb = reinterpret_cast<uint4*>(&sm.ms[0]);
+            for (int i = tid; i < 2 * T / 4; i += kThreads) zb[i] = make_uint4(kBias, kBias, kBias, kBias);   // ms, ds
+            uint4* zh = reinterpret_cast<uint4*>(&sm.head[0]);
+            for (int i = tid; i < T / 4; i += kThreads) zh[i] = make_uint4(kNoEvent, kNoEvent, kNoEvent, kNoEvent);
             for (int i = tid; i < T / 32; i += kThreads) sm.skipcov[i] = 0u;
             if (tid == 0) { sm.n_events = 0; }
             // 4 reference bases per thread -> one byte of the 2-bit tile and of the non-ACGT mask
@@ -340,7 +387,6 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
             for (int j = 0; j < 4; ++j) {
                 const int pp = tid * 4 + j;
                 const uint8_t ch = pp < tn ? ref[(int64_t)ts + pp] : (uint8_t)'N';
-                sm.refc[pp] = ch;
                 const int cd = nt4(ch);
                 if (cd < 4) r2 |= (uint32_t)cd << (2 * j); else rx |= 1u << (2 * j);
             }
@@ -355,6 +401,10 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
         // ---- accumulate: reads [lo, hi) that overlap the tile, one warp per read ----
         const int rlo = ws.tile_lo[tile], rhi = ws.tile_hi[tile];
         int n_overlap = 0;                                  // reads that really overlap the tile (block-uniform)
+        // byte counters (class totals, fast indel groups) are exact while <= 255 reads overlap the tile.  The overlap
+        // count is known before any read is processed only when the candidates fit one round; otherwise assume deep:
+        // then every indel event is chained and counted by the walk (16-bit results).
+        bool deep = rhi - rlo > kReadList;
         for (int rb = rlo; rb < rhi; rb += kReadList) {
             __syncthreads();
             if (tid == 0) { sm.n_rlist = 0; sm.next_task = 0; }
@@ -366,6 +416,7 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
             __syncthreads();
             const int nr = sm.n_rlist;
             n_overlap += nr;
+            deep = deep || nr > 255;
             // dynamic read -> warp assignment; the NEXT read's metadata is fetched before the current one is processed
             auto grab = [&]() { int t = 0; if (lane == 0) t = atomicAdd(&sm.next_task, 1); return __shfl_sync(0xffffffffu, t, 0); };
             int t = grab();
@@ -377,24 +428,24 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
                 ReadMeta mnext = {};
                 int rn = 0;
                 if (tn < nr) { rn = sm.rlist[tn]; mnext = load_meta(rd, ws, rn); }
-                process_read<T>(sm, rd, ws, slab, r, meta, ts, te, status);
+                process_read<T>(sm, rd, ws, slab, r, meta, ts, te, deep, status);
                 t = tn; r = rn; meta = mnext;
             }
         }
         __syncthreads();
-        const bool deep = n_overlap > 255;                  // class counters are bytes: exact only below 256 overlapping reads
-        if (tid == 0 && n_overlap > 65535) dev_fail(status, DEV_E_DEPTH, (int)(ts & 0x7fffffff));
+        if (tid == 0 && n_overlap > kMaxOverlap) dev_fail(status, DEV_E_DEPTH, (int)(ts & 0x7fffffff));
 
-        // ---- prefix sums: run starts/ends -> depths (fwd | rev << 16 stays valid: depths are < 65536) ----
+        // ---- prefix sums: biased boundary deltas -> depths (fwd | rev << 16 stays valid: depths are <= kMaxOverlap) ----
         {
             constexpr int K = T / kThreads;
+            constexpr int kB = (int)(kBias & 0xFFFFu);
             int s0 = 0, s1 = 0, s2 = 0, s3 = 0;          // read span fwd, span rev, del fwd, del rev
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 const int p = tid * K + j;
-                const uint32_t a = sm.ms[p], b = sm.me[p], c = sm.ds[p], d = sm.de[p];
-                s0 += (int)(a & 0xFFFF) - (int)(b & 0xFFFF); s1 += (int)(a >> 16) - (int)(b >> 16);
-                s2 += (int)(c & 0xFFFF) - (int)(d & 0xFFFF); s3 += (int)(c >> 16) - (int)(d >> 16);
+                const uint32_t a = sm.ms[p], c = sm.ds[p];
+                s0 += (int)(a & 0xFFFF) - kB; s1 += (int)(a >> 16) - kB;
+                s2 += (int)(c & 0xFFFF) - kB; s3 += (int)(c >> 16) - kB;
             }
             const int i0 = warp_incl_scan(s0), i1 = warp_incl_scan(s1), i2 = warp_incl_scan(s2), i3 = warp_incl_scan(s3);
             if (lane == 31) { sm.warp_tot[warp][0] = i0; sm.warp_tot[warp][1] = i1; sm.warp_tot[warp][2] = i2; sm.warp_tot[warp][3] = i3; }
@@ -404,33 +455,46 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 const int p = tid * K + j;
-                const uint32_t a = sm.ms[p], b = sm.me[p], c = sm.ds[p], d = sm.de[p];
-                e0 += (int)(a & 0xFFFF) - (int)(b & 0xFFFF); e1 += (int)(a >> 16) - (int)(b >> 16);
-                e2 += (int)(c & 0xFFFF) - (int)(d & 0xFFFF); e3 += (int)(c >> 16) - (int)(d >> 16);
+                const uint32_t a = sm.ms[p], c = sm.ds[p];
+                e0 += (int)(a & 0xFFFF) - kB; e1 += (int)(a >> 16) - kB;
+                e2 += (int)(c & 0xFFFF) - kB; e3 += (int)(c >> 16) - kB;
                 sm.ms[p] = (uint32_t)(e0 - e2) | ((uint32_t)(e1 - e3) << 16);        // aligned depth = span - deletions
                 sm.ds[p] = (uint32_t)e2 | ((uint32_t)e3 << 16);
             }
         }
         __syncthreads();
 
-        // ---- indel channels.  Totals come from the class counters; the multiplicity of the most frequent identical
-        //      indel (I1/D1) needs a chain walk only where a class holds >= 2 events (or the byte counters may have
-        //      wrapped).  Every warp owns the positions {warp*32 + lane + 256*k}: it first COMPACTS the positions that
-        //      need a walk into a list (ballot ranks), then walks them one per lane, so the walk runs with full lanes
-        //      and the channel epilogue below stays straight-line and convergent.  Results per position:
-        //      cnt4 <- tot I | i << 16,  head <- tot D | d << 16,  me <- max I | i << 16,  de <- max D | d << 16. ----
+        // ---- indel channels.  Totals come from the class byte counters; the multiplicity of the most frequent identical
+        //      indel (I1/D1) is the larger of the fast group counters and the largest group among the chained events.
+        //      The chain is walked only where a class holds >= 2 chained events (or the tile is deep).  Every warp owns
+        //      the positions {warp*32 + lane + 256*k}: it first COMPACTS the positions that need a walk into a list
+        //      (ballot ranks), then walks them one per lane, so the walk runs with full lanes and the channel epilogue
+        //      below stays straight-line and convergent.  Results per position (u16 pairs):
+        //      cnt4 <- tot I | i << 16,  head <- tot D | d << 16,  dfast <- max I | i << 16,  ifast[0] <- max D | d << 16. ----
         {
+            // per-class (I i D d) sum and maximum of the fast group counters, as bytes of one word each
+            auto fast_stats = [](uint32_t dfv, uint32_t if0, uint32_t if1, uint32_t& fsum, uint32_t& fmax) {
+                auto sum4 = [](uint32_t x) { const uint32_t t = (x & 0x00FF00FFu) + ((x >> 8) & 0x00FF00FFu); return (t + (t >> 16)) & 0x3FFu; };
+                auto max4 = [](uint32_t x) { const uint32_t t = __vmaxu4(x, x >> 16); return max(t & 0xFFu, (t >> 8) & 0xFFu); };
+                const uint32_t d0 = dfv & 0xFFu, d1 = (dfv >> 8) & 0xFFu, d2 = (dfv >> 16) & 0xFFu, d3 = dfv >> 24;
+                fsum = sum4(if0) | (sum4(if1) << 8) | ((d0 + d1) << 16) | ((d2 + d3) << 24);      // each <= 255 when not deep
+                fmax = max4(if0) | (max4(if1) << 8) | (max(d0, d1) << 16) | (max(d2, d3) << 24);
+            };
             int32_t* wl = sm.rlist + warp * (T / kWarps);          // the read list is dead here: 128 slots per warp
             int nlist = 0;
             for (int sb = warp * 32; sb < T; sb += kThreads) {
                 const int p = sb + lane;
                 const uint32_t c4 = sm.cnt4[p];                    // zero beyond tn
-                const bool need = p < tn && (deep || ((c4 + 0x7E7E7E7Eu) & 0x80808080u));      // some byte >= 2
+                uint32_t fsum, fmax;
+                fast_stats(sm.dfast[p], sm.ifast[0][p], sm.ifast[1][p], fsum, fmax);
+                const uint32_t oth = __vsub4(c4, fsum);            // chained events per class
+                const bool need = p < tn && (deep ? sm.head[p] != kNoEvent : ((oth + 0x7E7E7E7Eu) & 0x80808080u) != 0u);   // some byte >= 2
                 const uint32_t bal = __ballot_sync(0xffffffffu, need);
                 if (need) wl[nlist + __popc(bal & ((1u << lane) - 1u))] = p;
                 else {
-                    const uint32_t t01 = (c4 & 0xFFu) | ((c4 & 0xFF00u) << 8), t23 = ((c4 >> 16) & 0xFFu) | ((c4 >> 24) << 16);
-                    sm.cnt4[p] = t01; sm.head[p] = t23; sm.me[p] = t01; sm.de[p] = t23;
+                    const uint32_t mx = __vmaxu4(fmax, oth);       // a class with <= 1 chained event: that event is its own group
+                    sm.cnt4[p] = (c4 & 0xFFu) | ((c4 & 0xFF00u) << 8); sm.head[p] = ((c4 >> 16) & 0xFFu) | ((c4 >> 24) << 16);
+                    sm.dfast[p] = (mx & 0xFFu) | ((mx & 0xFF00u) << 8); sm.ifast[0][p] = ((mx >> 16) & 0xFFu) | ((mx >> 24) << 16);
                 }
                 nlist += __popc(bal);
             }
@@ -443,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
                 int tt[4] = {0, 0, 0, 0}, same[4] = {0, 0, 0, 0};
                 uint32_t finfo[4] = {0, 0, 0, 0};
                 uint64_t fseq[4] = {0, 0, 0, 0};
-                for (uint32_t e = sm.head[p]; e != 0xFFFFFFFFu;) {
+                for (uint32_t e = sm.head[p]; e != kNoEvent;) {
                     const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(slab + e));
                     const int cls = (raw.y >> 8) & 3, len = raw.y & 0xFF;
                     const uint64_t g = (uint64_t)raw.z | ((uint64_t)raw.w << 32);
@@ -465,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
                     else { mxs[c] = 0; need_full |= 1u << c; }
                 }
                 if (need_full) {
-                    for (uint32_t e = sm.head[p]; e != 0xFFFFFFFFu;) {
+                    for (uint32_t e = sm.head[p]; e != kNoEvent;) {
                         const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(slab + e));
                         const int cls = (raw.y >> 8) & 3, len = raw.y & 0xFF;
                         if ((need_full >> cls) & 1u) {
@@ -473,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
                             // multiplicity = this event + identical events further down the chain: the group member
                             // nearest the head sees the whole group
                             int mult = 1;
-                            for (uint32_t f = raw.x; f != 0xFFFFFFFFu;) {
+                            for (uint32_t f = raw.x; f != kNoEvent;) {
                                 const uint4 o = __ldcg(reinterpret_cast<const uint4*>(slab + f));
                                 if ((o.y & 0x3FF) == (raw.y & 0x3FF) &&
                                     (cls >= 2 || same_insert(seqw, nmw, g, (uint64_t)o.z | ((uint64_t)o.w << 32), len))) ++mult;
@@ -485,8 +549,15 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
                         e = raw.x;
                     }
                 }
+                if (!deep) {                                        // totals from the byte counters, groups: fast vs chained
+                    const uint32_t c4 = sm.cnt4[p];
+                    uint32_t fsum, fmax;
+                    fast_stats(sm.dfast[p], sm.ifast[0][p], sm.ifast[1][p], fsum, fmax);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { tt[c] = (c4 >> (8 * c)) & 0xFF; mxs[c] = max(mxs[c], (int)((fmax >> (8 * c)) & 0xFF)); }
+                }
                 sm.cnt4[p] = (uint32_t)tt[0] | ((uint32_t)tt[1] << 16); sm.head[p] = (uint32_t)tt[2] | ((uint32_t)tt[3] << 16);
-                sm.me[p] = (uint32_t)mxs[0] | ((uint32_t)mxs[1] << 16); sm.de[p] = (uint32_t)mxs[2] | ((uint32_t)mxs[3] << 16);
+                sm.dfast[p] = (uint32_t)mxs[0] | ((uint32_t)mxs[1] << 16); sm.ifast[0][p] = (uint32_t)mxs[2] | ((uint32_t)mxs[3] << 16);
             }
             __syncwarp();
         }
@@ -496,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
         for (int sb = warp * 32; sb < tn; sb += kThreads) {
             const int p = sb + lane;
             if (p < tn) {
-                const uint32_t t01 = sm.cnt4[p], t23 = sm.head[p], m01 = sm.me[p], m23 = sm.de[p];
+                const uint32_t t01 = sm.cnt4[p], t23 = sm.head[p], m01 = sm.dfast[p], m23 = sm.ifast[0][p];
                 const int tot0 = t01 & 0xFFFF, tot1 = t01 >> 16, tot2 = t23 & 0xFFFF, tot3 = t23 >> 16;
                 const int mx0 = m01 & 0xFFFF, mx1 = m01 >> 16, mx2 = m23 & 0xFFFF, mx3 = m23 >> 16;
                 const uint32_t md = sm.ms[p], dd = sm.ds[p], nnv = sm.nn[p];
@@ -506,59 +577,49 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
                 { const uint32_t w0 = sm.base[0][p], w1 = sm.base[1][p], w2 = sm.base[2][p], w3 = sm.base[3][p];
                   cf[0] = w0 & 0xFFFF; cf[1] = w0 >> 16; cf[2] = w1 & 0xFFFF; cf[3] = w1 >> 16;
                   cr[0] = w2 & 0xFFFF; cr[1] = w2 >> 16; cr[2] = w3 & 0xFFFF; cr[3] = w3 >> 16; }
-                const int rc4 = nt4(sm.refc[p]);
-                const int chr = rc4 < 4 ? rc4 : 0;                                   // evc_base_from: non-ACGT -> 'A'
+                const uint32_t rsh = 2u * (p & 15);
+                const int chr = (sm.ref2[p >> 4] >> rsh) & 3;                        // non-ACGT packs as 0: evc_base_from -> 'A'
+                const bool ref_acgt = ((sm.refx[p >> 4] >> rsh) & 1u) == 0u;
                 // merged-strand tallies (tensor_maker.cpp:124,168-171): the reference base's own count is implied
                 const int allb = mf + mr;
                 int tb[4];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) tb[b] = cf[b] + cr[b];
-                tb[chr] = 0;
+                for (int b = 0; b < 4; ++b) tb[b] = b == chr ? 0 : cf[b] + cr[b];
                 const int refcnt = allb - (tb[0] + tb[1] + tb[2] + tb[3]);
                 const int tI = tot0 + tot1, tD = tot2 + tot3;
                 const int depth = allb + df + dr;
                 // pass_af (tensor_maker.cpp:195-228,248): top allele (stable order A<C<D<G<I<T on ties) differs from the
-                // reference, or a non-reference allele / indel class reaches its minimum frequency
-                bool pass;
-                {
-                    // top != ref  <=>  some non-ref entry beats the ref count, or ties it while sorting before it
-                    const int key_ref = chr == 0 ? 0 : chr == 1 ? 1 : chr == 2 ? 3 : 5;
-                    bool top_other = false;
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int key = b == 0 ? 0 : b == 1 ? 1 : b == 2 ? 3 : 5;
-                        if (b != chr) top_other = top_other || (tb[b] > 0 && (tb[b] > refcnt || (tb[b] == refcnt && key < key_ref)));
-                    }
-                    top_other = top_other || (tD > 0 && (tD > refcnt || (tD == refcnt && 2 < key_ref)));
-                    top_other = top_other || (tI > 0 && (tI > refcnt || (tI == refcnt && 4 < key_ref)));
-                    const int mxb = max(max(tb[0], tb[1]), max(tb[2], tb[3]));
-                    const int mxi = max(tI, tD);
-                    bool af_pass;
-                    if (depth < kGateTab) {
-                        af_pass = (mxb > 0 && mxb >= sm.thr_snp[depth]) || (mxi > 0 && mxi >= sm.thr_indel[depth]);
-                    } else {
-                        af_pass = (mxb > 0 && 1.0 * mxb / depth >= prm.snp_min_af) || (mxi > 0 && 1.0 * mxi / depth >= prm.indel_min_af);
-                    }
-                    pass = top_other || af_pass;
-                }
-                const bool covered = (int)(md & 0xFFFF) + (int)(md >> 16) + df + dr > 0 || ((sm.skipcov[p >> 5] >> (p & 31)) & 1u);
-                const bool gate = covered && rc4 < 4 && pass && depth >= prm.min_coverage;       // main.cpp:196
+                // reference, or a non-reference allele / indel class reaches its minimum frequency.  Branch-free on purpose:
+                // short-circuit logic here split the warp for the rest of the loop body.
+                // top != ref  <=>  some non-ref entry beats the ref count, or ties it while sorting before it
+                const int key_ref = (0x5310 >> (4 * chr)) & 15;                      // A C G T -> 0 1 3 5 (D = 2, I = 4)
+                auto beats = [&](int v, int key) -> bool { return (v > 0) & ((v > refcnt) | ((v == refcnt) & (key < key_ref))); };
+                const bool top_other = beats(tb[0], 0) | beats(tb[1], 1) | beats(tb[2], 3) | beats(tb[3], 5) | beats(tD, 2) | beats(tI, 4);
+                const int mxb = max(max(tb[0], tb[1]), max(tb[2], tb[3]));
+                const int mxi = max(tI, tD);
+                const int dgt = min(depth, kGateTab - 1);
+                bool af_pass = ((mxb > 0) & (mxb >= sm.thr_snp[dgt])) | ((mxi > 0) & (mxi >= sm.thr_indel[dgt]));
+                if (depth >= kGateTab)                                                  // beyond the table: the divide itself
+                    af_pass = (mxb > 0 && 1.0 * mxb / depth >= prm.snp_min_af) || (mxi > 0 && 1.0 * mxi / depth >= prm.indel_min_af);
+                const bool pass = top_other | af_pass;
+                const bool covered = ((int)(md & 0xFFFF) + (int)(md >> 16) + df + dr > 0) | (((sm.skipcov[p >> 5] >> (p & 31)) & 1u) != 0u);
+                const bool gate = covered & ref_acgt & pass & (depth >= prm.min_coverage);      // main.cpp:196
                 flags[((int64_t)ts - region_start) + p] = (uint8_t)((covered ? NSNP_F_COVERED : 0) | (gate ? NSNP_F_GATE : 0));
-                // the row is 72 contiguous bytes at 72*p: 16-byte vector stores plus one 8-byte store (rows of odd positions
-                // start 8 bytes off a 16-byte boundary); neighbouring lanes complete each other's 32-byte sectors in L2
+                // the row is 72 contiguous bytes at 72*p: four 16-byte vector stores plus one 8-byte store.  Rows of odd
+                // positions start 8 bytes off a 16-byte boundary, so the 8-byte piece goes first there and last otherwise;
+                // the values are selected, not branched on (lane parity is loop-invariant: a branch gets unswitched and
+                // the two half-warps then run the whole loop separately).  Neighbouring lanes complete each other's sectors.
                 const int v0 = chr == 0 ? -mf : cf[0], v1 = chr == 1 ? -mf : cf[1], v2 = chr == 2 ? -mf : cf[2], v3 = chr == 3 ? -mf : cf[3];
                 const int v9 = chr == 0 ? -mr : cr[0], v10 = chr == 1 ? -mr : cr[1], v11 = chr == 2 ? -mr : cr[2], v12 = chr == 3 ? -mr : cr[3];
                 const int r[18] = {v0, v1, v2, v3, tot0, mx0, tot2, mx2, df, v9, v10, v11, v12, tot1, mx1, tot3, mx3, dr};
                 int32_t* orow = counts + (((int64_t)ts - region_start) + p) * 18;
-                if ((p & 1) == 0) {
+                const bool odd = (p & 1) != 0;
+                int4* o16 = reinterpret_cast<int4*>(orow + (odd ? 2 : 0));
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) st_stream(reinterpret_cast<int4*>(orow) + q, make_int4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]));
-                    st_stream(reinterpret_cast<int2*>(orow + 16), make_int2(r[16], r[17]));
-                } else {
-                    st_stream(reinterpret_cast<int2*>(orow), make_int2(r[0], r[1]));
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) st_stream(reinterpret_cast<int4*>(orow + 2) + q, make_int4(r[2 + 4 * q], r[3 + 4 * q], r[4 + 4 * q], r[5 + 4 * q]));
-                }
+                for (int q = 0; q < 4; ++q)
+                    st_stream(o16 + q, make_int4(odd ? r[4 * q + 2] : r[4 * q], odd ? r[4 * q + 3] : r[4 * q + 1],
+                                                 odd ? r[4 * q + 4] : r[4 * q + 2], odd ? r[4 * q + 5] : r[4 * q + 3]));
+                st_stream(reinterpret_cast<int2*>(orow + (odd ? 0 : 16)), make_int2(odd ? r[0] : r[16], odd ? r[1] : r[17]));
             }
         }
     }

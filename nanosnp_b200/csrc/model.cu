@@ -12,6 +12,7 @@
 //                        lanes own hidden-unit pairs, warps own site groups, cell state in registers.
 //   lstm_dir_kernel<L1>  one CTA = 32 sites x one direction, 197 KB of weights resident.
 //   tail_kernel          proj + dense/tanh + heads + softmax on the t=16 state.
+#include <stdlib.h>
 #include "model_common.cuh"
 
 namespace nsnp {
@@ -295,7 +296,9 @@ int nsnp_model_pack_weights(const nsnp_model_weights_t* w, void* host_blob, size
 size_t nsnp_model_workspace_bytes(int64_t n_sites) {
     int64_t ch = n_sites < kChunkSites ? n_sites : kChunkSites; if (ch < 1) ch = 1;
     ch = (ch + 127) / 128 * 128;                      // the tensor-core path stores layer-0 output in whole 128-site tiles
-    return (size_t)ch * (kT * 128 + 128) * sizeof(float) + 256;
+    // layer-0 output of one chunk + the t = 16 state of ALL sites (the tail runs once per call, not once per chunk)
+    const int64_t np = ((n_sites < 1 ? 1 : n_sites) + 127) / 128 * 128;
+    return (size_t)ch * kT * 128 * sizeof(float) + (size_t)np * 128 * sizeof(float) + 256;
 }
 
 int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, const float* x_f32_dev, int64_t n,
@@ -324,6 +327,8 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
     }
     float* h0 = (float*)workspace_dev;
     const int64_t ch = n < kChunkSites ? n : kChunkSites;
+    static const bool tail_tc_env = [] { const char* v = getenv("NSNP_TAIL_TC"); return !(v && v[0] == '0'); }();
+    const bool tail_tc = tail_tc_env && precision == NSNP_PREC_F16X3;
     float* h16 = h0 + ((ch + 127) / 128 * 128) * kT * 128;
     // n_dev (device-side site count) only makes sense for a single chunk; larger batches are chunked by the host count
     for (int64_t off = 0; off < n; off += ch) {
@@ -333,14 +338,20 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
         const float* xf = x_f32_dev ? x_f32_dev + off * kT * kF : nullptr;
         dim3 g0((unsigned)((m + Cfg<0>::S - 1) / Cfg<0>::S), 2), g1((unsigned)((m + Cfg<1>::S - 1) / Cfg<1>::S), 2);
         if (precision == NSNP_PREC_F16X3) {
-            if (int e = launch_lstm_tc(blob_dev, xi, xf, h0, h16, m, stream)) return e;
+            if (int e = launch_lstm_tc(blob_dev, xi, xf, h0, h16 + off * 128, m, stream)) return e;
+            if (tail_tc) continue;                   // one tensor-core tail launch over all chunks below
         } else {
             { ProfScope prof(NSNP_PROF_LSTM0, stream); lstm_dir_kernel<0><<<g0, 256, smem0, stream>>>(blob, xi, xf, nullptr, h0, m, nd); }
             { ProfScope prof(NSNP_PROF_LSTM1, stream); lstm_dir_kernel<1><<<g1, 256, smem1, stream>>>(blob, nullptr, nullptr, h0, h16, m, nd); }
         }
         ProfScope prof(NSNP_PROF_TAIL, stream);
-        tail_kernel<<<(unsigned)((m + kTailS - 1) / kTailS), 256, kTailSmem, stream>>>(blob, h16, m, nd, gt_prob_dev + off * 21, zy_prob_dev + off * 3);
+        tail_kernel<<<(unsigned)((m + kTailS - 1) / kTailS), 256, kTailSmem, stream>>>(blob, h16 + (precision == NSNP_PREC_F16X3 ? off * 128 : 0), m, nd,
+                                                                                         gt_prob_dev + off * 21, zy_prob_dev + off * 3);
         if (int e = cuda_status("pileup model kernels")) return e;
+    }
+    if (precision == NSNP_PREC_F16X3 && tail_tc) {
+        ProfScope prof(NSNP_PROF_TAIL, stream);
+        if (int e = launch_tail_tc(blob_dev, h16, n, n <= ch ? n_dev : nullptr, gt_prob_dev, zy_prob_dev, stream)) return e;
     }
     return NSNP_OK;
 }

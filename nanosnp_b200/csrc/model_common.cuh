@@ -42,11 +42,16 @@ constexpr size_t kOffTcBytes = ((kBlobFloats * 4 + 255) / 256) * 256;
 constexpr size_t tc_off(int layer, int dir, int lo) {
     return kOffTcBytes + (layer == 0 ? (size_t)(dir * 2 + lo) * kTcBytes0 : 4 * kTcBytes0 + (size_t)(dir * 2 + lo) * kTcBytes1);
 }
-constexpr size_t kBlobBytes = kOffTcBytes + 4 * kTcBytes0 + 4 * kTcBytes1;
+// tail: W' = dense o output_proj, [k/8 = 16][n = 256 dense outputs][k%8] halfs, hi then lo (64 KB each)
+constexpr size_t kTcBytesTail = (size_t)128 * 256 * 2;
+constexpr size_t kOffTcTail = kOffTcBytes + 4 * kTcBytes0 + 4 * kTcBytes1;
+constexpr size_t kBlobBytes = kOffTcTail + 2 * kTcBytesTail;
 
 // fp16 hi/lo tensor-core LSTM (model_tc.cu).  h0: fp16 [site][33][2][128]; h16: fp32 [site][128].
 int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, cudaStream_t stream);
 int pack_tc_weights(const nsnp_model_weights_t* w, unsigned char* blob);
+// (dense o output_proj) + tanh on the tensor cores, heads + softmax on the FMA pipe (model_tc.cu)
+int launch_tail_tc(const void* blob, const float* h16, int64_t n_max, const int32_t* n_dev, float* gt, float* zy, cudaStream_t stream);
 int debug_tc_gates(const void* blob, const int32_t* xi, int layer, int dir, int cg, const void* h0, float* gates_out, int64_t m, cudaStream_t stream);
 
 }  // namespace nsnp

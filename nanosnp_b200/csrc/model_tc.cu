@@ -22,6 +22,7 @@
 // CG = 2 pairs two CTAs (cta_group::2): M = 256, each CTA holds half of W (N/2 rows) -- that is what makes the
 // layer-1 weights (2 x 104 KB) fit; the leader CTA issues the MMAs, tcgen05.commit multicasts completion.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "model_common.cuh"
 
 namespace nsnp {
@@ -168,6 +169,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
 template <int LAYER> struct TcCfg;
@@ -187,7 +191,7 @@ template <int LAYER, int CG> struct TcSmem {
 // NWQ warps share each TMEM lane quadrant (each thread = one site row x 64/NWQ hidden units).
 // DEBUG: dump the raw accumulators of the first step and return.
 template <int LAYER, int CG, int NWQ, bool DEBUG>
-__global__ void __launch_bounds__(128 * NWQ + (LAYER == 1 ? 32 : 0), (LAYER == 0 && CG == 2 && NWQ == 2) ? 2 : 1)
+__global__ void __launch_bounds__(128 * NWQ + (LAYER == 1 ? 32 : 0), (LAYER == 0 && CG == 2) ? 2 : 1)
 lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict__ xi, const float* __restrict__ xf,
                const __half* __restrict__ h0_in, __half* __restrict__ h0_out, float* __restrict__ h16, float* __restrict__ dbg,
                int64_t n, int dir_override)
@@ -287,11 +291,16 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     //     h0[tile][t][hi|lo][chunk 16][row 128][8 halfs]
     uint64_t* barS = bar + 2;                                        // "input part of A for the next step has landed"
     constexpr uint32_t kPartBytes = 16u * kRows * 16u;               // 32 KB
+    const bool l2_prefetch = (dir_override >> 8) & 1;
     auto stage_h0_bulk = [&](int t) {                                // one thread
         const __half* src = h0_in + ((size_t)blockIdx.x * kT + t) * (2 * kPartBytes / 2);
         mbar_expect_tx(barS, 2 * kPartBytes);
         bulk_g2s(sAhi, src, kPartBytes, barS);
         bulk_g2s(sAlo, src + kPartBytes / 2, kPartBytes, barS);
+        // the rows of the step after this one: pull them into L2 now, so that their bulk copy (issued when the operand
+        // buffer is free again, one step from now) pays L2 latency instead of DRAM latency
+        const int tp = dir == 0 ? t + 1 : t - 1;
+        if (l2_prefetch && tp >= 0 && tp < kT) bulk_prefetch_l2(h0_in + ((size_t)blockIdx.x * kT + tp) * (2 * kPartBytes / 2), 2 * kPartBytes);
     };
     constexpr int XB = IN / 16;                                  // k-blocks of the input part; the rest is the h part
     constexpr uint32_t kTmemCols = LAYER == 1 ? 512 : 256;       // layer 1 double-buffers the accumulator
@@ -319,11 +328,12 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     constexpr uint32_t idesc = make_idesc(128 * CG, 256);
     const bool issuer = cta_rank == 0 && tid == 0;
     // k-blocks [kb0, kb1) x three hi/lo passes into the accumulator at tmem_d
+    const bool x_nomma = !DEBUG && ((dir_override >> 9) & 1), x_noepi = !DEBUG && ((dir_override >> 10) & 1);   // timing experiments
     auto issue = [&](int kb0, int kb1, uint32_t tmem_d, uint32_t acc) {
 #pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
+        for (int pass = 0; pass < (x_nomma ? 1 : 3); ++pass) {
 #pragma unroll 1
-            for (int kb = kb0; kb < kb1; ++kb) {
+            for (int kb = kb0; kb < (x_nomma ? kb0 + 1 : kb1); ++kb) {
                 // pass 0: a_hi.w_hi   pass 1: a_hi.w_lo (layer-0 counts: scaled copy)   pass 2: a_lo.w_hi
                 uint32_t aa = pass == 2 ? a_lo : a_hi;
                 if (LAYER == 0 && pass == 1 && kb < kTcIn0 / 16) aa = a_sc;
@@ -409,6 +419,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
                 // ex2(-2 c' log2e) <= 2^96 needs no clamp; an overflowing (1 + eo) makes rcp return 0 = the exact limit.
                 const float gi = fmaxf(__uint_as_float(v[u]), -25.f), gf = fmaxf(__uint_as_float(v[4 + u]), -25.f);
                 const float gg = fmaxf(__uint_as_float(v[8 + u]), -12.5f), go = __uint_as_float(v[12 + u]);
+                if (x_noepi) { hv[uh * 4 + u] = gi + gf + gg + go; continue; }
                 const float ei = ex2_approx(-kLog2e * gi), ef = ex2_approx(-kLog2e * gf), eg = ex2_approx(-2.f * kLog2e * gg);
                 const float pi = 1.f + ei, pf = 1.f + ef, pg = 1.f + eg;
                 // c' = sigmoid(f) c + sigmoid(i) tanh(g) over one common denominator
@@ -446,6 +457,440 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     if (warp == 0) tmem_dealloc<CG>(tmem_base, kTmemCols);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Layer 0, streaming variant: ONE persistent CTA per SM (cta_group::1, all of W resident: 96 KB), 16 epilogue warps
+// + 1 MMA-issuer warp, double-buffered TMEM accumulator (2 x 256 columns).
+//
+// The per-step barrier of lstm_tc_kernel serialises "all MMAs of step t+1" behind "the whole epilogue of step t".
+// Here the epilogue of step t hands its results to the issuer in K-SLICES: the 64 hidden units are produced in four
+// blocks of 16 (= one MMA k-block each), every warp works on its 4 units of block q and then arrives on mbarrier
+// barK[q]; the issuer warp waits for barK[q] and immediately issues the three hi/lo MMAs of that k-block for step t+1
+// into the OTHER accumulator.  The input part of step t+1 (x_{t+1}, staged at the start of the epilogue) is issued
+// first.  When the epilogue finishes, only the 3 MMAs of the last k-block are still outstanding -- instead of 18 --
+// so the tensor pipe works underneath the MUFU-bound cell update rather than after it.  Epilogue warps never block
+// on each other: the only waits are "my accumulator is complete" (barH) and the issuer's waits.
+// The site tiles of one direction are streamed through the same loop (weights and TMEM are set up once per CTA).
+constexpr int kS0EpiWarps = 16;
+constexpr int kS0Threads = kS0EpiWarps * 32 + 32;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kS0Threads, 1)
+lstm0_stream_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict__ xi, const float* __restrict__ xf,
+                    __half* __restrict__ h0_out, int64_t n, int n_tiles)
+{
+    using S = TcSmem<0, 1>;
+    constexpr int K = kTcK0, IN = kTcIn0;
+    constexpr int XB = IN / 16, HB = (K - IN) / 16;               // 2 input k-blocks, 4 hidden k-blocks
+    constexpr uint32_t LBO_A = kRows * 16, LBO_B = 256 * 16, SBO = 128;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sBhi = smem + S::off_bhi; unsigned char* sBlo = smem + S::off_blo;
+    unsigned char* sAhi = smem + S::off_ahi; unsigned char* sAlo = smem + S::off_alo; unsigned char* sAsc = smem + S::off_asc;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::off_bar);           // [0] barH, [1] barIn, [2..5] barK
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_bar + 48);
+    uint64_t* barH = bar; uint64_t* barIn = bar + 1; uint64_t* barK = bar + 2;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool issuer_warp = warp == kS0EpiWarps;
+    const int quad = warp & 3, sub = (warp >> 2) & 3;
+    const int row = quad * 32 + lane;
+    const int dir = (int)(blockIdx.x & 1);
+    const int tile0 = (int)(blockIdx.x >> 1), tile_stride = (int)(gridDim.x >> 1);
+    const int n_items = tile0 < n_tiles ? (n_tiles - tile0 + tile_stride - 1) / tile_stride : 0;
+    const int total_g = n_items * kT;
+
+    if (tid == 0) {
+        mbar_init(barH, 1); mbar_init(barIn, kS0EpiWarps);
+        for (int q = 0; q < HB; ++q) mbar_init(barK + q, kS0EpiWarps);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<1>(tmem_slot, 512);
+    {
+        const uint4* ghi = reinterpret_cast<const uint4*>(blob + tc_off(0, dir, 0));
+        const uint4* glo = reinterpret_cast<const uint4*>(blob + tc_off(0, dir, 1));
+        uint4* dhi = reinterpret_cast<uint4*>(sBhi); uint4* dlo = reinterpret_cast<uint4*>(sBlo);
+        for (int i = tid; i < (K / 8) * 256; i += kS0Threads) { dhi[i] = __ldg(ghi + i); dlo[i] = __ldg(glo + i); }
+        uint4* a = reinterpret_cast<uint4*>(sAhi);
+        const int n16 = (int)((2 * S::a_bytes + S::sc_bytes) / 16);
+        for (int i = tid; i < n16; i += kS0Threads) a[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (issuer_warp) {
+        if (lane == 0) {
+            const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), a_sc = smem_u32(sAsc), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
+            constexpr uint32_t idesc = make_idesc(128, 256);
+            auto issue_kb = [&](int kb, uint32_t tmem_d, uint32_t first_acc) {
+                // a_hi.w_hi, a_hi.w_lo (counts: scaled copy), a_lo.w_hi
+                const uint64_t bh = make_desc(b_hi + kb * 2 * LBO_B, LBO_B, SBO), bl = make_desc(b_lo + kb * 2 * LBO_B, LBO_B, SBO);
+                const uint32_t a1 = kb < XB ? a_sc : a_hi;
+                umma_f16<1>(tmem_d, make_desc(a_hi + kb * 2 * LBO_A, LBO_A, SBO), bh, idesc, first_acc);
+                umma_f16<1>(tmem_d, make_desc(a1 + kb * 2 * LBO_A, LBO_A, SBO), bl, idesc, 1);
+                umma_f16<1>(tmem_d, make_desc(a_lo + kb * 2 * LBO_A, LBO_A, SBO), bh, idesc, 1);
+            };
+            int step = 0;
+            for (int g = 0; g < total_g; ++g) {
+                const uint32_t acc = tmem_base + (uint32_t)(g & 1) * 256u;
+                mbar_wait(barIn, (uint32_t)(g & 1));                       // x of this step staged; accumulator drained two steps ago
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < XB; ++kb) issue_kb(kb, acc, kb == 0 ? 0u : 1u);
+#pragma unroll 1
+                for (int q = 0; q < HB; ++q) {
+                    if (g > 0) { mbar_wait(barK + q, (uint32_t)((g - 1) & 1)); tc_fence_after(); }
+                    if (step > 0) issue_kb(XB + q, acc, 1u);               // step 0 of a tile: h = 0
+                }
+                umma_commit<1>(barH);
+                if (++step == kT) step = 0;
+            }
+        }
+    } else {
+        // ---- epilogue warps ----
+        int2 xraw[4];
+        auto x_ptr = [&](int g) -> const int2* {
+            const int item = g / kT, st = g - item * kT;
+            const int t = dir == 0 ? st : (kT - 1 - st);
+            int64_t site = (int64_t)(tile0 + item * tile_stride) * kRows + row;
+            if (site >= n) site = n - 1;
+            return reinterpret_cast<const int2*>(xi ? (const void*)(xi + (site * kT + t) * kF) : (const void*)(xf + (site * kT + t) * kF));
+        };
+        // sub 0: x[0..7] (chunk 0), sub 1: x[8..15] (chunk 1), sub 3: x16, x17 + the bias column (chunk 2)
+        auto load_x = [&](int g) {
+            const int2* gp = x_ptr(g);
+            if (sub == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xraw[j] = ldg_nc_volatile(gp + j);
+            } else if (sub == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xraw[j] = ldg_nc_volatile(gp + 4 + j);
+            } else if (sub == 3) {
+                xraw[0] = ldg_nc_volatile(gp + 8);
+            }
+        };
+        auto xval = [&](int j) -> float {
+            const int2 p = xraw[j >> 1];
+            const int b = (j & 1) ? p.y : p.x;
+            return xi ? (float)b : __int_as_float(b);
+        };
+        auto store_x = [&]() {
+            if (sub == 0 || sub == 1) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = xval(j);
+                const HiLo8 s = split8(v);
+                reinterpret_cast<uint4*>(sAhi + sub * LBO_A)[row] = s.hi;
+                reinterpret_cast<uint4*>(sAlo + sub * LBO_A)[row] = s.lo;
+                reinterpret_cast<uint4*>(sAsc + sub * LBO_A)[row] = scale_hi(s.hi);
+            } else if (sub == 3) {
+                const float v[8] = {xval(0), xval(1), 1.0f, 0.f, 0.f, 0.f, 0.f, 0.f};  // x16, x17, bias column
+                const HiLo8 s = split8(v);
+                reinterpret_cast<uint4*>(sAhi + 2 * LBO_A)[row] = s.hi;
+                reinterpret_cast<uint4*>(sAlo + 2 * LBO_A)[row] = s.lo;
+                reinterpret_cast<uint4*>(sAsc + 2 * LBO_A)[row] = scale_hi(s.hi);
+            }
+        };
+        float c[16];
+        if (total_g > 0) {
+            load_x(0); store_x();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(barIn);
+            if (total_g > 1) load_x(1);
+        }
+        int step = 0, item = 0;
+        for (int g = 0; g < total_g; ++g) {
+            const int t = dir == 0 ? step : (kT - 1 - step);
+            const int tile = tile0 + item * tile_stride;
+            const bool live = (int64_t)tile * kRows + row < n;
+            if (step == 0) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) c[u] = 0.f;
+            }
+            mbar_wait(barH, (uint32_t)(g & 1));
+            tc_fence_after();
+            // the MMAs of this step have retired: the input operand takes x of the next step right away
+            if (g + 1 < total_g) {
+                store_x();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(barIn);
+                if (g + 2 < total_g) load_x(g + 2);
+            }
+            uint32_t vb[2][16];
+            const uint32_t tacc = tmem_base + (uint32_t)(g & 1) * 256u + ((uint32_t)(quad * 32) << 16) + (uint32_t)((sub >> 1) * 32 + (sub & 1) * 16);
+            tmem_ld16_nowait(tacc, vb[0]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < HB; ++q) {
+                const int jb = 2 * q + (sub >> 1), uh = sub & 1;
+                if (q + 1 < HB) tmem_ld16_nowait(tacc + (q + 1) * 64, vb[(q + 1) & 1]);
+                float hv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t* v = vb[q & 1];
+                    // see lstm_tc_kernel for the clamp / overflow argument
+                    const float gi = fmaxf(__uint_as_float(v[u]), -25.f), gf = fmaxf(__uint_as_float(v[4 + u]), -25.f);
+                    const float gg = fmaxf(__uint_as_float(v[8 + u]), -12.5f), go = __uint_as_float(v[12 + u]);
+                    const float ei = ex2_approx(-kLog2e * gi), ef = ex2_approx(-kLog2e * gf), eg = ex2_approx(-2.f * kLog2e * gg);
+                    const float pi = 1.f + ei, pf = 1.f + ef, pg = 1.f + eg;
+                    const float pig = pi * pg;
+                    const float num = fmaf(c[q * 4 + u], pig, (1.f - eg) * pf);
+                    const float cn = num * rcp_approx(pf * pig);
+                    c[q * 4 + u] = cn;
+                    const float ec = ex2_approx(-2.f * kLog2e * cn), eo = ex2_approx(-kLog2e * go);
+                    hv[u] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));
+                }
+                if (q + 1 < HB) tmem_wait_ld();
+                // 4 units -> 8 bytes of the hi and of the lo core-matrix row
+                const __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const uint2 hi = make_uint2(h2_bits(h01), h2_bits(h23));
+                const uint2 lo = make_uint2(h2_bits(__floats2half2_rn(hv[0] - f01.x, hv[1] - f01.y)), h2_bits(__floats2half2_rn(hv[2] - f23.x, hv[3] - f23.y)));
+                *reinterpret_cast<uint2*>(sAhi + (IN / 8 + jb) * LBO_A + row * 16 + uh * 8) = hi;
+                *reinterpret_cast<uint2*>(sAlo + (IN / 8 + jb) * LBO_A + row * 16 + uh * 8) = lo;
+                fence_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(barK + q);
+                if (live) {
+                    // layer-1 operand layout h0[tile][t][hi|lo][chunk][row][8]
+                    __half* o = h0_out + ((((size_t)tile * kT + t) * 2) * 16 + (dir * 8 + jb)) * (kRows * 8) + row * 8 + uh * 4;
+                    *reinterpret_cast<uint2*>(o) = hi;
+                    *reinterpret_cast<uint2*>(o + 16 * kRows * 8) = lo;
+                }
+            }
+            if (++step == kT) { step = 0; ++item; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<1>(tmem_base, 512);
+}
+
+int launch_l0_stream(const void* blob, const int32_t* xi, const float* xf, void* h0_out, int64_t m, cudaStream_t stream) {
+    using S = TcSmem<0, 1>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(lstm0_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total) != cudaSuccess)
+            return cuda_status("cudaFuncSetAttribute(lstm0_stream_kernel)");
+        attr_done = true;
+    }
+    const int n_tiles = (int)((m + kRows - 1) / kRows);
+    int grid = 2 * n_tiles; if (grid > kNumSMs) grid = kNumSMs & ~1;
+    lstm0_stream_kernel<<<grid, kS0Threads, S::total, stream>>>((const unsigned char*)blob, xi, xf, (__half*)h0_out, m, n_tiles);
+    return cuda_status("lstm0_stream_kernel");
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tail: probabilities from the t = 16 state (model.py:36-39,66-73 with output_proj folded into dense).
+//   d[128 sites x 256] = h16[128 x 128] . W'^T     24 tcgen05.mma (8 k-blocks x 3 hi/lo passes), fp32 in TMEM
+//   t = tanh(d + b'), logits = t . Wh + bh (24 = 21 genotype + 3 zygosity), two softmaxes.
+// One persistent CTA per SM, W' (2 x 64 KB) resident.  Warp roles:
+//   warps 0-7  epilogue: one site row x 128 dense outputs per thread; TMEM -> bias + tanh (1 ex2 + 1 rcp) -> 24 running
+//              dot products against Wh (shared-memory broadcasts); the two halves of a row meet in a small exchange
+//              buffer; softmax -> global.
+//   warps 8-11 loaders: the next tile's h16 rows -> fp16 hi/lo operand in shared memory
+//   warp  12   MMA issuer.
+// TMEM is double buffered (2 x 256 columns): the MMAs of tile g+1 run under the epilogue of tile g.
+constexpr int kTtEpiWarps = 8, kTtLoadWarps = 4;
+constexpr int kTtThreads = (kTtEpiWarps + kTtLoadWarps + 1) * 32;
+struct TailSmem {
+    static constexpr size_t w_bytes = kTcBytesTail;                 // one of hi / lo
+    static constexpr size_t a_bytes = (size_t)128 * kRows * 2;
+    static constexpr size_t off_whi = 0, off_wlo = w_bytes, off_ahi = 2 * w_bytes, off_alo = off_ahi + a_bytes,
+                            off_head = off_alo + a_bytes,            // float [256][24]
+                            off_bias = off_head + 256 * 24 * 4,      // float [256] dense bias, float [24] head bias
+                            off_xch = off_bias + (256 + 32) * 4,     // float [128][12] partial-logit exchange
+                            off_bar = off_xch + 128 * 12 * 4, total = off_bar + 64;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__global__ void __launch_bounds__(kTtThreads, 1)
+tail_tc_kernel(const unsigned char* __restrict__ blob, const float* __restrict__ h16, int64_t n_max, const int32_t* __restrict__ n_dev,
+               float* __restrict__ gt, float* __restrict__ zy)
+{
+    using S = TailSmem;
+    constexpr uint32_t LBO_A = kRows * 16, LBO_B = 256 * 16, SBO = 128;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sWhi = smem + S::off_whi; unsigned char* sWlo = smem + S::off_wlo;
+    unsigned char* sAhi = smem + S::off_ahi; unsigned char* sAlo = smem + S::off_alo;
+    float* sHead = reinterpret_cast<float*>(smem + S::off_head);
+    float* sBias = reinterpret_cast<float*>(smem + S::off_bias);
+    float* sXch = reinterpret_cast<float*>(smem + S::off_xch);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::off_bar);     // [0,1] barH, [2] barIn, [3,4] barFree
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_bar + 48);
+    uint64_t* barH = bar; uint64_t* barIn = bar + 2; uint64_t* barFree = bar + 3;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t n = n_max;
+    if (n_dev) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
+    const int n_tiles = (int)((n + kRows - 1) / kRows);
+    const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (tid == 0) {
+        mbar_init(barH, 1); mbar_init(barH + 1, 1); mbar_init(barIn, kTtLoadWarps);
+        mbar_init(barFree, kTtEpiWarps); mbar_init(barFree + 1, kTtEpiWarps);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<1>(tmem_slot, 512);
+    {
+        const uint4* ghi = reinterpret_cast<const uint4*>(blob + kOffTcTail);
+        const uint4* glo = reinterpret_cast<const uint4*>(blob + kOffTcTail + kTcBytesTail);
+        uint4* dhi = reinterpret_cast<uint4*>(sWhi); uint4* dlo = reinterpret_cast<uint4*>(sWlo);
+        for (int i = tid; i < (int)(S::w_bytes / 16); i += kTtThreads) { dhi[i] = __ldg(ghi + i); dlo[i] = __ldg(glo + i); }
+        const float* fb = reinterpret_cast<const float*>(blob);
+        for (int i = tid; i < 256 * 24; i += kTtThreads) sHead[i] = __ldg(fb + kOffHeadW + i);
+        for (int i = tid; i < 256; i += kTtThreads) sBias[i] = __ldg(fb + kOffDenseB + i);
+        if (tid < 24) sBias[256 + tid] = __ldg(fb + kOffHeadB + tid);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == kTtEpiWarps + kTtLoadWarps) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), b_hi = smem_u32(sWhi), b_lo = smem_u32(sWlo);
+            constexpr uint32_t idesc = make_idesc(128, 256);
+            for (int g = 0; g < my_tiles; ++g) {
+                const int b = g & 1;
+                mbar_wait(barIn, (uint32_t)(g & 1));                                     // operand of tile g staged
+                if (g >= 2) mbar_wait(barFree + b, (uint32_t)(((g >> 1) - 1) & 1));      // accumulator b drained by tile g-2
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)b * 256u;
+#pragma unroll 1
+                for (int kb = 0; kb < 8; ++kb) {
+                    const uint64_t bh = make_desc(b_hi + kb * 2 * LBO_B, LBO_B, SBO), bl = make_desc(b_lo + kb * 2 * LBO_B, LBO_B, SBO);
+                    const uint64_t ah = make_desc(a_hi + kb * 2 * LBO_A, LBO_A, SBO), al = make_desc(a_lo + kb * 2 * LBO_A, LBO_A, SBO);
+                    umma_f16<1>(acc, ah, bh, idesc, kb == 0 ? 0u : 1u);
+                    umma_f16<1>(acc, ah, bl, idesc, 1u);
+                    umma_f16<1>(acc, al, bh, idesc, 1u);
+                }
+                umma_commit<1>(barH + b);
+            }
+        }
+    } else if (warp >= kTtEpiWarps) {
+        // ---- loaders: thread = one site row; 16 chunks of 8 values = two float4 loads each.  The accumulators are double
+        //      buffered and the epilogue of a tile outlasts MMA + staging, so the loads need not be hoisted above the wait ----
+        const int row = (warp - kTtEpiWarps) * 32 + lane;
+        for (int g = 0; g < my_tiles; ++g) {
+            const int tile = (int)blockIdx.x + g * (int)gridDim.x;
+            int64_t site = (int64_t)tile * kRows + row; if (site >= n) site = n - 1;
+            const float4* src = reinterpret_cast<const float4*>(h16 + site * 128);
+            float4 pre[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pre[i] = __ldg(src + i);
+            if (g >= 1) mbar_wait(barH + ((g - 1) & 1), (uint32_t)(((g - 1) >> 1) & 1));    // the MMAs of the previous tile have read the operand
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (hf == 1) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pre[i] = __ldg(src + 16 + i);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float v[8] = {pre[2 * c].x, pre[2 * c].y, pre[2 * c].z, pre[2 * c].w, pre[2 * c + 1].x, pre[2 * c + 1].y, pre[2 * c + 1].z, pre[2 * c + 1].w};
+                    const HiLo8 sp = split8(v);
+                    reinterpret_cast<uint4*>(sAhi + (hf * 8 + c) * LBO_A)[row] = sp.hi;
+                    reinterpret_cast<uint4*>(sAlo + (hf * 8 + c) * LBO_A)[row] = sp.lo;
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(barIn);
+        }
+    } else {
+        // ---- epilogue: warp & 3 = TMEM lane quadrant, warp >> 2 = half of the 256 dense outputs; thread = site row ----
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;
+        for (int g = 0; g < my_tiles; ++g) {
+            const int b = g & 1;
+            const int tile = (int)blockIdx.x + g * (int)gridDim.x;
+            const int64_t site = (int64_t)tile * kRows + row;
+            mbar_wait(barH + b, (uint32_t)((g >> 1) & 1));
+            tc_fence_after();
+            float lg[24];
+#pragma unroll
+            for (int j = 0; j < 24; ++j) lg[j] = half == 0 ? sBias[256 + j] : 0.f;
+            uint32_t vb[2][16];
+            const uint32_t tacc = tmem_base + (uint32_t)b * 256u + ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 128u;
+            tmem_ld16_nowait(tacc, vb[0]);
+            tmem_wait_ld();
+#pragma unroll 2
+            for (int cb = 0; cb < 8; ++cb) {
+                if (cb + 1 < 8) tmem_ld16_nowait(tacc + (cb + 1) * 16, vb[(cb + 1) & 1]);
+                // tanh(d) = (1 - e) / (1 + e), e = exp(-2 d); d >= -20 keeps e finite (tanh(-20) = -1 to the last bit)
+                float t[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float d = fmaxf(__uint_as_float(vb[cb & 1][j]) + sBias[half * 128 + cb * 16 + j], -20.f);
+                    const float e = ex2_approx(-2.f * kLog2e * d);
+                    t[j] = (1.f - e) * rcp_approx(1.f + e);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4* wr = reinterpret_cast<const float4*>(sHead + (half * 128 + cb * 16 + j) * 24);
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        const float4 w = wr[q];
+                        lg[4 * q] = fmaf(t[j], w.x, lg[4 * q]); lg[4 * q + 1] = fmaf(t[j], w.y, lg[4 * q + 1]);
+                        lg[4 * q + 2] = fmaf(t[j], w.z, lg[4 * q + 2]); lg[4 * q + 3] = fmaf(t[j], w.w, lg[4 * q + 3]);
+                    }
+                }
+                if (cb + 1 < 8) tmem_wait_ld();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(barFree + b);
+            // the two halves of a quadrant add their partial logits through a 6 KB exchange buffer, 12 values per round
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float4* x = reinterpret_cast<float4*>(sXch + row * 12);
+                if (half == 1) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) x[q] = make_float4(lg[12 * r + 4 * q], lg[12 * r + 4 * q + 1], lg[12 * r + 4 * q + 2], lg[12 * r + 4 * q + 3]);
+                }
+                named_bar_sync(1 + quad, 64);
+                if (half == 0) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { const float4 v = x[q]; lg[12 * r + 4 * q] += v.x; lg[12 * r + 4 * q + 1] += v.y; lg[12 * r + 4 * q + 2] += v.z; lg[12 * r + 4 * q + 3] += v.w; }
+                }
+                named_bar_sync(1 + quad, 64);
+            }
+            if (half == 0 && site < n) {
+                float m = lg[0];
+#pragma unroll
+                for (int j = 1; j < 21; ++j) m = fmaxf(m, lg[j]);
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 21; ++j) { lg[j] = expf(lg[j] - m); sum += lg[j]; }
+#pragma unroll
+                for (int j = 0; j < 21; ++j) gt[site * 21 + j] = lg[j] / sum;
+                const float m2 = fmaxf(lg[21], fmaxf(lg[22], lg[23]));
+                const float e0 = expf(lg[21] - m2), e1 = expf(lg[22] - m2), e2 = expf(lg[23] - m2);
+                const float s2 = e0 + e1 + e2;
+                zy[site * 3 + 0] = e0 / s2; zy[site * 3 + 1] = e1 / s2; zy[site * 3 + 2] = e2 / s2;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<1>(tmem_base, 512);
+}
+
 template <int LAYER, int CG, int NWQ, bool DEBUG>
 int launch_one(const void* blob, const int32_t* xi, const float* xf, const void* h0_in, void* h0_out, float* h16, float* dbg,
                int64_t m, int dir_override, cudaStream_t stream)
@@ -475,12 +920,37 @@ int launch_one(const void* blob, const int32_t* xi, const float* xf, const void*
 
 }  // namespace
 
+int launch_tail_tc(const void* blob, const float* h16, int64_t n_max, const int32_t* n_dev, float* gt, float* zy, cudaStream_t stream) {
+    using S = TailSmem;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total) != cudaSuccess)
+            return cuda_status("cudaFuncSetAttribute(tail_tc_kernel)");
+        attr_done = true;
+    }
+    const int64_t n_tiles = (n_max + kRows - 1) / kRows;
+    const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+    tail_tc_kernel<<<grid, kTtThreads, S::total, stream>>>((const unsigned char*)blob, h16, n_max, n_dev, gt, zy);
+    return cuda_status("tail_tc_kernel");
+}
+
 int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, cudaStream_t stream) {
     // layer 0: CTA pairs share W (53 KB each) so two CTAs fit per SM and one CTA's MMAs overlap the other's epilogue
-    { ProfScope prof(NSNP_PROF_LSTM0, stream); if (int e = launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e; }
+    {
+        static const int variant = [] { const char* v = getenv("NSNP_L0_VARIANT"); return v ? atoi(v) : 0; }();
+        static const int xflags = [] { const char* v = getenv("NSNP_X_FLAGS"); return v ? atoi(v) : 0; }();
+        ProfScope prof(NSNP_PROF_LSTM0, stream);
+        int e;
+        if (variant == 1) e = launch_l0_stream(blob, xi, xf, h0, m, stream);
+        else if (variant == 2) e = launch_one<0, 2, 4, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream);
+        else e = launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, xflags << 8, stream);
+        if (e) return e;
+    }
     // layer 1: W only fits split across a CTA pair (2 x 104 KB); one CTA per SM, 16 warps for the epilogue
     ProfScope prof(NSNP_PROF_LSTM1, stream);
-    return launch_one<1, 2, 4, false>(blob, nullptr, nullptr, h0, nullptr, h16, nullptr, m, 0, stream);
+    static const int pf = [] { const char* v = getenv("NSNP_L1_PREFETCH"); return v ? atoi(v) : 1; }();
+    static const int xflags1 = [] { const char* v = getenv("NSNP_X_FLAGS"); return v ? atoi(v) : 0; }();
+    return launch_one<1, 2, 4, false>(blob, nullptr, nullptr, h0, nullptr, h16, nullptr, m, (pf | xflags1) << 8, stream);
 }
 
 int debug_tc_gates(const void* blob, const int32_t* xi, int layer, int dir, int cg, const void* h0, float* gates_out, int64_t m, cudaStream_t stream) {
@@ -514,6 +984,19 @@ int pack_tc_weights(const nsnp_model_weights_t* w, unsigned char* blob) {
                 }
             }
         }
+    }
+    // tail: folded dense weights (float [128 k][256 n], written by nsnp_model_pack_weights before this call)
+    {
+        const float* Wd = reinterpret_cast<const float*>(blob) + kOffDenseW;
+        __half* hi = reinterpret_cast<__half*>(blob + kOffTcTail);
+        __half* lo = reinterpret_cast<__half*>(blob + kOffTcTail + kTcBytesTail);
+        for (int n = 0; n < 256; ++n)
+            for (int k = 0; k < 128; ++k) {
+                const float v = Wd[(size_t)k * 256 + n];
+                const __half h = __float2half_rn(v);
+                const size_t idx = ((size_t)(k >> 3) * 256 + n) * 8 + (k & 7);
+                hi[idx] = h; lo[idx] = __float2half_rn(v - __half2float(h));
+            }
     }
     return NSNP_OK;
 }

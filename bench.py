@@ -114,15 +114,24 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Samples taken inside [t_begin, t_end] (the timed region); nvidia-smi needs a few hundred ms to start, so the
+        sampler is started before the warm-up and, if the timed region is shorter than one sampling period, the
+        samples of the load immediately before it (same kernels, same clocks) are used and the window says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        window = "timed region"
+        lines = [l for (t, l) in self.lines if t_begin is None or (t_begin <= t <= t_end + 0.12)]
+        if not lines and t_begin is not None:
+            lines = [l for (t, l) in self.lines if t <= t_end + 0.12][-5:]
+            window = "warm-up + timed region (timed region shorter than the sampling period)"
+        self.window = window
+        for l in lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
@@ -135,7 +144,7 @@ class ClockSampler:
                     reasons.add(nme)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def main_ours(args):
@@ -205,25 +214,26 @@ def main_ours(args):
         torch.cuda.synchronize()
 
     # ---- kernel-resident timing ----
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         n_sites = step_device()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     timer = StageTimer(True)
     lib = _lib.load()
     lib.nsnp_profile_enable(1)
     launches0 = runner.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         n_sites = step_device(timer)
     e1.record()
     barrier()
+    t_end = time.time()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    launches = runner.launches - launches0
+    clocks = sampler.stop(t_begin, t_end)
     stage_ms = timer.totals_ms()
     stage_calls = timer.counts()
     import ctypes as C
@@ -232,6 +242,8 @@ def main_ours(args):
     lib.nsnp_profile_enable(0)
     kernel_ms = {k: kms[i] for i, k in enumerate(_lib.PROF_SLOTS)}
     kernel_launches = {k: int(kln[i]) for i, k in enumerate(_lib.PROF_SLOTS)}
+    # kernels of this library launched inside the timed region, counted by the library itself (the select slot is three kernels)
+    launches = sum(kernel_launches.values()) + 2 * kernel_launches.get("select_kernels", 0)
 
     # ---- end to end through the host-buffer API ----
     e2e = None

@@ -111,7 +111,8 @@ class RegionRunner:
             timer.start("model")
             self.model(x, gt=gt, zy=zy)
             timer.stop()
-            self.launches += 1 + 3 * (-(-n // 75776))
+            chunks = -(-n // 75776)
+            self.launches += 1 + (2 * chunks + 1 if self.model.precision == _lib.PREC_F16X3 else 3 * chunks)   # gather + LSTM layers per chunk + tail
         if self.records:
             rec = self._buf("rec", (max(n, 1), 32), torch.uint8)[:n]
             if n:

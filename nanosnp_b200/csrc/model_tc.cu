@@ -191,7 +191,7 @@ template <int LAYER, int CG> struct TcSmem {
 // NWQ warps share each TMEM lane quadrant (each thread = one site row x 64/NWQ hidden units).
 // DEBUG: dump the raw accumulators of the first step and return.
 template <int LAYER, int CG, int NWQ, bool DEBUG>
-__global__ void __launch_bounds__(128 * NWQ + (LAYER == 1 ? 32 : 0), (LAYER == 0 && CG == 2) ? 2 : 1)
+__global__ void __launch_bounds__(128 * NWQ + (LAYER == 1 ? 32 : 0), (LAYER == 0 && CG == 2 && NWQ == 2) ? 2 : 1)
 lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict__ xi, const float* __restrict__ xf,
                const __half* __restrict__ h0_in, __half* __restrict__ h0_out, float* __restrict__ h16, float* __restrict__ dbg,
                int64_t n, int dir_override)
@@ -412,20 +412,24 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t* v = vb[hb & 1];
-                // only the lower clamps are needed: a very negative gate would give ex2 = +inf and inf * 0 below, a very
-                // positive one gives ex2 = 0, which is exact.  With the clamps every (1 + e) factor is <= 2^36 + 1, so the
-                // triple product stays below 2^108 and its reciprocal stays a normal float.  |c'| <= 33 after 33 steps, so
-                // ex2(-2 c' log2e) <= 2^96 needs no clamp; an overflowing (1 + eo) makes rcp return 0 = the exact limit.
-                const float gi = fmaxf(__uint_as_float(v[u]), -25.f), gf = fmaxf(__uint_as_float(v[4 + u]), -25.f);
-                const float gg = fmaxf(__uint_as_float(v[8 + u]), -12.5f), go = __uint_as_float(v[12 + u]);
-                const float ei = ex2_approx(-kLog2e * gi), ef = ex2_approx(-kLog2e * gf), eg = ex2_approx(-2.f * kLog2e * gg);
+                // The packed weights carry the activation scales (pack_tc_weights): the accumulators are
+                //     xi = -log2e i,  xf = -log2e f,  xg = -2 log2e g,  xo = -log2e o
+                // so every exponential is a bare ex2, and the cell state is kept as cs = -2 log2e c, which makes the
+                // argument of tanh(c')'s exponential the state itself.
+                // Only the upper clamps are needed: a huge argument would give ex2 = +inf and inf * 0 below, a very negative
+                // one gives ex2 = 0, which is exact.  With the clamps every (1 + e) factor is <= 2^36 + 1, so the triple
+                // product stays below 2^108 and its reciprocal stays a normal float.  |c'| <= 33 after 33 steps, so
+                // ex2(cs') <= 2^96 needs no clamp; an overflowing (1 + eo) makes rcp return 0 = the exact limit.
+                const float xi_ = fminf(__uint_as_float(v[u]), 36.f), xf_ = fminf(__uint_as_float(v[4 + u]), 36.f);
+                const float xg_ = fminf(__uint_as_float(v[8 + u]), 36.f), xo_ = __uint_as_float(v[12 + u]);
+                const float ei = ex2_approx(xi_), ef = ex2_approx(xf_), eg = ex2_approx(xg_), eo = ex2_approx(xo_);
                 const float pi = 1.f + ei, pf = 1.f + ef, pg = 1.f + eg;
-                // c' = sigmoid(f) c + sigmoid(i) tanh(g) over one common denominator
+                // cs' = sigmoid(f) cs + K sigmoid(i) tanh(g), K = -2 log2e, over one common denominator
                 const float pig = pi * pg;
-                const float num = fmaf(c[jl][uh * 4 + u], pig, (1.f - eg) * pf);
+                const float num = fmaf(c[jl][uh * 4 + u], pig, fmaf(eg, 2.f * kLog2e, -2.f * kLog2e) * pf);
                 const float cn = num * rcp_approx(pf * pig);
                 c[jl][uh * 4 + u] = cn;
-                const float ec = ex2_approx(-2.f * kLog2e * cn), eo = ex2_approx(-kLog2e * go);
+                const float ec = ex2_approx(cn);
                 hv[uh * 4 + u] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));        // sigmoid(o) tanh(c')
             }
             if (hb + 1 < 2 * UB) tmem_wait_ld();
@@ -456,237 +460,9 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
 }
 
 
-// ------------------------------------------------------------------------------------------------------------------
-// Layer 0, streaming variant: ONE persistent CTA per SM (cta_group::1, all of W resident: 96 KB), 16 epilogue warps
-// + 1 MMA-issuer warp, double-buffered TMEM accumulator (2 x 256 columns).
-//
-// The per-step barrier of lstm_tc_kernel serialises "all MMAs of step t+1" behind "the whole epilogue of step t".
-// Here the epilogue of step t hands its results to the issuer in K-SLICES: the 64 hidden units are produced in four
-// blocks of 16 (= one MMA k-block each), every warp works on its 4 units of block q and then arrives on mbarrier
-// barK[q]; the issuer warp waits for barK[q] and immediately issues the three hi/lo MMAs of that k-block for step t+1
-// into the OTHER accumulator.  The input part of step t+1 (x_{t+1}, staged at the start of the epilogue) is issued
-// first.  When the epilogue finishes, only the 3 MMAs of the last k-block are still outstanding -- instead of 18 --
-// so the tensor pipe works underneath the MUFU-bound cell update rather than after it.  Epilogue warps never block
-// on each other: the only waits are "my accumulator is complete" (barH) and the issuer's waits.
-// The site tiles of one direction are streamed through the same loop (weights and TMEM are set up once per CTA).
-constexpr int kS0EpiWarps = 16;
-constexpr int kS0Threads = kS0EpiWarps * 32 + 32;
-
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-
-__global__ void __launch_bounds__(kS0Threads, 1)
-lstm0_stream_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict__ xi, const float* __restrict__ xf,
-                    __half* __restrict__ h0_out, int64_t n, int n_tiles)
-{
-    using S = TcSmem<0, 1>;
-    constexpr int K = kTcK0, IN = kTcIn0;
-    constexpr int XB = IN / 16, HB = (K - IN) / 16;               // 2 input k-blocks, 4 hidden k-blocks
-    constexpr uint32_t LBO_A = kRows * 16, LBO_B = 256 * 16, SBO = 128;
-    extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sBhi = smem + S::off_bhi; unsigned char* sBlo = smem + S::off_blo;
-    unsigned char* sAhi = smem + S::off_ahi; unsigned char* sAlo = smem + S::off_alo; unsigned char* sAsc = smem + S::off_asc;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::off_bar);           // [0] barH, [1] barIn, [2..5] barK
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_bar + 48);
-    uint64_t* barH = bar; uint64_t* barIn = bar + 1; uint64_t* barK = bar + 2;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool issuer_warp = warp == kS0EpiWarps;
-    const int quad = warp & 3, sub = (warp >> 2) & 3;
-    const int row = quad * 32 + lane;
-    const int dir = (int)(blockIdx.x & 1);
-    const int tile0 = (int)(blockIdx.x >> 1), tile_stride = (int)(gridDim.x >> 1);
-    const int n_items = tile0 < n_tiles ? (n_tiles - tile0 + tile_stride - 1) / tile_stride : 0;
-    const int total_g = n_items * kT;
-
-    if (tid == 0) {
-        mbar_init(barH, 1); mbar_init(barIn, kS0EpiWarps);
-        for (int q = 0; q < HB; ++q) mbar_init(barK + q, kS0EpiWarps);
-        fence_mbar_init();
-    }
-    if (warp == 0) tmem_alloc<1>(tmem_slot, 512);
-    {
-        const uint4* ghi = reinterpret_cast<const uint4*>(blob + tc_off(0, dir, 0));
-        const uint4* glo = reinterpret_cast<const uint4*>(blob + tc_off(0, dir, 1));
-        uint4* dhi = reinterpret_cast<uint4*>(sBhi); uint4* dlo = reinterpret_cast<uint4*>(sBlo);
-        for (int i = tid; i < (K / 8) * 256; i += kS0Threads) { dhi[i] = __ldg(ghi + i); dlo[i] = __ldg(glo + i); }
-        uint4* a = reinterpret_cast<uint4*>(sAhi);
-        const int n16 = (int)((2 * S::a_bytes + S::sc_bytes) / 16);
-        for (int i = tid; i < n16; i += kS0Threads) a[i] = make_uint4(0, 0, 0, 0);
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (issuer_warp) {
-        if (lane == 0) {
-            const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), a_sc = smem_u32(sAsc), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
-            constexpr uint32_t idesc = make_idesc(128, 256);
-            auto issue_kb = [&](int kb, uint32_t tmem_d, uint32_t first_acc) {
-                // a_hi.w_hi, a_hi.w_lo (counts: scaled copy), a_lo.w_hi
-                const uint64_t bh = make_desc(b_hi + kb * 2 * LBO_B, LBO_B, SBO), bl = make_desc(b_lo + kb * 2 * LBO_B, LBO_B, SBO);
-                const uint32_t a1 = kb < XB ? a_sc : a_hi;
-                umma_f16<1>(tmem_d, make_desc(a_hi + kb * 2 * LBO_A, LBO_A, SBO), bh, idesc, first_acc);
-                umma_f16<1>(tmem_d, make_desc(a1 + kb * 2 * LBO_A, LBO_A, SBO), bl, idesc, 1);
-                umma_f16<1>(tmem_d, make_desc(a_lo + kb * 2 * LBO_A, LBO_A, SBO), bh, idesc, 1);
-            };
-            int step = 0;
-            for (int g = 0; g < total_g; ++g) {
-                const uint32_t acc = tmem_base + (uint32_t)(g & 1) * 256u;
-                mbar_wait(barIn, (uint32_t)(g & 1));                       // x of this step staged; accumulator drained two steps ago
-                tc_fence_after();
-#pragma unroll
-                for (int kb = 0; kb < XB; ++kb) issue_kb(kb, acc, kb == 0 ? 0u : 1u);
-#pragma unroll 1
-                for (int q = 0; q < HB; ++q) {
-                    if (g > 0) { mbar_wait(barK + q, (uint32_t)((g - 1) & 1)); tc_fence_after(); }
-                    if (step > 0) issue_kb(XB + q, acc, 1u);               // step 0 of a tile: h = 0
-                }
-                umma_commit<1>(barH);
-                if (++step == kT) step = 0;
-            }
-        }
-    } else {
-        // ---- epilogue warps ----
-        int2 xraw[4];
-        auto x_ptr = [&](int g) -> const int2* {
-            const int item = g / kT, st = g - item * kT;
-            const int t = dir == 0 ? st : (kT - 1 - st);
-            int64_t site = (int64_t)(tile0 + item * tile_stride) * kRows + row;
-            if (site >= n) site = n - 1;
-            return reinterpret_cast<const int2*>(xi ? (const void*)(xi + (site * kT + t) * kF) : (const void*)(xf + (site * kT + t) * kF));
-        };
-        // sub 0: x[0..7] (chunk 0), sub 1: x[8..15] (chunk 1), sub 3: x16, x17 + the bias column (chunk 2)
-        auto load_x = [&](int g) {
-            const int2* gp = x_ptr(g);
-            if (sub == 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xraw[j] = ldg_nc_volatile(gp + j);
-            } else if (sub == 1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xraw[j] = ldg_nc_volatile(gp + 4 + j);
-            } else if (sub == 3) {
-                xraw[0] = ldg_nc_volatile(gp + 8);
-            }
-        };
-        auto xval = [&](int j) -> float {
-            const int2 p = xraw[j >> 1];
-            const int b = (j & 1) ? p.y : p.x;
-            return xi ? (float)b : __int_as_float(b);
-        };
-        auto store_x = [&]() {
-            if (sub == 0 || sub == 1) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = xval(j);
-                const HiLo8 s = split8(v);
-                reinterpret_cast<uint4*>(sAhi + sub * LBO_A)[row] = s.hi;
-                reinterpret_cast<uint4*>(sAlo + sub * LBO_A)[row] = s.lo;
-                reinterpret_cast<uint4*>(sAsc + sub * LBO_A)[row] = scale_hi(s.hi);
-            } else if (sub == 3) {
-                const float v[8] = {xval(0), xval(1), 1.0f, 0.f, 0.f, 0.f, 0.f, 0.f};  // x16, x17, bias column
-                const HiLo8 s = split8(v);
-                reinterpret_cast<uint4*>(sAhi + 2 * LBO_A)[row] = s.hi;
-                reinterpret_cast<uint4*>(sAlo + 2 * LBO_A)[row] = s.lo;
-                reinterpret_cast<uint4*>(sAsc + 2 * LBO_A)[row] = scale_hi(s.hi);
-            }
-        };
-        float c[16];
-        if (total_g > 0) {
-            load_x(0); store_x();
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(barIn);
-            if (total_g > 1) load_x(1);
-        }
-        int step = 0, item = 0;
-        for (int g = 0; g < total_g; ++g) {
-            const int t = dir == 0 ? step : (kT - 1 - step);
-            const int tile = tile0 + item * tile_stride;
-            const bool live = (int64_t)tile * kRows + row < n;
-            if (step == 0) {
-#pragma unroll
-                for (int u = 0; u < 16; ++u) c[u] = 0.f;
-            }
-            mbar_wait(barH, (uint32_t)(g & 1));
-            tc_fence_after();
-            // the MMAs of this step have retired: the input operand takes x of the next step right away
-            if (g + 1 < total_g) {
-                store_x();
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(barIn);
-                if (g + 2 < total_g) load_x(g + 2);
-            }
-            uint32_t vb[2][16];
-            const uint32_t tacc = tmem_base + (uint32_t)(g & 1) * 256u + ((uint32_t)(quad * 32) << 16) + (uint32_t)((sub >> 1) * 32 + (sub & 1) * 16);
-            tmem_ld16_nowait(tacc, vb[0]);
-            tmem_wait_ld();
-#pragma unroll
-            for (int q = 0; q < HB; ++q) {
-                const int jb = 2 * q + (sub >> 1), uh = sub & 1;
-                if (q + 1 < HB) tmem_ld16_nowait(tacc + (q + 1) * 64, vb[(q + 1) & 1]);
-                float hv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t* v = vb[q & 1];
-                    // see lstm_tc_kernel for the clamp / overflow argument
-                    const float gi = fmaxf(__uint_as_float(v[u]), -25.f), gf = fmaxf(__uint_as_float(v[4 + u]), -25.f);
-                    const float gg = fmaxf(__uint_as_float(v[8 + u]), -12.5f), go = __uint_as_float(v[12 + u]);
-                    const float ei = ex2_approx(-kLog2e * gi), ef = ex2_approx(-kLog2e * gf), eg = ex2_approx(-2.f * kLog2e * gg);
-                    const float pi = 1.f + ei, pf = 1.f + ef, pg = 1.f + eg;
-                    const float pig = pi * pg;
-                    const float num = fmaf(c[q * 4 + u], pig, (1.f - eg) * pf);
-                    const float cn = num * rcp_approx(pf * pig);
-                    c[q * 4 + u] = cn;
-                    const float ec = ex2_approx(-2.f * kLog2e * cn), eo = ex2_approx(-kLog2e * go);
-                    hv[u] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));
-                }
-                if (q + 1 < HB) tmem_wait_ld();
-                // 4 units -> 8 bytes of the hi and of the lo core-matrix row
-                const __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                const uint2 hi = make_uint2(h2_bits(h01), h2_bits(h23));
-                const uint2 lo = make_uint2(h2_bits(__floats2half2_rn(hv[0] - f01.x, hv[1] - f01.y)), h2_bits(__floats2half2_rn(hv[2] - f23.x, hv[3] - f23.y)));
-                *reinterpret_cast<uint2*>(sAhi + (IN / 8 + jb) * LBO_A + row * 16 + uh * 8) = hi;
-                *reinterpret_cast<uint2*>(sAlo + (IN / 8 + jb) * LBO_A + row * 16 + uh * 8) = lo;
-                fence_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(barK + q);
-                if (live) {
-                    // layer-1 operand layout h0[tile][t][hi|lo][chunk][row][8]
-                    __half* o = h0_out + ((((size_t)tile * kT + t) * 2) * 16 + (dir * 8 + jb)) * (kRows * 8) + row * 8 + uh * 4;
-                    *reinterpret_cast<uint2*>(o) = hi;
-                    *reinterpret_cast<uint2*>(o + 16 * kRows * 8) = lo;
-                }
-            }
-            if (++step == kT) { step = 0; ++item; }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<1>(tmem_base, 512);
-}
-
-int launch_l0_stream(const void* blob, const int32_t* xi, const float* xf, void* h0_out, int64_t m, cudaStream_t stream) {
-    using S = TcSmem<0, 1>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (cudaFuncSetAttribute(lstm0_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total) != cudaSuccess)
-            return cuda_status("cudaFuncSetAttribute(lstm0_stream_kernel)");
-        attr_done = true;
-    }
-    const int n_tiles = (int)((m + kRows - 1) / kRows);
-    int grid = 2 * n_tiles; if (grid > kNumSMs) grid = kNumSMs & ~1;
-    lstm0_stream_kernel<<<grid, kS0Threads, S::total, stream>>>((const unsigned char*)blob, xi, xf, (__half*)h0_out, m, n_tiles);
-    return cuda_status("lstm0_stream_kernel");
-}
-
 
 // ------------------------------------------------------------------------------------------------------------------
 // Tail: probabilities from the t = 16 state (model.py:36-39,66-73 with output_proj folded into dense).
@@ -935,13 +711,8 @@ int launch_tail_tc(const void* blob, const float* h16, int64_t n_max, const int3
 int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, cudaStream_t stream) {
     // layer 0: CTA pairs share W (53 KB each) so two CTAs fit per SM and one CTA's MMAs overlap the other's epilogue
     {
-        static const int variant = [] { const char* v = getenv("NSNP_L0_VARIANT"); return v ? atoi(v) : 0; }();
         ProfScope prof(NSNP_PROF_LSTM0, stream);
-        int e;
-        if (variant == 1) e = launch_l0_stream(blob, xi, xf, h0, m, stream);
-        else if (variant == 2) e = launch_one<0, 2, 4, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream);
-        else e = launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream);
-        if (e) return e;
+        if (int e = launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e;
     }
     // layer 1: W only fits split across a CTA pair (2 x 104 KB); one CTA per SM, 16 warps for the epilogue
     ProfScope prof(NSNP_PROF_LSTM1, stream);
@@ -972,6 +743,7 @@ int pack_tc_weights(const nsnp_model_weights_t* w, unsigned char* blob) {
                     if (k < nin) v = wih[rowi * nin + k];
                     else if (k == nin) v = bi[rowi] + bh[rowi];
                     else if (k >= IN) v = whh[rowi * kH + (k - IN)];
+                    v *= gate == 2 ? -2.0f * kLog2e : -kLog2e;         // activation scale folded into the weights (see the epilogue)
                     const float scale = (layer == 0 && k < IN) ? kTcLoScale : 1.0f;
                     const __half h = __float2half_rn(v);
                     const __half l = __float2half_rn((v - __half2float(h)) * scale);

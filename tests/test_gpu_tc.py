@@ -30,6 +30,12 @@ def _col_order():
     return ((n >> 2) & 3) * 64 + (n >> 5) * 8 + ((n >> 4) & 1) * 4 + (n & 3)
 
 
+def _col_scale():
+    """Activation scale folded into the packed weights (model_tc.cu): -log2(e) for i, f, o and -2 log2(e) for g."""
+    n = np.arange(256)
+    return np.where(((n >> 2) & 3) == 2, -2.0, -1.0) * np.log2(np.e)
+
+
 @pytest.mark.parametrize("layer,cg", [(0, 1), (0, 2), (1, 2)])
 def test_umma_operand_layout_first_step_gates(weights, golden_weights, small_case, layer, cg):
     """Raw TMEM accumulators of step 0 == W_ih . in + b (h = 0): validates descriptors, operand layout, hi/lo split."""
@@ -55,8 +61,8 @@ def test_umma_operand_layout_first_step_gates(weights, golden_weights, small_cas
         torch.cuda.synchronize()
         w = enc[f"lstm.weight_ih_l{layer}{sfx}"].astype(np.float64)
         b = (enc[f"lstm.bias_ih_l{layer}{sfx}"] + enc[f"lstm.bias_hh_l{layer}{sfx}"]).astype(np.float64)
-        ref = (xin[:, 0 if d == 0 else 32, :].astype(np.float64) @ w.T + b)[:, _col_order()]
-        assert np.abs(out.cpu().numpy() - ref).max() < 3e-5
+        ref = (xin[:, 0 if d == 0 else 32, :].astype(np.float64) @ w.T + b)[:, _col_order()] * _col_scale()
+        assert np.abs(out.cpu().numpy() - ref).max() < 1e-4          # accumulators carry the folded activation scale (up to 2.89x)
 
 
 def test_tensor_core_forward_matches_oracle(weights, golden, small_case):

@@ -36,7 +36,9 @@ def col_order():
 def gates_ref(layer, d, inp):
     sfx = "_reverse" if d else ""
     wih = enc[f"lstm.weight_ih_l{layer}{sfx}"].astype(np.float64); b = (enc[f"lstm.bias_ih_l{layer}{sfx}"] + enc[f"lstm.bias_hh_l{layer}{sfx}"]).astype(np.float64)
-    return (inp.astype(np.float64) @ wih.T + b)[:, col_order()]
+    n = np.arange(256)
+    scale = np.where(((n >> 2) & 3) == 2, -2.0, -1.0) * np.log2(np.e)      # activation scale folded into the packed weights
+    return (inp.astype(np.float64) @ wih.T + b)[:, col_order()] * scale
 
 
 def run_gates(layer, d, cg, xin, h0=None, m=300):

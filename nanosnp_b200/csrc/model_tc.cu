@@ -334,6 +334,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
 #pragma unroll 1
             for (int kb = kb0; kb < kb1; ++kb) {
                 // pass 0: a_hi.w_hi   pass 1: a_hi.w_lo (layer-0 counts: scaled copy)   pass 2: a_lo.w_hi
+                if (LAYER == 1 && pass == 2 && kb == kIn1 / 16) continue;     // the bias k-block: its A operand is the constant 1.0, lo half exactly zero
                 uint32_t aa = pass == 2 ? a_lo : a_hi;
                 if (LAYER == 0 && pass == 1 && kb < kTcIn0 / 16) aa = a_sc;
                 const uint32_t bb = pass == 1 ? b_lo : b_hi;

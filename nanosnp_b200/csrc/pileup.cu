@@ -199,7 +199,13 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
         cg_next = (32 + lane < left) ? __ldg(cgp + 32 + lane) : 6u;
         const int op = cg & 15, len = cg >> 4;                          // 6 = pad: consumes nothing
         const int rl = op_ref(op) ? len : 0, ql = op_query(op) ? len : 0;
-        const int ri = warp_incl_scan(rl), qi = warp_incl_scan(ql);
+        int ri, qi;
+        if (!__any_sync(0xffffffffu, len >= 2048)) {                    // both prefix sums fit 16 bits: one packed scan
+            const int pk = warp_incl_scan(rl | (ql << 16));
+            ri = pk & 0xFFFF; qi = (int)((uint32_t)pk >> 16);
+        } else {
+            ri = warp_incl_scan(rl); qi = warp_incl_scan(ql);
+        }
         const int rs = R + ri - rl;                                     // reference start of this lane's op
         const int qs = Q + qi - ql;                                     // query start (relative to the read)
         R += __shfl_sync(0xffffffffu, ri, 31);
@@ -208,10 +214,6 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
         // ---- phase 1: one lane per CIGAR op, straight-line predicated bookkeeping ----
         const bool aligned = op_aligned(op), isdel = op == 2;
         const int a = max(rs, ts), b = min(rs + len, te);                               // clipped reference span
-        if (isdel && a < b) {                                                           // '*' / '#' run boundaries
-            atomicAdd(&sm.ds[a - ts], sinc);
-            if (b < te) atomicSub(&sm.ds[b - ts], sinc);
-        }
         // indel event anchored at the preceding reference position (appendix A.8 iii/iv); leading ops are never reported.
         // Totals per class go to byte counters.  The multiplicity of the most frequent IDENTICAL indel (I1/D1) needs
         // grouping by (length, sequence): the common groups -- deletions of 1 or 2 bases, 1-base insertions of A/C/G/T --
@@ -221,13 +223,21 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
         const bool ev = (isins || isdel) && len <= NSNP_MAX_INDEL && rs > rpos && anchor >= ts && anchor < te;
         const int64_t gq = sbase + qs;                                   // absolute base index of an inserted sequence
         const bool ins1 = ev && isins && len == 1 && !deep;
+        // '*' / '#' depth: a counted 1- or 2-base deletion anchored inside the tile is covered by its fast counter (the
+        // epilogue adds D1[p-1] + D2[p-1] + D2[p-2]); every other deletion -- longer, leading, anchored in the previous
+        // tile, or any in a deep tile -- marks its clipped span with two boundary deltas
+        const bool fastdel = ev && isdel && len <= 2 && !deep;
+        if (isdel && a < b && !fastdel) {
+            atomicAdd(&sm.ds[a - ts], sinc);
+            if (b < te) atomicSub(&sm.ds[b - ts], sinc);
+        }
         uint32_t iword = 0, inbit = 0;
         if (ins1) { iword = __ldg(seqw + (gq >> 4)); if (nmw) inbit = (__ldg(nmw + (gq >> 5)) >> (gq & 31)) & 1u; }   // consumed after phase 2
         if (ev) {
             const int cls = (isdel ? 2 : 0) + strand;
             const int ap = anchor - ts;
             atomicAdd(&sm.cnt4[ap], 1u << (8 * cls));
-            if (isdel && len <= 2 && !deep) {
+            if (fastdel) {
                 atomicAdd(&sm.dfast[ap], 1u << (8 * (2 * strand + len - 1)));
             } else if (!ins1) {
                 const int e = atomicAdd(&sm.n_events, 1);
@@ -458,8 +468,12 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
                 const uint32_t a = sm.ms[p], c = sm.ds[p];
                 e0 += (int)(a & 0xFFFF) - kB; e1 += (int)(a >> 16) - kB;
                 e2 += (int)(c & 0xFFFF) - kB; e3 += (int)(c >> 16) - kB;
-                sm.ms[p] = (uint32_t)(e0 - e2) | ((uint32_t)(e1 - e3) << 16);        // aligned depth = span - deletions
-                sm.ds[p] = (uint32_t)e2 | ((uint32_t)e3 << 16);
+                // deletions covered by the fast counters: 1-base anchored at p-1, 2-base anchored at p-1 or p-2
+                const uint32_t f1 = p >= 1 ? sm.dfast[p - 1] : 0u, f2 = p >= 2 ? sm.dfast[p - 2] : 0u;
+                const int d2 = e2 + (int)(f1 & 0xFF) + (int)((f1 >> 8) & 0xFF) + (int)((f2 >> 8) & 0xFF);
+                const int d3 = e3 + (int)((f1 >> 16) & 0xFF) + (int)(f1 >> 24) + (int)(f2 >> 24);
+                sm.ms[p] = (uint32_t)(e0 - d2) | ((uint32_t)(e1 - d3) << 16);        // aligned depth = span - deletions
+                sm.ds[p] = (uint32_t)d2 | ((uint32_t)d3 << 16);
             }
         }
         __syncthreads();

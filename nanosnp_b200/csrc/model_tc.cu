@@ -292,15 +292,18 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     uint64_t* barS = bar + 2;                                        // "input part of A for the next step has landed"
     constexpr uint32_t kPartBytes = 16u * kRows * 16u;               // 32 KB
     const bool l2_prefetch = (dir_override >> 8) & 1;
+    // the padding CTA of an odd tile count (clusters come in pairs) re-reads the last real tile: it must not touch memory
+    // past the layer-0 output (found by compute-sanitizer memcheck)
+    const size_t src_tile = min((size_t)blockIdx.x, (size_t)((n + kRows - 1) / kRows - 1));
     auto stage_h0_bulk = [&](int t) {                                // one thread
-        const __half* src = h0_in + ((size_t)blockIdx.x * kT + t) * (2 * kPartBytes / 2);
+        const __half* src = h0_in + (src_tile * kT + t) * (2 * kPartBytes / 2);
         mbar_expect_tx(barS, 2 * kPartBytes);
         bulk_g2s(sAhi, src, kPartBytes, barS);
         bulk_g2s(sAlo, src + kPartBytes / 2, kPartBytes, barS);
         // the rows of the step after this one: pull them into L2 now, so that their bulk copy (issued when the operand
         // buffer is free again, one step from now) pays L2 latency instead of DRAM latency
         const int tp = dir == 0 ? t + 1 : t - 1;
-        if (l2_prefetch && tp >= 0 && tp < kT) bulk_prefetch_l2(h0_in + ((size_t)blockIdx.x * kT + tp) * (2 * kPartBytes / 2), 2 * kPartBytes);
+        if (l2_prefetch && tp >= 0 && tp < kT) bulk_prefetch_l2(h0_in + (src_tile * kT + tp) * (2 * kPartBytes / 2), 2 * kPartBytes);
     };
     constexpr int XB = IN / 16;                                  // k-blocks of the input part; the rest is the h part
     constexpr uint32_t kTmemCols = LAYER == 1 ? 512 : 256;       // layer 1 double-buffers the accumulator

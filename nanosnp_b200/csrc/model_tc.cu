@@ -47,6 +47,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// cluster-scope flavours for the hand-off between the two CTAs of a pair
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_C;\n\t"
+        "bra WAIT_LOOP_C;\n\t"
+        "DONE_C:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t target_cta) {     // same barrier offset in CTA target_cta
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(target_cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// Relaxed remote arrive: execution ordering only.  The operand rows were already made visible to the async proxy by
+// fence.proxy.async and the TMEM reads retired (tcgen05.fence); a .release at cluster scope would additionally drain this
+// thread's outstanding GLOBAL stores (the layer-0 output rows) on every step.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t target_cta) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(target_cta));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -222,7 +246,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     if (!live) site = n - 1;                                     // clamp loads, skip stores
 
     // ---- one-time setup ----
-    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); mbar_init(bar + 3, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc<CG>(tmem_slot, LAYER == 1 ? 512 : 256);
     {   // this CTA's weight rows: global [K/8][256][8] halfs -> shared [K/8][RB][8]
         const uint4* ghi = reinterpret_cast<const uint4*>(blob + tc_off(LAYER, dir, 0));
@@ -290,6 +314,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     // layer 1: the layer-0 output of one (tile, t) is stored exactly in operand layout, hi part then lo part, 32 KB each:
     //     h0[tile][t][hi|lo][chunk 16][row 128][8 halfs]
     uint64_t* barS = bar + 2;                                        // "input part of A for the next step has landed"
+    uint64_t* barS2 = bar + 3;                                       // leader CTA only: "... and so has the peer CTA's"
     constexpr uint32_t kPartBytes = 16u * kRows * 16u;               // 32 KB
     const bool l2_prefetch = (dir_override >> 8) & 1;
     // the padding CTA of an odd tile count (clusters come in pairs) re-reads the last real tile: it must not touch memory
@@ -318,7 +343,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();         // barriers initialised, operands zeroed, TMEM allocated
     tc_fence_after();
-    uint32_t phaseH = 0, phaseX = 0, phaseS = 0;
+    uint32_t phaseH = 0, phaseX = 0, phaseS = 0, phaseS2 = 0;
     if (LAYER == 1) {
         if (producer && lane == 0) stage_h0_bulk(dir == 0 ? 0 : kT - 1);
         mbar_wait(barS, phaseS); phaseS ^= 1;
@@ -329,7 +354,11 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), a_sc = smem_u32(sAsc), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
     constexpr uint32_t idesc = make_idesc(128 * CG, 256);
-    const bool issuer = cta_rank == 0 && tid == 0;
+    // Layer 1: the MMAs are issued from the producer warp.  tcgen05.mma issue blocks while the tensor pipe's queue is full,
+    // so 39 back-to-back MMAs hold the issuing thread for most of a step; an epilogue warp that issues them starts its
+    // own cell updates ~4000 cycles late and the whole CTA pair waits for it at the next hand-off (clock64 trace:
+    // 7400 -> 6100 cycles per step).  Layer 0 waits for all of its MMAs anyway, so thread 0 issues them.
+    const bool issuer = cta_rank == 0 && (LAYER == 1 ? (producer && lane == 0) : tid == 0);
     // k-blocks [kb0, kb1) x three hi/lo passes into the accumulator at tmem_d
     auto issue = [&](int kb0, int kb1, uint32_t tmem_d, uint32_t acc) {
 #pragma unroll 1
@@ -351,8 +380,9 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
         // while the epilogue of step t runs on the SM; only the 12 h-part MMAs stay on the per-step critical path
         if (issuer) { tc_fence_after(); issue(0, XB, tmem_base, 0); umma_commit<CG>(barX); }
         if (producer) {
-            mbar_wait(barX, phaseX); phaseX ^= 1;
-            if (lane == 0 && C::STEPS > 1 && !DEBUG) stage_h0_bulk(dir == 0 ? 1 : kT - 2);
+            if (lane == 0) { mbar_wait(barX, phaseX); if (C::STEPS > 1 && !DEBUG) stage_h0_bulk(dir == 0 ? 1 : kT - 2); }
+            phaseX ^= 1;
+            __syncwarp();
         }
     }
 
@@ -362,28 +392,42 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
         const bool more = !DEBUG && step + 1 < C::STEPS;
         const uint32_t acc_cols = LAYER == 1 ? (uint32_t)(step & 1) * 256u : 0u;
         // ---- operands written by the generic proxy -> visible to the tensor core; TMEM reads of the last step retired ----
-        if (LAYER == 1 && more) { mbar_wait(barS, phaseS); phaseS ^= 1; }      // the input rows of step t+1 have landed (their MMAs are issued below)
         fence_async_smem();
         tc_fence_before();
         if (CG == 2) cluster_sync_exec(); else __syncthreads();
-        if (issuer) {
+        if (LAYER == 0 && issuer) {
             tc_fence_after();
-            if (LAYER == 1) {
-                issue(XB, KB, tmem_base + acc_cols, 1);                       // += W_hh . h_{t-1}
-                umma_commit<CG>(barH);
-                if (more) { issue(0, XB, tmem_base + (acc_cols ^ 256u), 0); umma_commit<CG>(barX); }
-            } else {
-                issue(0, KB, tmem_base, 0);
-                umma_commit<CG>(barH);
-            }
+            issue(0, KB, tmem_base, 0);
+            umma_commit<CG>(barH);
         }
         if (producer) {
-            // producer warp: once the input-part MMAs of step t+1 have completed, their operand region takes the rows of
-            // step t+2 (two 32 KB bulk copies); it never touches TMEM and skips the epilogue
-            if (more) {
-                mbar_wait(barX, phaseX); phaseX ^= 1;
-                if (lane == 0 && step + 2 < C::STEPS) stage_h0_bulk(dir == 0 ? step + 2 : kT - 3 - step);
+            // Layer 1, producer warp (one lane): issues the MMAs (leader CTA), tracks the bulk copies and refills the input
+            // operand.  It never touches TMEM and skips the epilogue.  Nobody else waits for the copies: the h-part MMAs
+            // of this step go out at once, the input part of step t+1 follows when BOTH CTAs' rows have landed (the peer
+            // reports through barS2), and the rows of step t+2 are requested as soon as those MMAs have retired.
+            if (lane == 0) {
+                if (cta_rank == 0) {
+                    tc_fence_after();
+                    issue(XB, KB, tmem_base + acc_cols, 1);                       // += W_hh . h_{t-1}
+                    umma_commit<CG>(barH);
+                    if (more) {
+                        mbar_wait(barS, phaseS);
+                        if (CG == 2) mbar_wait_cluster(barS2, phaseS2);
+                        tc_fence_after();
+                        issue(0, XB, tmem_base + (acc_cols ^ 256u), 0);
+                        umma_commit<CG>(barX);
+                    }
+                } else if (more) {
+                    mbar_wait(barS, phaseS);
+                    mbar_arrive_remote(barS2, 0);
+                }
+                if (more) {
+                    mbar_wait(barX, phaseX);
+                    if (step + 2 < C::STEPS) stage_h0_bulk(dir == 0 ? step + 2 : kT - 3 - step);
+                }
             }
+            if (more) { phaseS ^= 1; phaseS2 ^= 1; phaseX ^= 1; }
+            __syncwarp();
             if (DEBUG) break;
             continue;
         }
@@ -466,6 +510,231 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Layer 0, "two groups per CTA" variant.  A clock64 trace of lstm_tc_kernel<0,2,2> (two independent CTAs per SM) shows a
+// step period of 8100 cycles while the two co-resident CTAs alternate (one waits for its MMAs while the other runs its
+// cell updates) and 10400 once later waves have drifted into phase: then both wait for the tensor pipe together and both
+// fight for the MUFU pipe together.  Here the alternation is built in: one CTA per SM holds TWO 128-site groups
+// (16 warps, 2 x 256 TMEM columns, one copy of this CTA's half of W), still paired with a second CTA through
+// cta_group::2.  There is no cluster barrier: every warp reports "my part of the epilogue is done" on an mbarrier of the
+// leader CTA (remote arrive from the peer), the leader's thread 0 of the group issues the 18 MMAs and tcgen05.commit
+// multicasts completion to both CTAs.  A second pair of mbarriers passes a token between the two groups so that their
+// MMA bursts strictly alternate.
+constexpr int kP2GroupThreads = 256, kP2Threads = 2 * kP2GroupThreads;
+struct P2Smem {
+    static constexpr size_t b_bytes = (size_t)kTcK0 * 128 * 2;                  // this CTA's half of W, one of hi / lo
+    static constexpr size_t a_bytes = (size_t)kTcK0 * kRows * 2;
+    static constexpr size_t sc_bytes = (size_t)kTcIn0 * kRows * 2;
+    static constexpr size_t a_stride = 2 * a_bytes + sc_bytes;
+    static constexpr size_t off_bhi = 0, off_blo = b_bytes, off_a = 2 * b_bytes, off_bar = off_a + 2 * a_stride, total = off_bar + 128;
+};
+
+__global__ void __launch_bounds__(kP2Threads, 1)
+lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict__ xi, const float* __restrict__ xf,
+                   __half* __restrict__ h0_out, int64_t n)
+{
+    using S = P2Smem;
+    constexpr int K = kTcK0, IN = kTcIn0, KB = K / 16, RB = 128, UB = 4;
+    constexpr uint32_t LBO_A = kRows * 16, LBO_B = RB * 16, SBO = 128;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int grp = (int)threadIdx.x / kP2GroupThreads;
+    const int tid = (int)threadIdx.x - grp * kP2GroupThreads, lane = tid & 31, warp = tid >> 5;
+    unsigned char* sBhi = smem + S::off_bhi; unsigned char* sBlo = smem + S::off_blo;
+    unsigned char* sAhi = smem + S::off_a + grp * S::a_stride; unsigned char* sAlo = sAhi + S::a_bytes; unsigned char* sAsc = sAlo + S::a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_bar);
+    uint64_t* barH = bars + grp;               // [0,1]  gates of this group complete (commit, multicast to both CTAs)
+    uint64_t* barReady = bars + 2 + grp;       // [2,3]  leader CTA: all 16 warps of this group (both CTAs) finished their epilogue
+    uint64_t* barTurn = bars + 4;              // [4,5]  leader CTA: token, barTurn[g] = "group g may issue"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_bar + 64);
+
+    const int quad = warp & 3, sub = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int dir = (int)blockIdx.y;
+    const uint32_t cta_rank = cluster_ctarank();
+    const int64_t tile_idx = (int64_t)blockIdx.x * 2 + grp;
+    int64_t site = tile_idx * kRows + row;
+    const bool live = site < n;
+    if (!live) site = n - 1;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bars + 0, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 16); mbar_init(bars + 3, 16);
+        mbar_init(bars + 4, 1); mbar_init(bars + 5, 1);
+        fence_mbar_init();
+    }
+    if (threadIdx.x < 32) tmem_alloc<2>(tmem_slot, 512);
+    {
+        const uint4* ghi = reinterpret_cast<const uint4*>(blob + tc_off(0, dir, 0));
+        const uint4* glo = reinterpret_cast<const uint4*>(blob + tc_off(0, dir, 1));
+        uint4* dhi = reinterpret_cast<uint4*>(sBhi); uint4* dlo = reinterpret_cast<uint4*>(sBlo);
+        for (int i = (int)threadIdx.x; i < (K / 8) * RB; i += kP2Threads) {
+            const int ch = i / RB, r = i - ch * RB;
+            const int g = ch * 256 + (int)cta_rank * RB + r;
+            dhi[i] = __ldg(ghi + g); dlo[i] = __ldg(glo + g);
+        }
+        uint4* a = reinterpret_cast<uint4*>(sAhi);
+        for (int i = tid; i < (int)(S::a_stride / 16); i += kP2GroupThreads) a[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    float c[UB][8];
+#pragma unroll
+    for (int j = 0; j < UB; ++j)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[j][u] = 0.f;
+
+    int2 xraw[8];
+    auto load_x = [&](int t) {
+        const int2* g = reinterpret_cast<const int2*>(xi ? (const void*)(xi + (site * kT + t) * kF) : (const void*)(xf + (site * kT + t) * kF));
+        if (sub == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xraw[j] = ldg_nc_volatile(g + j);
+        } else {
+            xraw[0] = ldg_nc_volatile(g + 8);
+        }
+    };
+    auto xval = [&](int j) -> float {
+        const int2 p = xraw[j >> 1];
+        const int b = (j & 1) ? p.y : p.x;
+        return xi ? (float)b : __int_as_float(b);
+    };
+    auto store_x = [&]() {
+        if (sub == 0) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = xval(ch * 8 + j);
+                const HiLo8 sp = split8(v);
+                reinterpret_cast<uint4*>(sAhi + ch * LBO_A)[row] = sp.hi;
+                reinterpret_cast<uint4*>(sAlo + ch * LBO_A)[row] = sp.lo;
+                reinterpret_cast<uint4*>(sAsc + ch * LBO_A)[row] = scale_hi(sp.hi);
+            }
+        } else {
+            const float v[8] = {xval(0), xval(1), 1.0f, 0.f, 0.f, 0.f, 0.f, 0.f};  // x16, x17, bias column
+            const HiLo8 sp = split8(v);
+            reinterpret_cast<uint4*>(sAhi + 2 * LBO_A)[row] = sp.hi;
+            reinterpret_cast<uint4*>(sAlo + 2 * LBO_A)[row] = sp.lo;
+            reinterpret_cast<uint4*>(sAsc + 2 * LBO_A)[row] = scale_hi(sp.hi);
+        }
+    };
+    // "this warp's operand rows are written and its TMEM reads have retired": one arrival per warp on the leader's barrier
+    auto report_ready = [&]() {
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(barReady, 0);      // the leader maps to itself
+    };
+    {
+        load_x(dir == 0 ? 0 : kT - 1); store_x();
+    }
+    tc_fence_before();
+    cluster_sync_all();                                            // barriers initialised, operands zeroed, TMEM allocated (both CTAs)
+    tc_fence_after();
+    report_ready();
+
+    const uint32_t tmem_base = *tmem_slot + (uint32_t)grp * 256u;
+    const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), a_sc = smem_u32(sAsc), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
+    constexpr uint32_t idesc = make_idesc(256, 256);
+    const bool issuer = cta_rank == 0 && tid == 0;
+    uint32_t phaseH = 0, phaseR = 0, phaseT = 0;
+    if (cta_rank == 0 && threadIdx.x == 0) mbar_arrive(barTurn + 0);          // group 0 issues first
+
+    for (int step = 0; step < kT; ++step) {
+        const int t = dir == 0 ? step : (kT - 1 - step);
+        const int tn = dir == 0 ? step + 1 : (kT - 2 - step);
+        const bool more = step + 1 < kT;
+        if (issuer) {
+            mbar_wait_cluster(barReady, phaseR);                   // every warp of this group, in both CTAs, has reported
+            mbar_wait(barTurn + grp, phaseT);                      // and it is this group's turn on the tensor pipe
+            tc_fence_after();
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll 1
+                for (int kb = 0; kb < KB; ++kb) {
+                    uint32_t aa = pass == 2 ? a_lo : a_hi;
+                    if (pass == 1 && kb < IN / 16) aa = a_sc;
+                    const uint32_t bb = pass == 1 ? b_lo : b_hi;
+                    umma_f16<2>(tmem_base, make_desc(aa + kb * 2 * LBO_A, LBO_A, SBO), make_desc(bb + kb * 2 * LBO_B, LBO_B, SBO), idesc,
+                                (pass | kb) ? 1u : 0u);
+                }
+            }
+            umma_commit<2>(barH);
+            mbar_arrive(barTurn + (grp ^ 1));                      // hand the token to the other group
+        }
+        phaseR ^= 1; phaseT ^= 1;
+        if (more) load_x(tn);
+        mbar_wait(barH, phaseH);
+        phaseH ^= 1;
+        tc_fence_after();
+
+        uint32_t vb[2][16];
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * UB) * 32u;
+        tmem_ld16_nowait(tacc, vb[0]);
+        tmem_wait_ld();
+        float hv[8];
+#pragma unroll
+        for (int hb = 0; hb < 2 * UB; ++hb) {
+            const int jl = hb >> 1, uh = hb & 1, jb = sub * UB + jl;
+            if (hb + 1 < 2 * UB) tmem_ld16_nowait(tacc + (hb + 1) * 16, vb[(hb + 1) & 1]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t* v = vb[hb & 1];
+                // same cell update as lstm_tc_kernel (scales folded into the weights, scaled cell state)
+                const float xi_ = fminf(__uint_as_float(v[u]), 36.f), xf_ = fminf(__uint_as_float(v[4 + u]), 36.f);
+                const float xg_ = fminf(__uint_as_float(v[8 + u]), 36.f), xo_ = __uint_as_float(v[12 + u]);
+                const float ei = ex2_approx(xi_), ef = ex2_approx(xf_), eg = ex2_approx(xg_), eo = ex2_approx(xo_);
+                const float pi = 1.f + ei, pf = 1.f + ef, pg = 1.f + eg;
+                const float pig = pi * pg;
+                const float num = fmaf(c[jl][uh * 4 + u], pig, fmaf(eg, 2.f * kLog2e, -2.f * kLog2e) * pf);
+                const float cn = num * rcp_approx(pf * pig);
+                c[jl][uh * 4 + u] = cn;
+                const float ec = ex2_approx(cn);
+                hv[uh * 4 + u] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));
+            }
+            if (hb + 1 < 2 * UB) tmem_wait_ld();
+            if (uh == 1) {
+                const HiLo8 sp = split8(hv);
+                reinterpret_cast<uint4*>(sAhi + (IN / 8 + jb) * LBO_A)[row] = sp.hi;
+                reinterpret_cast<uint4*>(sAlo + (IN / 8 + jb) * LBO_A)[row] = sp.lo;
+                if (live) {
+                    __half* o = h0_out + ((((size_t)tile_idx * kT + t) * 2) * 16 + (dir * 8 + jb)) * (kRows * 8) + row * 8;
+                    *reinterpret_cast<uint4*>(o) = sp.hi;
+                    *reinterpret_cast<uint4*>(o + 16 * kRows * 8) = sp.lo;
+                }
+            }
+        }
+        if (more) { store_x(); report_ready(); }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (threadIdx.x < 32) tmem_dealloc<2>(*tmem_slot, 512);
+}
+
+int launch_l0_pair2(const void* blob, const int32_t* xi, const float* xf, void* h0_out, int64_t m, cudaStream_t stream) {
+    using S = P2Smem;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(lstm0_pair2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total) != cudaSuccess)
+            return cuda_status("cudaFuncSetAttribute(lstm0_pair2_kernel)");
+        attr_done = true;
+    }
+    unsigned tiles = (unsigned)((m + kRows - 1) / kRows);
+    unsigned gx = (tiles + 1) / 2; if (gx & 1) ++gx;             // two groups per CTA, whole clusters; padding groups work on clamped rows
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, 2, 1);
+    cfg.blockDim = dim3(kP2Threads, 1, 1);
+    cfg.dynamicSmemBytes = S::total;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, lstm0_pair2_kernel, (const unsigned char*)blob, xi, xf, (__half*)h0_out, m);
+    if (e != cudaSuccess) return set_error(NSNP_E_CUDA, "lstm0_pair2_kernel: %s", cudaGetErrorString(e));
+    return NSNP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -713,10 +982,13 @@ int launch_tail_tc(const void* blob, const float* h16, int64_t n_max, const int3
 }
 
 int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, cudaStream_t stream) {
-    // layer 0: CTA pairs share W (53 KB each) so two CTAs fit per SM and one CTA's MMAs overlap the other's epilogue
+    // layer 0: CTA pairs share W (half each); two 128-site groups per CTA alternate between tensor pipe and cell update
     {
         ProfScope prof(NSNP_PROF_LSTM0, stream);
-        if (int e = launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e;
+        // default: two alternating groups per CTA (lstm0_pair2_kernel); NSNP_L0_VARIANT=0 selects two independent CTAs per SM
+        static const int variant = [] { const char* v = getenv("NSNP_L0_VARIANT"); return v ? atoi(v) : 1; }();
+        if (int e = variant == 1 ? launch_l0_pair2(blob, xi, xf, h0, m, stream)
+                                 : launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e;
     }
     // layer 1: W only fits split across a CTA pair (2 x 104 KB); one CTA per SM, 16 warps for the epilogue
     ProfScope prof(NSNP_PROF_LSTM1, stream);

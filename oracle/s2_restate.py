@@ -70,6 +70,15 @@ class PileupModelOracle(nn.Module):
         gt, zy = self.forward_layer(self.encoder(x))
         return torch.softmax(gt, 1), torch.softmax(zy, 1)
 
+    @torch.no_grad()
+    def predict64(self, x):
+        """The same network evaluated in float64 (results rounded to float32): a checker whose value does not depend on
+        which fp32 LSTM kernel the host CPU's torch build picks (two GPU boxes differed by 2e-5 in `predict`)."""
+        import copy
+        m = copy.deepcopy(self).double()
+        gt, zy = m.forward_layer(m.encoder(torch.as_tensor(x).to(torch.float64)))
+        return torch.softmax(gt, 1).float(), torch.softmax(zy, 1).float()
+
     def state_dicts(self):
         return ({k: v.detach().clone() for k, v in self.encoder.state_dict().items()},
                 {k: v.detach().clone() for k, v in self.forward_layer.state_dict().items()})

@@ -98,6 +98,6 @@ def test_tensor_core_random_weights(small_case):
     m = PileupModelOracle(seed=77)
     tc = PileupModelForward(PileupModelWeights(*m.state_dicts(), device="cuda:0"), _lib.PREC_F16X3)
     x = small_case["windows"][:2000]
-    g0, z0 = m.predict(x)
+    g0, z0 = m.predict64(x)
     g1, z1 = tc(torch.from_numpy(x).cuda())
     assert np.abs(g1.cpu().numpy() - g0.numpy()).max() < F16X3_ATOL and np.abs(z1.cpu().numpy() - z0.numpy()).max() < F16X3_ATOL

@@ -237,7 +237,9 @@ __global__ void __launch_bounds__(256, 4) tail_kernel(const float* __restrict__ 
 }
 constexpr size_t kTailSmem = (size_t)kTailS * (128 + 256) * sizeof(float);
 
-constexpr int64_t kChunkSites = 148 * 128 * 4;     // 75,776 sites: whole waves of 128-site CTAs on 148 SMs (both LSTM kernels)
+// sites per LSTM launch: whole waves of 128-site tiles on 148 SMs for both LSTM kernels; bounds the layer-0 output buffer
+// (16.9 KB per site).  NSNP_CHUNK_WAVES (experiments) scales it.
+static const int64_t kChunkSites = [] { const char* v = getenv("NSNP_CHUNK_WAVES"); const int w = v ? atoi(v) : 4; return (int64_t)148 * 128 * (w < 1 ? 1 : w); }();
 
 }  // namespace
 }  // namespace nsnp

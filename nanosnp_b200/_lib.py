@@ -5,11 +5,12 @@ deliberately no pure-Python / PyTorch fallback for any kernel.
 """
 from __future__ import annotations
 
+import os
 import ctypes as C
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libnanosnp_b200.so"
+LIB_PATH = Path(os.environ["NSNP_LIB"]) if os.environ.get("NSNP_LIB") else _HERE / "libnanosnp_b200.so"   # NSNP_LIB: A/B builds
 
 # error codes (include/nanosnp_b200.h)
 OK, E_INVALID, E_CUDA, E_WORKSPACE, E_OVERFLOW, E_NO_DEVICE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6

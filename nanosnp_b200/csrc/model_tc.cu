@@ -246,7 +246,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     if (!live) site = n - 1;                                     // clamp loads, skip stores
 
     // ---- one-time setup ----
-    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); mbar_init(bar + 3, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc<CG>(tmem_slot, LAYER == 1 ? 512 : 256);
     {   // this CTA's weight rows: global [K/8][256][8] halfs -> shared [K/8][RB][8]
         const uint4* ghi = reinterpret_cast<const uint4*>(blob + tc_off(LAYER, dir, 0));
@@ -314,7 +314,6 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     // layer 1: the layer-0 output of one (tile, t) is stored exactly in operand layout, hi part then lo part, 32 KB each:
     //     h0[tile][t][hi|lo][chunk 16][row 128][8 halfs]
     uint64_t* barS = bar + 2;                                        // "input part of A for the next step has landed"
-    uint64_t* barS2 = bar + 3;                                       // leader CTA only: "... and so has the peer CTA's"
     constexpr uint32_t kPartBytes = 16u * kRows * 16u;               // 32 KB
     const bool l2_prefetch = (dir_override >> 8) & 1;
     // the padding CTA of an odd tile count (clusters come in pairs) re-reads the last real tile: it must not touch memory
@@ -343,7 +342,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();         // barriers initialised, operands zeroed, TMEM allocated
     tc_fence_after();
-    uint32_t phaseH = 0, phaseX = 0, phaseS = 0, phaseS2 = 0;
+    uint32_t phaseH = 0, phaseX = 0, phaseS = 0;
     if (LAYER == 1) {
         if (producer && lane == 0) stage_h0_bulk(dir == 0 ? 0 : kT - 1);
         mbar_wait(barS, phaseS); phaseS ^= 1;
@@ -354,11 +353,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), a_sc = smem_u32(sAsc), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
     constexpr uint32_t idesc = make_idesc(128 * CG, 256);
-    // Layer 1: the MMAs are issued from the producer warp.  tcgen05.mma issue blocks while the tensor pipe's queue is full,
-    // so 39 back-to-back MMAs hold the issuing thread for most of a step; an epilogue warp that issues them starts its
-    // own cell updates ~4000 cycles late and the whole CTA pair waits for it at the next hand-off (clock64 trace:
-    // 7400 -> 6100 cycles per step).  Layer 0 waits for all of its MMAs anyway, so thread 0 issues them.
-    const bool issuer = cta_rank == 0 && (LAYER == 1 ? (producer && lane == 0) : tid == 0);
+    const bool issuer = cta_rank == 0 && tid == 0;
     // k-blocks [kb0, kb1) x three hi/lo passes into the accumulator at tmem_d
     auto issue = [&](int kb0, int kb1, uint32_t tmem_d, uint32_t acc) {
 #pragma unroll 1
@@ -380,9 +375,8 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
         // while the epilogue of step t runs on the SM; only the 12 h-part MMAs stay on the per-step critical path
         if (issuer) { tc_fence_after(); issue(0, XB, tmem_base, 0); umma_commit<CG>(barX); }
         if (producer) {
-            if (lane == 0) { mbar_wait(barX, phaseX); if (C::STEPS > 1 && !DEBUG) stage_h0_bulk(dir == 0 ? 1 : kT - 2); }
-            phaseX ^= 1;
-            __syncwarp();
+            mbar_wait(barX, phaseX); phaseX ^= 1;
+            if (lane == 0 && C::STEPS > 1 && !DEBUG) stage_h0_bulk(dir == 0 ? 1 : kT - 2);
         }
     }
 
@@ -392,42 +386,28 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
         const bool more = !DEBUG && step + 1 < C::STEPS;
         const uint32_t acc_cols = LAYER == 1 ? (uint32_t)(step & 1) * 256u : 0u;
         // ---- operands written by the generic proxy -> visible to the tensor core; TMEM reads of the last step retired ----
+        if (LAYER == 1 && more) { mbar_wait(barS, phaseS); phaseS ^= 1; }      // the input rows of step t+1 have landed (their MMAs are issued below)
         fence_async_smem();
         tc_fence_before();
         if (CG == 2) cluster_sync_exec(); else __syncthreads();
-        if (LAYER == 0 && issuer) {
+        if (issuer) {
             tc_fence_after();
-            issue(0, KB, tmem_base, 0);
-            umma_commit<CG>(barH);
+            if (LAYER == 1) {
+                issue(XB, KB, tmem_base + acc_cols, 1);                       // += W_hh . h_{t-1}
+                umma_commit<CG>(barH);
+                if (more) { issue(0, XB, tmem_base + (acc_cols ^ 256u), 0); umma_commit<CG>(barX); }
+            } else {
+                issue(0, KB, tmem_base, 0);
+                umma_commit<CG>(barH);
+            }
         }
         if (producer) {
-            // Layer 1, producer warp (one lane): issues the MMAs (leader CTA), tracks the bulk copies and refills the input
-            // operand.  It never touches TMEM and skips the epilogue.  Nobody else waits for the copies: the h-part MMAs
-            // of this step go out at once, the input part of step t+1 follows when BOTH CTAs' rows have landed (the peer
-            // reports through barS2), and the rows of step t+2 are requested as soon as those MMAs have retired.
-            if (lane == 0) {
-                if (cta_rank == 0) {
-                    tc_fence_after();
-                    issue(XB, KB, tmem_base + acc_cols, 1);                       // += W_hh . h_{t-1}
-                    umma_commit<CG>(barH);
-                    if (more) {
-                        mbar_wait(barS, phaseS);
-                        if (CG == 2) mbar_wait_cluster(barS2, phaseS2);
-                        tc_fence_after();
-                        issue(0, XB, tmem_base + (acc_cols ^ 256u), 0);
-                        umma_commit<CG>(barX);
-                    }
-                } else if (more) {
-                    mbar_wait(barS, phaseS);
-                    mbar_arrive_remote(barS2, 0);
-                }
-                if (more) {
-                    mbar_wait(barX, phaseX);
-                    if (step + 2 < C::STEPS) stage_h0_bulk(dir == 0 ? step + 2 : kT - 3 - step);
-                }
+            // producer warp: once the input-part MMAs of step t+1 have completed, their operand region takes the rows of
+            // step t+2 (two 32 KB bulk copies); it never touches TMEM and skips the epilogue
+            if (more) {
+                mbar_wait(barX, phaseX); phaseX ^= 1;
+                if (lane == 0 && step + 2 < C::STEPS) stage_h0_bulk(dir == 0 ? step + 2 : kT - 3 - step);
             }
-            if (more) { phaseS ^= 1; phaseS2 ^= 1; phaseX ^= 1; }
-            __syncwarp();
             if (DEBUG) break;
             continue;
         }
@@ -982,7 +962,7 @@ int launch_tail_tc(const void* blob, const float* h16, int64_t n_max, const int3
 }
 
 int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, cudaStream_t stream) {
-    // layer 0: CTA pairs share W (half each); two 128-site groups per CTA alternate between tensor pipe and cell update
+    // layer 0: CTA pairs share W (53 KB each) so two CTAs fit per SM and one CTA's MMAs overlap the other's epilogue
     {
         ProfScope prof(NSNP_PROF_LSTM0, stream);
         // default: two alternating groups per CTA (lstm0_pair2_kernel); NSNP_L0_VARIANT=0 selects two independent CTAs per SM

@@ -349,7 +349,7 @@ def main_ours(args):
                     "traffic": traffic.get(dom, {}).get("dram_bytes_per_position", 0) * Lr / len(regions) or None}
     else:
         d = kernels[dom]
-        roofline = {"kernel": {"lstm_layer0": "lstm_tc_kernel<0,2,2> (layer-0 BiLSTM, tcgen05 cta_group::2)",
+        roofline = {"kernel": {"lstm_layer0": "lstm0_pair2_kernel (layer-0 BiLSTM, tcgen05 cta_group::2, two alternating site groups per CTA)",
                                "lstm_layer1": "lstm_tc_kernel<1,2,4> (layer-1 BiLSTM, tcgen05 cta_group::2)"}[dom] if args.precision != "fp32" else dom,
                     "bound": "tensor", "achieved": d["achieved"], "peak": tf_peak, "unit": "TFLOP/s", "frac": d["frac"],
                     "traffic": d.get("traffic"), "traffic_note": "DRAM bytes per launch, scaled from the ncu capture in profiles/traffic.json",

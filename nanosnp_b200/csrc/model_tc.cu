@@ -47,7 +47,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// cluster-scope flavours for the hand-off between the two CTAs of a pair
+// cluster-scope wait for the hand-off between the two CTAs of a pair
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
@@ -57,11 +57,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         "bra WAIT_LOOP_C;\n\t"
         "DONE_C:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t target_cta) {     // same barrier offset in CTA target_cta
-    uint32_t raddr;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(target_cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 // Relaxed remote arrive: execution ordering only.  The operand rows were already made visible to the async proxy by
 // fence.proxy.async and the TMEM reads retired (tcgen05.fence); a .release at cluster scope would additionally drain this

@@ -32,8 +32,9 @@ constexpr size_t kBlobFloats = kOffHeadB + 24 + 8;
 //   B[k/8][n][k%8] halfs, n = unit_block*32 + unit_half*16 + gate*4 + unit_in_half  (TMEM column order: every
 //   16 columns hold i,f,g,o of 4 hidden units, so the epilogue can pipeline 16-column TMEM loads)
 //   layer 0: K = 96  = [x 0..17 | bias column 18 | pad ..31 | h 32..95]; lo part of k < 32 is pre-scaled by 2^10
-//   layer 1: K = 208 = [l0 out 0..127 | bias column 128 | pad ..143 | h 144..207]
-constexpr int kTcK0 = 96, kTcIn0 = 32, kTcK1 = 208, kTcIn1 = 144;
+//   layer 1: K = 192 = [l0 out 0..127 | h 128..191]; its bias is added in the epilogue (a bias column would cost a whole
+//            k-block = 2 of 38 MMAs per step on a tensor-bound kernel): float [2 dirs][256] in column order n, at kOffTcBias1
+constexpr int kTcK0 = 96, kTcIn0 = 32, kTcK1 = 192, kTcIn1 = 128;
 constexpr float kTcLoScale = 1024.0f;
 constexpr size_t kTcBytes0 = (size_t)kTcK0 * 256 * 2;       // one (hi or lo) array of one direction
 constexpr size_t kTcBytes1 = (size_t)kTcK1 * 256 * 2;
@@ -45,7 +46,8 @@ constexpr size_t tc_off(int layer, int dir, int lo) {
 // tail: W' = dense o output_proj, [k/8 = 16][n = 256 dense outputs][k%8] halfs, hi then lo (64 KB each)
 constexpr size_t kTcBytesTail = (size_t)128 * 256 * 2;
 constexpr size_t kOffTcTail = kOffTcBytes + 4 * kTcBytes0 + 4 * kTcBytes1;
-constexpr size_t kBlobBytes = kOffTcTail + 2 * kTcBytesTail;
+constexpr size_t kOffTcBias1 = kOffTcTail + 2 * kTcBytesTail;
+constexpr size_t kBlobBytes = kOffTcBias1 + 2 * 256 * sizeof(float);
 
 // fp16 hi/lo tensor-core LSTM (model_tc.cu).  h0: fp16 [site][33][2][128]; h16: fp32 [site][128].
 int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, cudaStream_t stream);

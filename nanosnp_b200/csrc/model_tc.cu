@@ -204,7 +204,8 @@ template <int LAYER, int CG> struct TcSmem {
     static constexpr size_t a_bytes = (size_t)K * kRows * 2;
     static constexpr size_t sc_bytes = LAYER == 0 ? (size_t)kTcIn0 * kRows * 2 : 0;
     static constexpr size_t off_bhi = 0, off_blo = b_bytes, off_ahi = 2 * b_bytes, off_alo = off_ahi + a_bytes,
-                            off_asc = off_alo + a_bytes, off_bar = off_asc + sc_bytes, total = off_bar + 64;
+                            off_asc = off_alo + a_bytes, off_bar = off_asc + sc_bytes, off_bias = off_bar + 64,
+                            total = off_bias + (LAYER == 1 ? 256 * sizeof(float) : 0);
 };
 
 // NWQ warps share each TMEM lane quadrant (each thread = one site row x 64/NWQ hidden units).
@@ -258,7 +259,13 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     }
     __syncthreads();
     // constant chunk holding the bias column (1.0) -- layer 0: chunk 2 is rewritten every step with x16, x17
-    if (LAYER == 1 && sub == 0 && !producer) reinterpret_cast<uint4*>(sAhi + (size_t)(kIn1 / 8) * LBO_A)[row] = make_uint4(0x3C00u, 0, 0, 0);
+    // layer 1: the (scaled) bias of this direction, added to the accumulators in the epilogue
+    const float* sBias = reinterpret_cast<const float*>(smem + S::off_bias);
+    if (LAYER == 1) {
+        const float* gb = reinterpret_cast<const float*>(blob + kOffTcBias1) + dir * 256;
+        for (int i = tid; i < 256; i += kThreads) reinterpret_cast<float*>(smem + S::off_bias)[i] = __ldg(gb + i);
+        __syncthreads();
+    }
 
     float c[UB][8];
 #pragma unroll
@@ -356,7 +363,6 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
 #pragma unroll 1
             for (int kb = kb0; kb < kb1; ++kb) {
                 // pass 0: a_hi.w_hi   pass 1: a_hi.w_lo (layer-0 counts: scaled copy)   pass 2: a_lo.w_hi
-                if (LAYER == 1 && pass == 2 && kb == kIn1 / 16) continue;     // the bias k-block: its A operand is the constant 1.0, lo half exactly zero
                 uint32_t aa = pass == 2 ? a_lo : a_hi;
                 if (LAYER == 0 && pass == 1 && kb < kTcIn0 / 16) aa = a_sc;
                 const uint32_t bb = pass == 1 ? b_lo : b_hi;
@@ -416,7 +422,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
             for (int jb = sub * UB; jb < sub * UB + UB; ++jb) {
                 float v[32];
                 tmem_ld32(tmem_base + acc_cols + ((uint32_t)(quad * 32) << 16) + jb * 32, v);
-                if (live) for (int i = 0; i < 32; ++i) dbg[(site0 + row) * 256 + jb * 32 + i] = v[i];
+                if (live) for (int i = 0; i < 32; ++i) dbg[(site0 + row) * 256 + jb * 32 + i] = v[i] + (LAYER == 1 ? sBias[jb * 32 + i] : 0.f);
             }
             break;
         }
@@ -443,8 +449,10 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
                 // one gives ex2 = 0, which is exact.  With the clamps every (1 + e) factor is <= 2^36 + 1, so the triple
                 // product stays below 2^108 and its reciprocal stays a normal float.  |c'| <= 33 after 33 steps, so
                 // ex2(cs') <= 2^96 needs no clamp; an overflowing (1 + eo) makes rcp return 0 = the exact limit.
-                const float xi_ = fminf(__uint_as_float(v[u]), 36.f), xf_ = fminf(__uint_as_float(v[4 + u]), 36.f);
-                const float xg_ = fminf(__uint_as_float(v[8 + u]), 36.f), xo_ = __uint_as_float(v[12 + u]);
+                const float* bq = sBias + jb * 32 + uh * 16 + u;              // layer 1 only: bias of gate columns i, f, g, o
+                const float bi_ = LAYER == 1 ? bq[0] : 0.f, bf_ = LAYER == 1 ? bq[4] : 0.f, bg_ = LAYER == 1 ? bq[8] : 0.f, bo_ = LAYER == 1 ? bq[12] : 0.f;
+                const float xi_ = fminf(__uint_as_float(v[u]) + bi_, 36.f), xf_ = fminf(__uint_as_float(v[4 + u]) + bf_, 36.f);
+                const float xg_ = fminf(__uint_as_float(v[8 + u]) + bg_, 36.f), xo_ = __uint_as_float(v[12 + u]) + bo_;
                 const float ei = ex2_approx(xi_), ef = ex2_approx(xf_), eg = ex2_approx(xg_), eo = ex2_approx(xo_);
                 const float pi = 1.f + ei, pf = 1.f + ef, pg = 1.f + eg;
                 // cs' = sigmoid(f) cs + K sigmoid(i) tanh(g), K = -2 log2e, over one common denominator
@@ -992,7 +1000,7 @@ int pack_tc_weights(const nsnp_model_weights_t* w, unsigned char* blob) {
                 for (int k = 0; k < K; ++k) {
                     float v = 0.f;
                     if (k < nin) v = wih[rowi * nin + k];
-                    else if (k == nin) v = bi[rowi] + bh[rowi];
+                    else if (layer == 0 && k == nin) v = bi[rowi] + bh[rowi];          // layer 0: bias rides as a constant-1 input column
                     else if (k >= IN) v = whh[rowi * kH + (k - IN)];
                     v *= gate == 2 ? -2.0f * kLog2e : -kLog2e;         // activation scale folded into the weights (see the epilogue)
                     const float scale = (layer == 0 && k < IN) ? kTcLoScale : 1.0f;
@@ -1001,6 +1009,7 @@ int pack_tc_weights(const nsnp_model_weights_t* w, unsigned char* blob) {
                     const size_t idx = ((size_t)(k >> 3) * 256 + n) * 8 + (k & 7);
                     hi[idx] = h; lo[idx] = l;
                 }
+                if (layer == 1) reinterpret_cast<float*>(blob + kOffTcBias1)[d * 256 + n] = (bi[rowi] + bh[rowi]) * (gate == 2 ? -2.0f * kLog2e : -kLog2e);
             }
         }
     }

@@ -2,14 +2,16 @@
 // as tcgen05.mma with TMEM accumulators, hand-written for sm_100a.
 //
 // One CTA = 128 candidate sites x one direction of one layer; per time step
-//     gates[128 x 256] = [in_t | 1 | h_{t-1}] [128 x K]  .  W^T [K x 256]        (K = 96 layer 0, 208 layer 1)
+//     gates[128 x 256] = [in_t | h_{t-1}] [128 x K]  .  W^T [K x 256]            (K = 96 layer 0, 192 layer 1)
 // runs as K/16 x 3 tcgen05.mma (M=128 or 256, N=256, K=16, kind::f16, fp32 accumulate in 256 TMEM columns).
 //
 // Precision: fp32-grade results from fp16 tensor-core inputs by hi/lo operand splitting,
 //     a.w  ~=  a_hi.w_hi + a_hi.w_lo + a_lo.w_hi        (dropped term a_lo.w_lo ~ 2^-22 relative)
 // implemented as three K-passes into the same accumulator.  Counts (layer-0 inputs, integers that reach
 // hundreds) use a pre-scaled low part -- (x_hi 2^-10).(w_lo 2^10) -- so the low weight halves stay in the
-// normal fp16 range.  Biases ride in the GEMM as a constant-1 input column.
+// normal fp16 range.  Layer 0's bias rides in the GEMM as a constant-1 input column (its input k-blocks have spare
+// columns); layer 1 is tensor-bound, so its bias is added in the epilogue instead of costing a k-block.  The activation
+// scales (-log2 e, -2 log2 e) are folded into the packed weights: every exponential is a bare ex2 of an accumulator.
 //
 // Operands sit in shared memory in the UMMA canonical K-major / no-swizzle layout: 8x(16-byte) core
 // matrices, [k/8][row][k%8]; a thread owns one site row, so it writes whole 16-byte core-matrix rows
@@ -20,7 +22,10 @@
 // st.shared (next step's operand) and -> global for layer 1.
 //
 // CG = 2 pairs two CTAs (cta_group::2): M = 256, each CTA holds half of W (N/2 rows) -- that is what makes the
-// layer-1 weights (2 x 104 KB) fit; the leader CTA issues the MMAs, tcgen05.commit multicasts completion.
+// layer-1 weights (2 x 96 KB) fit; the leader CTA issues the MMAs, tcgen05.commit multicasts completion.
+//
+// Kernels: lstm0_pair2_kernel (layer 0, production), lstm_tc_kernel<1,2,4> (layer 1, production),
+// lstm_tc_kernel<0,...> (layer-0 alternative NSNP_L0_VARIANT=0 and the raw-accumulator debug entry), tail_tc_kernel.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "model_common.cuh"
@@ -372,7 +377,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
         }
     };
     if (LAYER == 1) {
-        // software pipeline: the input part of step t+1 (27 of 39 MMAs, independent of h_t) runs on the tensor core
+        // software pipeline: the input part of step t+1 (24 of 36 MMAs, independent of h_t) runs on the tensor core
         // while the epilogue of step t runs on the SM; only the 12 h-part MMAs stay on the per-step critical path
         if (issuer) { tc_fence_after(); issue(0, XB, tmem_base, 0); umma_commit<CG>(barX); }
         if (producer) {

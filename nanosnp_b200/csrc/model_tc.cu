@@ -539,12 +539,17 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
 
     const int quad = warp & 3, sub = warp >> 2;
     const int row = quad * 32 + lane;
-    const int dir = (int)blockIdx.y;
+    // Persistent: cluster k works in direction k & 1 on the tile quads k >> 1, k >> 1 + stride, ... (a quad = the four
+    // 128-site tiles of one cluster: two groups in each of the two CTAs).  Weights, TMEM and barriers are set up once.
     const uint32_t cta_rank = cluster_ctarank();
-    const int64_t tile_idx = (int64_t)blockIdx.x * 2 + grp;
-    int64_t site = tile_idx * kRows + row;
-    const bool live = site < n;
-    if (!live) site = n - 1;
+    const int cluster_id = (int)(blockIdx.x >> 1);
+    const int dir = cluster_id & 1;
+    const int quad_stride = (int)(gridDim.x >> 2);
+    const int n_quads = (int)((n + 4 * kRows - 1) / (4 * kRows));
+    const int q0 = cluster_id >> 1;
+    const int my_quads = q0 < n_quads ? (n_quads - q0 + quad_stride - 1) / quad_stride : 0;
+    const int total_g = my_quads * kT;                          // this group's stream of (quad, step) pairs
+    auto tile_of = [&](int qi) -> int64_t { return (int64_t)(q0 + qi * quad_stride) * 4 + (int64_t)cta_rank * 2 + grp; };
 
     if (threadIdx.x == 0) {
         mbar_init(bars + 0, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 16); mbar_init(bars + 3, 16);
@@ -573,7 +578,11 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
         for (int u = 0; u < 8; ++u) c[j][u] = 0.f;
 
     int2 xraw[8];
-    auto load_x = [&](int t) {
+    auto load_x = [&](int gstep) {                              // count row of stream element gstep
+        const int qi = gstep / kT, st = gstep - qi * kT;
+        const int t = dir == 0 ? st : (kT - 1 - st);
+        int64_t site = tile_of(qi) * kRows + row;
+        if (site >= n) site = n - 1;
         const int2* g = reinterpret_cast<const int2*>(xi ? (const void*)(xi + (site * kT + t) * kF) : (const void*)(xf + (site * kT + t) * kF));
         if (sub == 0) {
 #pragma unroll
@@ -614,13 +623,11 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
         __syncwarp();
         if (lane == 0) mbar_arrive_remote_relaxed(barReady, 0);      // the leader maps to itself
     };
-    {
-        load_x(dir == 0 ? 0 : kT - 1); store_x();
-    }
+    if (total_g > 0) { load_x(0); store_x(); }
     tc_fence_before();
     cluster_sync_all();                                            // barriers initialised, operands zeroed, TMEM allocated (both CTAs)
     tc_fence_after();
-    report_ready();
+    if (total_g > 0) report_ready();
 
     const uint32_t tmem_base = *tmem_slot + (uint32_t)grp * 256u;
     const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), a_sc = smem_u32(sAsc), b_hi = smem_u32(sBhi), b_lo = smem_u32(sBlo);
@@ -629,10 +636,18 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
     uint32_t phaseH = 0, phaseR = 0, phaseT = 0;
     if (cta_rank == 0 && threadIdx.x == 0) mbar_arrive(barTurn + 0);          // group 0 issues first
 
-    for (int step = 0; step < kT; ++step) {
+    int step = 0, qi = 0;
+    for (int g = 0; g < total_g; ++g) {
         const int t = dir == 0 ? step : (kT - 1 - step);
-        const int tn = dir == 0 ? step + 1 : (kT - 2 - step);
-        const bool more = step + 1 < kT;
+        const bool more = g + 1 < total_g;
+        const int64_t tile_idx = tile_of(qi);
+        const bool live = tile_idx * kRows + row < n;
+        if (step == 0) {                                            // a new tile: the recurrence starts from c = 0, h = 0
+#pragma unroll
+            for (int j = 0; j < UB; ++j)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) c[j][u] = 0.f;
+        }
         if (issuer) {
             mbar_wait_cluster(barReady, phaseR);                   // every warp of this group, in both CTAs, has reported
             mbar_wait(barTurn + grp, phaseT);                      // and it is this group's turn on the tensor pipe
@@ -640,7 +655,7 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
 #pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll 1
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int kb = 0; kb < (step == 0 ? IN / 16 : KB); ++kb) {      // h = 0 at the first step of a tile: input k-blocks only
                     uint32_t aa = pass == 2 ? a_lo : a_hi;
                     if (pass == 1 && kb < IN / 16) aa = a_sc;
                     const uint32_t bb = pass == 1 ? b_lo : b_hi;
@@ -652,7 +667,7 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
             mbar_arrive(barTurn + (grp ^ 1));                      // hand the token to the other group
         }
         phaseR ^= 1; phaseT ^= 1;
-        if (more) load_x(tn);
+        if (more) load_x(g + 1);
         mbar_wait(barH, phaseH);
         phaseH ^= 1;
         tc_fence_after();
@@ -694,6 +709,7 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
             }
         }
         if (more) { store_x(); report_ready(); }
+        if (++step == kT) { step = 0; ++qi; }
     }
 
     tc_fence_before();
@@ -709,10 +725,11 @@ int launch_l0_pair2(const void* blob, const int32_t* xi, const float* xf, void* 
             return cuda_status("cudaFuncSetAttribute(lstm0_pair2_kernel)");
         attr_done = true;
     }
-    unsigned tiles = (unsigned)((m + kRows - 1) / kRows);
-    unsigned gx = (tiles + 1) / 2; if (gx & 1) ++gx;             // two groups per CTA, whole clusters; padding groups work on clamped rows
+    // persistent: at most one CTA per SM; clusters alternate between the two directions, so an even number of clusters
+    const unsigned quads = (unsigned)((m + 4 * kRows - 1) / (4 * kRows));
+    unsigned clusters = 2 * quads; if (clusters > (unsigned)kNumSMs / 2) clusters = ((unsigned)kNumSMs / 2) & ~1u;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(gx, 2, 1);
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
     cfg.blockDim = dim3(kP2Threads, 1, 1);
     cfg.dynamicSmemBytes = S::total;
     cfg.stream = stream;

@@ -9,6 +9,7 @@
 // Host code only (no kernels): this is the caller either side of the GPU path.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -156,6 +157,7 @@ extern "C" int64_t nsnp_vcf_format_batch(const char* contig, int64_t n, const in
 // Fast path: same records, hand-rolled number formatting, batches formatted on host threads.
 // Every shortcut falls back to the libc path above whenever its exactness argument does not hold.
 // ===================================================================================================
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -163,11 +165,28 @@ extern "C" int64_t nsnp_vcf_format_batch(const char* contig, int64_t n, const in
 
 namespace {
 
+// decimal digits two at a time from a 200-byte table, 32-bit arithmetic (every VCF field here fits 32 bits; larger values
+// peel off 9-digit groups first).  This is most of the per-record cost of the text assembly.
+alignas(64) const char kDigits2[201] =
+    "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+    "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+inline char* put_u32(char* p, uint32_t v) {
+    if (v < 100) {
+        if (v < 10) { *p++ = (char)('0' + v); return p; }
+        memcpy(p, kDigits2 + 2 * v, 2); return p + 2;
+    }
+    char tmp[10]; int n = 10;
+    while (v >= 100) { const uint32_t q = v / 100; n -= 2; memcpy(tmp + n, kDigits2 + 2 * (v - q * 100), 2); v = q; }
+    if (v >= 10) { n -= 2; memcpy(tmp + n, kDigits2 + 2 * v, 2); } else tmp[--n] = (char)('0' + v);
+    memcpy(p, tmp + n, 10 - n > 8 ? 10 : 8);                      // over-copy a fixed size: the caller's buffer has slack
+    return p + (10 - n);
+}
 inline char* put_uint(char* p, unsigned long long v) {
-    char tmp[24]; int n = 0;
-    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) *p++ = tmp[--n];
-    return p;
+    if (v <= 0xFFFFFFFFull) return put_u32(p, (uint32_t)v);
+    const unsigned long long hi = v / 1000000000ull; const uint32_t lo = (uint32_t)(v - hi * 1000000000ull);
+    p = put_uint(p, hi);
+    char d[9]; uint32_t f = lo; for (int i = 8; i >= 0; --i) { d[i] = (char)('0' + f % 10); f /= 10; }
+    memcpy(p, d, 9); return p + 9;
 }
 
 // QUAL: str(float(round(v, 2))) and int(...) of it.  v >= 0.  round() is correct rounding of the exact binary value
@@ -249,14 +268,14 @@ inline char* put_record(char* p, const char* contig, size_t clen, long long pos,
 }
 
 // one batch (predict.py:54-194), appended to `o`
-void format_batch_fast(std::string& o, const char* contig, size_t clen, int64_t n, const int32_t* pos1, const uint8_t* refbase,
+// writes the records at p (the caller provides kMaxRecordBytes + clen bytes per site) and returns the end
+char* format_batch_fast(char* p, const char* contig, size_t clen, int64_t n, const int32_t* pos1, const uint8_t* refbase,
                        const float* gt_prob, const float* zy_prob, const float* cov8)
 {
     int head_gt[10];
     const int nhead = n < 10 ? (int)n : 10;
     auto argmax = [](const float* v, int m) { int b = 0; for (int i = 1; i < m; ++i) if (v[i] > v[b]) b = i; return b; };
     for (int i = 0; i < nhead; ++i) head_gt[i] = argmax(gt_prob + (size_t)i * 21, 21);
-    char line[256 + 64];
     for (int64_t j = 0; j < n; ++j) {
         const float* gp = gt_prob + j * 21; const float* zp = zy_prob + j * 3;
         const int gt = argmax(gp, 21), zyo = argmax(zp, 3);
@@ -284,7 +303,7 @@ void format_batch_fast(std::string& o, const char* contig, size_t clen, int64_t 
         if (na == 0) {
             if (zyo == 0) {
                 const char a1[2] = {sref, 0};
-                e = put_record(line, contig, clen, pos1[j], sref, a1, qual, "RefCall", zy, depth, af, af_one);
+                e = put_record(p, contig, clen, pos1[j], sref, a1, qual, "RefCall", zy, depth, af, af_one);
             } else {
                 static const int tis_hom[4] = {0, 4, 7, 9};
                 static const int tis_het[6] = {1, 2, 3, 5, 6, 8};
@@ -299,7 +318,7 @@ void format_batch_fast(std::string& o, const char* contig, size_t clen, int64_t 
                 if (raised) continue;
                 char a1[2] = {0, 0};
                 if (zyo == 1) a1[0] = kGt[max_ti][0]; else a1[0] = kGt[max_ti][0] == sref ? kGt[max_ti][1] : kGt[max_ti][0];
-                e = put_record(line, contig, clen, pos1[j], sref, a1, zy_q, "PASS", zy, depth, af, af_one);
+                e = put_record(p, contig, clen, pos1[j], sref, a1, zy_q, "PASS", zy, depth, af, af_one);
             }
         } else {
             char alts[8];
@@ -307,12 +326,65 @@ void format_batch_fast(std::string& o, const char* contig, size_t clen, int64_t 
             else if (alt[0] == alt[1]) { alts[0] = alt[0]; alts[1] = 0; }
             else { alts[0] = alt[0]; alts[1] = ','; alts[2] = alt[1]; alts[3] = 0; }
             if (alts[1] == ',' && zyo != 2) zy = "1/2";
-            e = put_record(line, contig, clen, pos1[j], sref, alts, zyo == 0 ? gt_q : qual, "PASS", zy, depth, af, af_one);
+            e = put_record(p, contig, clen, pos1[j], sref, alts, zyo == 0 ? gt_q : qual, "PASS", zy, depth, af, af_one);
         }
-        o.append(line, (size_t)(e - line));
+        p = e;
     }
+    return p;
 }
 
+}  // namespace
+
+namespace {
+constexpr size_t kMaxRecordBytes = 128;     // upper bound of one record's text without the contig name
+
+// Runs nt workers; work(t, p) writes the t-th part at p (capacity need(t) bytes) and returns its end.  The parts are then
+// concatenated into `out` by the workers themselves once every size is known (spin barrier): a single-threaded memcpy of
+// ~64 bytes per record cost as much as formatting the records on two threads.  Part buffers persist in a pool (no page
+// faults after the first call).  Returns the total size, negated if it does not fit.
+struct PartBuf { char* data = nullptr; size_t cap = 0; };
+template <class Need, class Work>
+int64_t run_parts_parallel(int nt, Need&& need, Work&& work, char* out, int64_t out_capacity) {
+    static std::mutex pool_mu;
+    static std::vector<PartBuf> pool;
+    std::vector<PartBuf> parts((size_t)nt);
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        for (int t = 0; t < nt && !pool.empty(); ++t) { parts[(size_t)t] = pool.back(); pool.pop_back(); }
+    }
+    std::vector<int64_t> sizes((size_t)nt, 0);
+    std::atomic<int> done{0};
+    std::atomic<int> failed{0};
+    auto body = [&](int t) {
+        PartBuf pb = parts[(size_t)t];                     // worked on locally: the entries of `parts` share cache lines
+        const size_t want = need(t);
+        if (pb.cap < want) { free(pb.data); pb.data = (char*)malloc(want + want / 8 + 64); pb.cap = pb.data ? want + want / 8 + 64 : 0; }
+        if (!pb.data) failed.store(1);
+        else sizes[(size_t)t] = (int64_t)(work(t, pb.data) - pb.data);
+        done.fetch_add(1, std::memory_order_acq_rel);
+        while (done.load(std::memory_order_acquire) < nt) std::this_thread::yield();
+        int64_t off = 0, total = 0;
+        for (int k = 0; k < nt; ++k) { if (k < t) off += sizes[(size_t)k]; total += sizes[(size_t)k]; }
+        if (out && total <= out_capacity && !failed.load() && pb.data) memcpy(out + off, pb.data, (size_t)sizes[(size_t)t]);
+        parts[(size_t)t] = pb;
+    };
+    if (nt == 1) body(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(body, t);
+        body(0);
+        for (auto& x : th) x.join();
+    }
+    int64_t total = 0;
+    for (auto v : sizes) total += v;
+    const bool fits = out && total <= out_capacity && !failed.load();
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        for (auto& pb : parts) { if (pool.size() < 256) pool.push_back(pb); else free(pb.data); }
+    }
+    if (failed.load()) return 0;
+    return fits ? total : -total;
+}
 }  // namespace
 
 extern "C" int64_t nsnp_vcf_format_contig(const char* contig, int64_t n, const int32_t* pos1, const uint8_t* refbase,
@@ -327,43 +399,15 @@ extern "C" int64_t nsnp_vcf_format_contig(const char* contig, int64_t n, const i
     if ((int64_t)nt > n_batches) nt = (int)(n_batches > 0 ? n_batches : 1);
     // per-thread text buffers are kept between calls (fresh 40 MB allocations page-fault under the process-wide mm lock
     // and stop the threads from scaling); the pool is guarded for concurrent callers
-    static std::mutex pool_mu;
-    static std::vector<std::string> pool;
-    std::vector<std::string> parts((size_t)nt);
-    {
-        std::lock_guard<std::mutex> lk(pool_mu);
-        for (int t = 0; t < nt && !pool.empty(); ++t) { parts[(size_t)t] = std::move(pool.back()); pool.pop_back(); }
-    }
-    auto work = [&](int t) {
+    auto need = [&](int t) { return (size_t)((n_batches * (t + 1) / nt - n_batches * t / nt) * batch_size) * (kMaxRecordBytes + clen) + 64; };
+    return run_parts_parallel(nt, need, [&](int t, char* p) {
         const int64_t b0 = n_batches * t / nt, b1 = n_batches * (t + 1) / nt;
-        std::string o = std::move(parts[(size_t)t]);      // worked on locally: the headers in `parts` share cache lines
-        o.clear();
-        o.reserve((size_t)((b1 - b0) * batch_size) * (72 + clen));
         for (int64_t b = b0; b < b1; ++b) {
             const int64_t s = b * batch_size, m = (n - s) < batch_size ? (n - s) : batch_size;
-            format_batch_fast(o, contig, clen, m, pos1 + s, refbase + s, gt_prob + s * 21, zy_prob + s * 3, cov8 + s * 8);
+            p = format_batch_fast(p, contig, clen, m, pos1 + s, refbase + s, gt_prob + s * 21, zy_prob + s * 3, cov8 + s * 8);
         }
-        parts[(size_t)t] = std::move(o);
-    };
-    if (nt == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
-        work(0);
-        for (auto& x : th) x.join();
-    }
-    int64_t total = 0;
-    for (auto& s2 : parts) total += (int64_t)s2.size();
-    const bool fits = out && total <= out_capacity;
-    if (fits) {
-        char* p = out;
-        for (auto& s2 : parts) { memcpy(p, s2.data(), s2.size()); p += s2.size(); }
-    }
-    {
-        std::lock_guard<std::mutex> lk(pool_mu);
-        for (auto& s2 : parts) if (pool.size() < 256) pool.push_back(std::move(s2));
-    }
-    return fits ? total : -total;
+        return p;
+    }, out, out_capacity);
 }
 
 
@@ -411,19 +455,17 @@ inline char* put_record_q(char* p, const char* contig, size_t clen, long long po
     if (af_q == NSNP_AF_ONE) { memcpy(p, "1.000000", 8); p += 8; }
     else if (af_q == NSNP_AF_NAN) { memcpy(p, "nan", 3); p += 3; }
     else {
-        const unsigned long long u = (unsigned long long)af_q;
-        p = put_uint(p, u / 1000000ull);
+        const uint32_t u = (uint32_t)af_q, ip = u / 1000000u, f = u - ip * 1000000u;
+        p = put_u32(p, ip);
         *p++ = '.';
-        unsigned long long f = u % 1000000ull;
-        char d[6]; for (int i = 5; i >= 0; --i) { d[i] = (char)('0' + f % 10); f /= 10; }
-        memcpy(p, d, 6); p += 6;
+        const uint32_t f01 = f / 10000u, f2345 = f - f01 * 10000u, f23 = f2345 / 100u, f45 = f2345 - f23 * 100u;
+        memcpy(p, kDigits2 + 2 * f01, 2); memcpy(p + 2, kDigits2 + 2 * f23, 2); memcpy(p + 4, kDigits2 + 2 * f45, 2); p += 6;
     }
     *p++ = '\n';
     return p;
 }
 
-void format_batch_records(std::string& o, const char* contig, size_t clen, int64_t n, const nsnp_site_record_t* rec) {
-    char line[256 + 64];
+char* format_batch_records(char* p, const char* contig, size_t clen, int64_t n, const nsnp_site_record_t* rec) {
     for (int64_t j = 0; j < n; ++j) {
         const nsnp_site_record_t& r = rec[j];
         const int gt = r.gt, zyo = r.zy;
@@ -443,7 +485,7 @@ void format_batch_records(std::string& o, const char* contig, size_t clen, int64
         if (na == 0) {
             if (zyo == 0) {
                 const char a1[2] = {sref, 0};
-                e = put_record_q(line, contig, clen, r.pos1, sref, a1, qual, "RefCall", zy, r.depth, r.af_q);
+                e = put_record_q(p, contig, clen, r.pos1, sref, a1, qual, "RefCall", zy, r.depth, r.af_q);
             } else {
                 static const int tis_hom[4] = {0, 4, 7, 9};
                 static const int tis_het[6] = {1, 2, 3, 5, 6, 8};
@@ -459,7 +501,7 @@ void format_batch_records(std::string& o, const char* contig, size_t clen, int64
                 if (raised) continue;
                 char a1[2] = {0, 0};
                 if (zyo == 1) a1[0] = kGt[max_ti][0]; else a1[0] = kGt[max_ti][0] == sref ? kGt[max_ti][1] : kGt[max_ti][0];
-                e = put_record_q(line, contig, clen, r.pos1, sref, a1, zy_q, "PASS", zy, r.depth, r.af_q);
+                e = put_record_q(p, contig, clen, r.pos1, sref, a1, zy_q, "PASS", zy, r.depth, r.af_q);
             }
         } else {
             char alts[8];
@@ -467,10 +509,11 @@ void format_batch_records(std::string& o, const char* contig, size_t clen, int64
             else if (alt[0] == alt[1]) { alts[0] = alt[0]; alts[1] = 0; }
             else { alts[0] = alt[0]; alts[1] = ','; alts[2] = alt[1]; alts[3] = 0; }
             if (alts[1] == ',' && zyo != 2) zy = "1/2";
-            e = put_record_q(line, contig, clen, r.pos1, sref, alts, zyo == 0 ? gt_q : qual, "PASS", zy, r.depth, r.af_q);
+            e = put_record_q(p, contig, clen, r.pos1, sref, alts, zyo == 0 ? gt_q : qual, "PASS", zy, r.depth, r.af_q);
         }
-        o.append(line, (size_t)(e - line));
+        p = e;
     }
+    return p;
 }
 
 }  // namespace
@@ -484,41 +527,13 @@ extern "C" int64_t nsnp_vcf_format_contig_records(const char* contig, int64_t n,
     const int64_t n_batches = (n + batch_size - 1) / batch_size;
     int nt = n_threads < 1 ? 1 : n_threads;
     if ((int64_t)nt > n_batches) nt = (int)(n_batches > 0 ? n_batches : 1);
-    static std::mutex pool_mu;
-    static std::vector<std::string> pool;
-    std::vector<std::string> parts((size_t)nt);
-    {
-        std::lock_guard<std::mutex> lk(pool_mu);
-        for (int t = 0; t < nt && !pool.empty(); ++t) { parts[(size_t)t] = std::move(pool.back()); pool.pop_back(); }
-    }
-    auto work = [&](int t) {
+    auto need = [&](int t) { return (size_t)((n_batches * (t + 1) / nt - n_batches * t / nt) * batch_size) * (kMaxRecordBytes + clen) + 64; };
+    return run_parts_parallel(nt, need, [&](int t, char* p) {
         const int64_t b0 = n_batches * t / nt, b1 = n_batches * (t + 1) / nt;
-        std::string o = std::move(parts[(size_t)t]);
-        o.clear();
-        o.reserve((size_t)((b1 - b0) * batch_size) * (72 + clen));
         for (int64_t b = b0; b < b1; ++b) {
             const int64_t s = b * batch_size, m = (n - s) < batch_size ? (n - s) : batch_size;
-            format_batch_records(o, contig, clen, m, rec + s);
+            p = format_batch_records(p, contig, clen, m, rec + s);
         }
-        parts[(size_t)t] = std::move(o);
-    };
-    if (nt == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
-        work(0);
-        for (auto& x : th) x.join();
-    }
-    int64_t total = 0;
-    for (auto& s2 : parts) total += (int64_t)s2.size();
-    const bool fits = out && total <= out_capacity;
-    if (fits) {
-        char* p = out;
-        for (auto& s2 : parts) { memcpy(p, s2.data(), s2.size()); p += s2.size(); }
-    }
-    {
-        std::lock_guard<std::mutex> lk(pool_mu);
-        for (auto& s2 : parts) if (pool.size() < 256) pool.push_back(std::move(s2));
-    }
-    return fits ? total : -total;
+        return p;
+    }, out, out_capacity);
 }

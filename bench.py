@@ -200,7 +200,8 @@ def main_ours(args):
     prec = _lib.PREC_FP32 if args.precision == "fp32" else _lib.PREC_F16X3
     model = PileupModelForward(PileupModelWeights(enc, fwd, device=dev), precision=prec)
     runner = RegionRunner(eng, model)
-    runner_e2e = RegionRunner(eng, model, records=True)      # e2e: numeric record logic on the GPU, 32 B/site D2H
+    # fewer than 4 host cores per rank: host waits sleep instead of spinning, the core goes to the VCF text assembly
+    runner_e2e = RegionRunner(eng, model, records=True, blocking_sync=(os.cpu_count() or 1) < 4 * world)      # e2e: numeric record logic on the GPU, 32 B/site D2H
 
     def step_device(timer=None):
         n = 0

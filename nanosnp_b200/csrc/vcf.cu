@@ -433,30 +433,36 @@ inline bool rec_q100(float p, int32_t q_dev, bool tie, long long* q100) {
     return true;
 }
 
+// One record from already-decided fields.  Short strings are copied as fixed-size words and the pointer advanced by
+// their length (alt <= 3, filter <= 7, zy = 3 characters; the caller's buffer has slack), and the integer part of QUAL,
+// which is printed twice (QUAL and GQ), is converted once.
 inline char* put_record_q(char* p, const char* contig, size_t clen, long long pos, char ref, const char* alt, long long q100,
                           const char* filter, const char* zy, long long depth, int32_t af_q)
 {
     memcpy(p, contig, clen); p += clen; *p++ = '\t';
-    p = put_uint(p, (unsigned long long)pos);
-    *p++ = '\t'; *p++ = '.'; *p++ = '\t'; *p++ = ref; *p++ = '\t';
-    for (const char* a = alt; *a; ++a) *p++ = *a;
+    p = put_u32(p, (uint32_t)pos);
+    memcpy(p, "\t.\t", 3); p[3] = ref; p[4] = '\t'; p += 5;
+    { char a4[4] = {0, 0, 0, 0}; int na = 0; while (alt[na]) { a4[na] = alt[na]; ++na; } memcpy(p, a4, 4); p += na; }
     *p++ = '\t';
-    long long qi = 0;
-    p = put_q100(p, q100, &qi);
+    const uint32_t ip = (uint32_t)(q100 / 100); const uint32_t f2 = (uint32_t)(q100 - (long long)ip * 100);
+    char ipd[12]; const int ipn = (int)(put_u32(ipd, ip) - ipd);
+    memcpy(p, ipd, 12); p += ipn;
+    *p++ = '.';
+    *p++ = (char)('0' + f2 / 10);
+    if (f2 % 10) *p++ = (char)('0' + f2 % 10);
     *p++ = '\t';
-    for (const char* a = filter; *a; ++a) *p++ = *a;
+    if (filter[0] == 'P') { memcpy(p, "PASS", 4); p += 4; } else { memcpy(p, "RefCall", 7); p += 7; }
     memcpy(p, "\t.\tGT:GQ:DP:AF\t", 15); p += 15;
-    for (const char* a = zy; *a; ++a) *p++ = *a;
+    memcpy(p, zy, 3); p[3] = ':'; p += 4;
+    memcpy(p, ipd, 12); p += ipn;
     *p++ = ':';
-    p = put_uint(p, (unsigned long long)qi);
-    *p++ = ':';
-    if (depth < 0) { *p++ = '-'; p = put_uint(p, (unsigned long long)(-depth)); } else p = put_uint(p, (unsigned long long)depth);
+    if (depth < 0) { *p++ = '-'; p = put_uint(p, (unsigned long long)(-depth)); } else p = put_u32(p, (uint32_t)depth);
     *p++ = ':';
     if (af_q == NSNP_AF_ONE) { memcpy(p, "1.000000", 8); p += 8; }
     else if (af_q == NSNP_AF_NAN) { memcpy(p, "nan", 3); p += 3; }
     else {
-        const uint32_t u = (uint32_t)af_q, ip = u / 1000000u, f = u - ip * 1000000u;
-        p = put_u32(p, ip);
+        const uint32_t u = (uint32_t)af_q, ipa = u / 1000000u, f = u - ipa * 1000000u;
+        p = put_u32(p, ipa);
         *p++ = '.';
         const uint32_t f01 = f / 10000u, f2345 = f - f01 * 10000u, f23 = f2345 / 100u, f45 = f2345 - f23 * 100u;
         memcpy(p, kDigits2 + 2 * f01, 2); memcpy(p + 2, kDigits2 + 2 * f23, 2); memcpy(p + 4, kDigits2 + 2 * f45, 2); p += 6;

@@ -64,7 +64,12 @@ class StageTimer:
 
 
 class RegionRunner:
-    def __init__(self, engine: PileupEngine, model: PileupModelForward, keep_windows: bool = False, records: bool = False):
+    def __init__(self, engine: PileupEngine, model: PileupModelForward, keep_windows: bool = False, records: bool = False,
+                 blocking_sync: bool = False):
+        """blocking_sync: host waits sleep on a blocking CUDA event instead of spinning in cudaStreamSynchronize.  A
+        spinning wait costs one host core per GPU for the whole run; with few cores per GPU (8 ranks on 16 cores) that
+        core is better spent on VCF text assembly.  Spinning wakes up a little faster, so it stays the default."""
+        self.blocking_sync = blocking_sync
         self.eng = engine
         self.model = model
         self.device = engine.device
@@ -98,7 +103,16 @@ class RegionRunner:
         eng.select(flags, ref, region.start, region.emit_start, region.emit_end, cap, pos=pos, n_dev=n_dev)
         timer.stop()
         self.launches += 3
-        n = int(n_dev.item())                    # the one host sync per region
+        if self.blocking_sync:
+            if not hasattr(self, "_n_host"):
+                self._n_host = torch.empty(1, dtype=torch.int32).pin_memory()
+                self._n_ev = torch.cuda.Event(blocking=True)
+            self._n_host.copy_(n_dev, non_blocking=True)
+            self._n_ev.record()
+            self._n_ev.synchronize()
+            n = int(self._n_host[0])
+        else:
+            n = int(n_dev.item())                # the one host sync per region
         eng.check_status()
         x = self._buf("x", (max(n, 1), _lib.WINDOW, _lib.CHANNELS), torch.int32)[:n]
         refbase = self._buf("refbase", (max(n, 1),), torch.uint8)[:n]
@@ -182,7 +196,7 @@ class RegionRunner:
                     h = ho[name][: out.n]
                     h.copy_(t, non_blocking=True)
                     res[name] = h
-                ev2 = torch.cuda.Event(); ev2.record(down_s); down_done[k] = ev2
+                ev2 = torch.cuda.Event(blocking=self.blocking_sync); ev2.record(down_s); down_done[k] = ev2
             main.wait_event(ev2)                                  # run_device's buffers are reused by region k+1
             results[k] = res
             total += out.n

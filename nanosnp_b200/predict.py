@@ -56,6 +56,43 @@ def predict(model: LSTMNetwork, testing_paths, reference_index_file, batch_size,
             runner = RegionRunner(PileupEngine(device), model._forward(), records=True)
         return runner
 
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    if world > 1:
+        # one process per GPU (torchrun): every rank decodes the reads, computes its LPT share of the regions, rank 0
+        # merges the records in (contig, position) order and writes the file (caller.call_contigs_sharded)
+        from .caller import call_contigs_sharded, records_of_regions
+        if any(f.endswith(".pd") for f in testing_paths):
+            raise NotImplementedError("multi-GPU runs take read inputs (.bam / .reads.npz); .pd files hold ready-made windows")
+        if reference is None:
+            raise ValueError("read inputs need the reference FASTA")
+        fasta = load_fasta(reference)
+        todo = []
+        for testing_file in testing_paths:
+            if testing_file.endswith(".bam"):
+                from .bam import read_bam
+                refs, by_contig = read_bam(testing_file)
+                todo += [(name, by_contig[name]) for name, _ in refs if name in by_contig]
+            else:
+                reads, contig, _ = load_reads_npz(testing_file)
+                todo.append((contig, reads))
+        for contig, _ in todo:
+            if contig not in fasta:
+                raise KeyError(f"contig {contig} is not in the reference")
+        contigs = [(contig, len(fasta[contig])) for contig, _ in todo]
+        model.eval()
+
+        def produce(ci, rgs):
+            return records_of_regions(get_runner(), todo[ci][1], fasta[todo[ci][0]], rgs)
+        import contextlib, io
+        with (open(output_file, "wb") if rank == 0 else contextlib.nullcontext()) as fwriter:
+            if rank == 0:
+                head = io.StringIO(); write_head(reference_index_file, head)
+                fwriter.write(head.getvalue().encode())
+            call_contigs_sharded(contigs, produce, fwriter, batch_size, region_len)
+        return
+
     with open(output_file, "wb") as fwriter:
         import io
         head = io.StringIO(); write_head(reference_index_file, head)
@@ -102,12 +139,20 @@ def main(argv=None):
     parser.add_argument("-batch_size", type=int, default=1000, help="batch size")
     parser.add_argument("--no_cuda", action="store_true", help="refused: the B200 path has no CPU fallback")
     parser.add_argument("--precision", default="f16x3", choices=["fp32", "f16x3"])
+    parser.add_argument("--region_len", type=int, default=12_500_000, help="positions per GPU work unit (read inputs)")
     opt = parser.parse_args(argv)
     if opt.no_cuda:
         raise SystemExit("nanosnp_b200.predict: --no_cuda is not supported (no CPU fallback); use the reference's predict.py on CPU")
     import yaml
     from .utils import AttrDict
     device = torch.device("cuda")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:              # torchrun: one process per GPU, NCCL only gathers the call lists
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        device = torch.device("cuda", local)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=device)
     config = AttrDict(yaml.load(open(opt.config), Loader=yaml.FullLoader))
     pred_model = LSTMNetwork(config.model, precision=opt.precision).to(device)
     if opt.model_path.endswith(".npz"):
@@ -123,7 +168,12 @@ def main(argv=None):
     else:
         testing_paths = sorted(opt.data + "/" + f for f in os.listdir(opt.data) if f.endswith((".pd", ".reads.npz", ".bam")))
     assert os.path.exists(opt.reference + ".fai"), "reference index file does not exist."
-    predict(pred_model, testing_paths, opt.reference + ".fai", opt.batch_size, opt.output, device, reference=opt.reference)
+    predict(pred_model, testing_paths, opt.reference + ".fai", opt.batch_size, opt.output, device, reference=opt.reference,
+            region_len=opt.region_len)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

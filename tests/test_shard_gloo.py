@@ -95,3 +95,68 @@ def test_merge_orders_by_contig_then_position():
     b = {"contig_index": np.array([0, 1], np.int32), "pos": np.array([7, 2], np.int32)}
     m = merge_site_lists([a, None, b])
     assert m["contig_index"].tolist() == [0, 1, 1, 1] and m["pos"].tolist() == [7, 2, 5, 9]
+
+
+# ---- the sharded predict driver (caller.call_contigs_sharded) with a stand-in for the GPU: VCF bytes must not depend on
+#      the number of ranks, although predict.py's record logic depends on the 1000-site batch composition ----
+_SH_CONTIGS = [("ctgA", 260_000), ("ctgB", 91_000), ("ctgC", 150_000)]
+
+
+def _fake_records(ci, L):
+    """Deterministic compact site records of a whole contig (what the GPU would emit), ascending positions."""
+    from nanosnp_b200.predict_io import RECORD_DTYPE
+    rng = np.random.default_rng(77 + ci)
+    pos = np.sort(rng.choice(L, size=L // 23, replace=False)).astype(np.int32)
+    n = len(pos)
+    rec = np.zeros(n, RECORD_DTYPE)
+    rec["gt"] = rng.choice([0, 1, 2, 3, 4, 5, 7, 9, 12], n); rec["zy"] = rng.integers(0, 3, n)
+    rec["ref"] = rng.choice(np.frombuffer(b"ACGT", np.uint8), n); rec["pos1"] = pos + 1
+    rec["q100_gt"] = rng.integers(0, 5000, n); rec["q100_zy"] = rng.integers(0, 5000, n)
+    rec["depth"] = rng.integers(6, 80, n); rec["af_q"] = rng.integers(0, 1000001, n)
+    rec["p_gt"] = 0.5; rec["p_zy"] = 0.5
+    return rec
+
+
+def _fake_produce(ci, rgs):
+    rec = _fake_records(ci, _SH_CONTIGS[ci][1])
+    out = []
+    for r in rgs:
+        p0 = rec["pos1"] - 1
+        out.append(rec[(p0 >= r.emit_start) & (p0 < r.emit_end)])
+    return out
+
+
+def _sharded_worker(rank, world, port, q):
+    import io
+    import torch.distributed as dist
+    from nanosnp_b200.caller import call_contigs_sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sink = io.BytesIO() if rank == 0 else None
+    res = call_contigs_sharded(_SH_CONTIGS, _fake_produce, sink, batch_size=1000, region_len=40_000, n_threads=2)
+    if rank == 0:
+        q.put((sink.getvalue(), res))
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_predict_driver_two_ranks_equals_one():
+    import io
+    from nanosnp_b200.caller import call_contigs_sharded
+    sink = io.BytesIO()
+    res1 = call_contigs_sharded(_SH_CONTIGS, _fake_produce, sink, batch_size=1000, region_len=40_000, n_threads=2)
+    assert res1["world"] == 1 and res1["sites"] == sum(L // 23 for _, L in _SH_CONTIGS)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    text2, res2 = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res2["world"] == 2 and res2["sites"] == res1["sites"]
+    assert text2 == sink.getvalue() and len(text2) > 100_000

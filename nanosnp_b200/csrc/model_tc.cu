@@ -181,9 +181,6 @@ __device__ __forceinline__ uint4 scale_hi(const uint4& hi) {
     auto m = [&](uint32_t x) { __half2 t = *reinterpret_cast<__half2*>(&x); return h2_bits(__hmul2(t, k)); };
     return make_uint4(m(hi.x), m(hi.y), m(hi.z), m(hi.w));
 }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -196,7 +193,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
 template <int LAYER> struct TcCfg;
 template <> struct TcCfg<0> { static constexpr int K = kTcK0, IN = kTcIn0, STEPS = 33; };

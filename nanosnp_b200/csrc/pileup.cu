@@ -24,7 +24,6 @@ constexpr int kCkShift = 5;                 // checkpoint every 32 ops
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kReadList = 1024;             // overlapping reads handled per round
-constexpr int kStageRows = kThreads;        // epilogue sub-block
 
 struct Event {                               // 16 bytes, lives in the per-CTA global slab (L2 resident)
     uint32_t next;                           // previous event anchored at the same position (chain)

@@ -175,7 +175,7 @@ inline char* put_u32(char* p, uint32_t v) {
         if (v < 10) { *p++ = (char)('0' + v); return p; }
         memcpy(p, kDigits2 + 2 * v, 2); return p + 2;
     }
-    char tmp[10]; int n = 10;
+    char tmp[20]; int n = 10;                                      // digits end at tmp[10]; the tail keeps the fixed-size copy in bounds
     while (v >= 100) { const uint32_t q = v / 100; n -= 2; memcpy(tmp + n, kDigits2 + 2 * (v - q * 100), 2); v = q; }
     if (v >= 10) { n -= 2; memcpy(tmp + n, kDigits2 + 2 * v, 2); } else tmp[--n] = (char)('0' + v);
     memcpy(p, tmp + n, 10 - n > 8 ? 10 : 8);                      // over-copy a fixed size: the caller's buffer has slack

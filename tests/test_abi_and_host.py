@@ -213,3 +213,28 @@ def test_synth_generator_properties():
             assert (s % 20_000) < 19_600 and ((e - 1) % 20_000) < 19_600 and (e - s) < 20_000
     assert npass > 0.9 * rd.n_reads * 0.9
     assert set(np.unique(ref)) <= set(b"ACGTacgtNnR")
+
+
+def test_compact_record_formatter_edge_values():
+    """Largest positions / depths, a long contig name, AF = 1 and nan, every digit count of QUAL: the hand-rolled decimal
+    writer must print what Python prints."""
+    from nanosnp_b200.predict_io import AF_NAN, AF_ONE, RECORD_DTYPE, format_compact_records_into, vcf_buffer_bytes
+    name = "chrUn_" + "x" * 150
+    pos = np.array([1, 9, 10, 99, 100, 12345, 999999, 1000000, 99999999, 100000000, 2147483647], np.int32)
+    n = len(pos)
+    rec = np.zeros(n, RECORD_DTYPE)
+    rec["gt"] = 1; rec["zy"] = 2; rec["ref"] = ord("A"); rec["pos1"] = pos            # AC, 0/1, ref A -> ALT C
+    rec["q100_gt"] = [0, 5, 10, 99, 100, 101, 1230, 9999, 10000, 123456, 30100]; rec["q100_zy"] = 500000
+    rec["depth"] = [0, 6, 9, 10, 99, 100, 144, 1000, 65535, 16383, 2000000000]
+    rec["af_q"] = [0, 1, 10, 999999, AF_ONE, AF_NAN, 500000, 123456, 100000, 99, 1000000]
+    rec["p_gt"] = 0.5; rec["p_zy"] = 0.5
+    buf = np.empty(vcf_buffer_bytes(n, name), np.uint8)
+    w = format_compact_records_into(buf, name, rec, 1000, 1)
+    lines = buf[:w].tobytes().decode().splitlines()
+    assert len(lines) == n
+    for i, l in enumerate(lines):
+        q = int(rec["q100_gt"][i])
+        qs = str(float(round(q / 100.0, 2)))
+        af = "1.000000" if rec["af_q"][i] == AF_ONE else "nan" if rec["af_q"][i] == AF_NAN else "%f" % (int(rec["af_q"][i]) / 1e6)
+        exp = "%s\t%d\t.\tA\tC\t%s\tPASS\t.\tGT:GQ:DP:AF\t0/1:%d:%d:%s" % (name, pos[i], qs, int(float(qs)), int(rec["depth"][i]), af)
+        assert l == exp, (i, l, exp)

@@ -358,7 +358,9 @@ def main_ours(args):
                     "peak_source": peak_src,
                     "note": ("fp32 FFMA path (no tensor cores): algorithmic FLOPs over the bf16 sustained peak" if args.precision == "fp32" else
                              "algorithmic (exact-minimal) FLOPs of this layer over the measured sustained bf16 peak; every algorithmic MAC "
-                             "costs three fp16 MMAs (hi/lo split), so frac <= 1/3 by construction")}
+                             "costs three fp16 MMAs (hi/lo split), so frac <= 1/3 by construction.  ncu: tensor pipe 51 % active, MUFU "
+                             "(cell update: 7 ex2/rcp per unit and step) 79 % -- the layer-0 kernel is bound by the MUFU rate, layer 1 by "
+                             "the sustained tensor rate; both run under sw_power_cap (DESIGN.md 4.4)")}
     model_ms = stage_ms["model"] / K
     tfs = FLOP_PER_SITE * n_sites / (model_ms * 1e-3) / 1e12 if model_ms > 0 else 0.0
     stages["model"] = {"bound": "tensor", "achieved": tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfs / tf_peak, "ms_per_step": model_ms,

@@ -50,7 +50,7 @@ def synth_cfg(args, rank, contig_len):
 
 
 def load_weights():
-    from oracle.s2_restate import load_weights_npz      # reading the committed checkpoint fixture, no oracle compute
+    from nanosnp_b200.utils import load_weights_npz     # the committed checkpoint fixture (flat .npz of the shipped .chkpt)
     return load_weights_npz(ROOT / "tests" / "golden" / "ont_pileup_weights.npz")
 
 

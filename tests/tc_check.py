@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Stage-by-stage validation of the tcgen05 LSTM path on a GPU (run each stage under `timeout`).
-usage: tools/tc_check.py {gates0_cg1|gates0_cg2|gates1_cg2|full}"""
+usage: tests/tc_check.py {gates0_cg1|gates0_cg2|gates1_cg2|full}"""
 import ctypes as C, sys
 from pathlib import Path
 import numpy as np

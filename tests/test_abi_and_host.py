@@ -238,3 +238,37 @@ def test_compact_record_formatter_edge_values():
         af = "1.000000" if rec["af_q"][i] == AF_ONE else "nan" if rec["af_q"][i] == AF_NAN else "%f" % (int(rec["af_q"][i]) / 1e6)
         exp = "%s\t%d\t.\tA\tC\t%s\tPASS\t.\tGT:GQ:DP:AF\t0/1:%d:%d:%s" % (name, pos[i], qs, int(float(qs)), int(rec["depth"][i]), af)
         assert l == exp, (i, l, exp)
+
+
+def test_checkpoint_fixture_loader_and_blob_size(golden):
+    """The product-side .npz checkpoint loader returns the two state dicts of utils.py:67-77; packing them fills the blob
+    the library sizes (host-only calls: no GPU needed)."""
+    import ctypes as C
+    from nanosnp_b200 import _lib
+    from nanosnp_b200.utils import load_weights_npz
+    enc, fwd = load_weights_npz(golden / "ont_pileup_weights.npz")
+    assert set(enc) >= {"lstm.weight_ih_l0", "lstm.weight_hh_l1_reverse", "output_proj.weight"} and set(fwd) >= {"dense.weight", "genotype_layer.bias"}
+    assert enc["lstm.weight_ih_l0"].shape == (256, 18) and enc["lstm.weight_ih_l1"].shape == (256, 128) and fwd["genotype_layer.weight"].shape == (21, 256)
+    lib = _lib.load()
+    nbytes = lib.nsnp_model_blob_bytes()
+    assert nbytes > 1_000_000
+    keep = []
+
+    def ptr(a):
+        a = np.ascontiguousarray(a, dtype=np.float32); keep.append(a); return a.ctypes.data
+    w = _lib.ModelWeights()
+    for layer in range(2):
+        for d, sfx in enumerate(("", "_reverse")):
+            i = layer * 2 + d
+            w.w_ih[i] = ptr(enc[f"lstm.weight_ih_l{layer}{sfx}"]); w.w_hh[i] = ptr(enc[f"lstm.weight_hh_l{layer}{sfx}"])
+            w.b_ih[i] = ptr(enc[f"lstm.bias_ih_l{layer}{sfx}"]); w.b_hh[i] = ptr(enc[f"lstm.bias_hh_l{layer}{sfx}"])
+    w.proj_w, w.proj_b = ptr(enc["output_proj.weight"]), ptr(enc["output_proj.bias"])
+    w.dense_w, w.dense_b = ptr(fwd["dense.weight"]), ptr(fwd["dense.bias"])
+    w.gt_w, w.gt_b = ptr(fwd["genotype_layer.weight"]), ptr(fwd["genotype_layer.bias"])
+    w.zy_w, w.zy_b = ptr(fwd["zygosity_layer.weight"]), ptr(fwd["zygosity_layer.bias"])
+    blob = np.zeros(nbytes, np.uint8)
+    assert lib.nsnp_model_pack_weights(C.byref(w), blob.ctypes.data, nbytes) == 0
+    assert lib.nsnp_model_pack_weights(C.byref(w), blob.ctypes.data, nbytes - 1) < 0          # too small: refused, not truncated
+    tail = blob[-2048:].view(np.float32)                                                     # layer-1 bias (scaled), last block of the blob
+    b = (enc["lstm.bias_ih_l1_reverse"] + enc["lstm.bias_hh_l1_reverse"]).astype(np.float32)
+    assert np.isclose(np.abs(tail[256:]).max(), max(np.abs(b[128:192]).max() * 2 * np.log2(np.e), np.abs(np.delete(b, np.s_[128:192])).max() * np.log2(np.e)), rtol=1e-5)

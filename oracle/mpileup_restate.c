@@ -69,8 +69,8 @@ int64_t orc_mpileup_write(const nsnp_reads_t* r, const char* contig_name, int32_
 {
     FILE* out = fopen(path, append ? "a" : "w");
     if (!out) return -1;
-    static char iobuf[1 << 20];
-    setvbuf(out, iobuf, _IOFBF, sizeof iobuf);
+    char* iobuf = (char*)malloc(1 << 20);          /* per call: the tests run pieces of a contig on several threads */
+    if (iobuf) setvbuf(out, iobuf, _IOFBF, 1 << 20);
 
     cursor_t* act = NULL; size_t n_act = 0, cap_act = 0;
     sbuf_t bases = {0, 0, 0};
@@ -165,7 +165,9 @@ int64_t orc_mpileup_write(const nsnp_reads_t* r, const char* contig_name, int32_
         ++p;
     }
     free(act); free(bases.s);
-    if (fclose(out) != 0) return -1;
+    const int cerr = fclose(out);
+    free(iobuf);
+    if (cerr != 0) return -1;
     if (max_depth_seen) *max_depth_seen = deepest;
     return too_deep ? -2 : rows;
 }

@@ -1,0 +1,231 @@
+"""GPU parity AT THE BENCH'S OWN SCALE.
+
+bench.py pushes 12.5 Mb regions of a 100 Mb / 30x contig (~520 k sites each) through multi-wave, multi-chunk code
+paths that the small cases never reach.  These tests build the very same workload (same SynthConfig seeds, same
+device generator, same region plan, same RegionRunner) and check
+
+  s1   counts / flags / candidate positions / windows BIT-EXACT against the oracle chain on a whole 12.5 Mb region
+       (>= 10 Mb prefix of the 100 Mb workload), on the last 2 Mb of the contig, and on 10x / 60x regions;
+  s2   >= 200 k sites (>= 3 host chunks, >= 10 waves, an odd 128-site tile count) through NSNP_PREC_F16X3: ALL sites
+       against the fp32 path, a strided sample of >= 20 k sites spanning every chunk against the float64 oracle
+       network (|dp| < 5e-5, argmax identical), and the compact site records against the array formatter.
+
+The oracle runs on 1 Mb pieces in a thread pool (ctypes releases the GIL): ~3 s of CPU per Mb and piece.
+"""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+F16X3_ATOL = 5e-5
+PIECE = 1_000_000
+
+
+def bench_cfg(coverage=30.0, contig_mb=100.0):
+    from nanosnp_b200.synth import SynthConfig
+    return SynthConfig(contig_len=int(contig_mb * 1e6), coverage=coverage, contig="ctg1", seed_ref=1000, seed_var=2000, seed_reads=3000)
+
+
+@pytest.fixture(scope="module")
+def rig(golden_weights):
+    import torch
+    from nanosnp_b200 import _lib
+    from nanosnp_b200.pipeline import PileupEngine, PileupModelForward, PileupModelWeights
+    from nanosnp_b200.runner import RegionRunner
+    assert torch.cuda.is_available()
+    eng = PileupEngine("cuda:0")
+    w = PileupModelWeights(*golden_weights, device="cuda:0")
+    tc = PileupModelForward(w, _lib.PREC_F16X3)
+    f32 = PileupModelForward(w, _lib.PREC_FP32)
+    return {"eng": eng, "tc": tc, "f32": f32, "runner": RegionRunner(eng, tc, keep_windows=True)}
+
+
+def region_reads(reads, pos_host, rg, max_span):
+    """The slice bench.py hands to the runner for region rg (device tensors)."""
+    import torch
+    from nanosnp_b200.reads import PackedReads
+    from nanosnp_b200.shard import read_range_for_region
+    n_total = reads.n_reads
+    total_bases = int(reads.seq2.numel()) * 4
+    lo, hi = read_range_for_region(pos_host, max_span, rg)
+    c0, c1 = int(reads.cigar_off[lo].item()), int(reads.cigar_off[hi].item())
+    b0 = int(reads.seq_off[lo].item()) if lo < n_total else total_bases
+    b1 = int(reads.seq_off[hi].item()) if hi < n_total else total_bases - 64
+    pad = torch.zeros(16, dtype=torch.uint8, device=reads.pos.device)
+    return PackedReads(reads.pos[lo:hi].clone(), reads.flag[lo:hi].clone(), reads.mapq[lo:hi].clone(),
+                       (reads.cigar_off[lo:hi + 1] - c0), reads.cigar[c0:c1].clone(), (reads.seq_off[lo:hi] - b0),
+                       torch.cat([reads.seq2[b0 // 4:(b1 + 3) // 4], pad]),
+                       None if reads.nmask is None else torch.cat([reads.nmask[b0 // 8:(b1 + 7) // 8], pad]))
+
+
+def oracle_piece(orc, rd_host, ref_host, s, e, max_span, tmpdir, tag):
+    """Oracle chain on [s, e) of the contig: the reads that can overlap it, shifted to a private origin."""
+    from nanosnp_b200.reads import slice_reads
+    lo = int(np.searchsorted(rd_host.pos, s - max_span - 64, side="left"))
+    hi = int(np.searchsorted(rd_host.pos, e + 64, side="left"))
+    sub = slice_reads(rd_host, lo, hi)
+    origin = max(0, min(s - 64, int(sub.pos[0]) if hi > lo else s))
+    end = min(len(ref_host), e + max_span + 64)
+    sub.pos = (sub.pos - origin).astype(np.int32)
+    mp = os.path.join(str(tmpdir), f"{tag}.mpileup")
+    orc.mpileup_text(sub, "ctg1", mp)
+    res = orc.s1_restate(mp, "ctg1", ref_host[origin:end])
+    os.unlink(mp)
+    a, b = s - origin, e - origin
+    sel = (res.positions - 1 >= a + 16) & (res.positions - 1 < b - 16)       # windows complete inside the piece
+    return {"s": s, "e": e, "counts": res.counts[a:b].copy(), "flags": res.flags[a:b].copy(),
+            "pos0": res.positions[sel] - 1 + origin, "windows": res.windows[sel]}
+
+
+def check_span(orc, runner, out, rg, rd_host, ref_host, lo, hi, max_span, tmpdir):
+    """Compares the GPU region output on contig span [lo, hi) with the oracle, piece by piece."""
+    rlen = rg.length
+    counts = runner._bufs["counts"][: rlen * 18].view(rlen, 18)
+    flags = runner._bufs["flags"][:rlen]
+    pos_gpu = out.pos0.cpu().numpy()
+    pieces = [(s, min(hi, s + PIECE + 32)) for s in range(lo, hi - 32, PIECE)]       # 32-bp overlap: every window lies inside one piece
+    with ThreadPoolExecutor(min(len(pieces), os.cpu_count() or 1)) as pool:
+        futs = [pool.submit(oracle_piece, orc, rd_host, ref_host, s, e, max_span, tmpdir, f"p{s}") for s, e in pieces]
+        n_sites = 0
+        for f in futs:
+            r = f.result()
+            s, e = r["s"], r["e"]
+            c = counts[s - rg.start:e - rg.start].cpu().numpy()
+            fl = flags[s - rg.start:e - rg.start].cpu().numpy()
+            cov = (r["flags"] & 1).astype(bool)
+            assert np.array_equal(fl & 1, r["flags"] & 1), f"covered differs in [{s},{e})"
+            bad = np.nonzero((c[cov] != r["counts"][cov]).any(1))[0]
+            assert bad.size == 0, f"counts differ at 0-based {s + np.nonzero(cov)[0][bad[0]]} ({bad.size} rows)"
+            assert (c[~cov] == 0).all()
+            assert np.array_equal(fl, r["flags"]), f"gate differs in [{s},{e})"
+            # candidate list and windows whose 33 rows lie inside the piece and inside the region's emit span
+            a, b = max(s + 16, rg.emit_start), min(e - 16, rg.emit_end)
+            g = (pos_gpu >= a) & (pos_gpu < b)
+            o = (r["pos0"] >= a) & (r["pos0"] < b)
+            assert np.array_equal(pos_gpu[g], r["pos0"][o]), f"candidate sites differ in [{a},{b})"
+            idx = np.nonzero(g)[0]
+            if idx.size:
+                xw = out.x[int(idx[0]):int(idx[-1]) + 1].cpu().numpy()
+                assert np.array_equal(xw, r["windows"][o]), f"windows differ in [{a},{b})"
+            n_sites += int(g.sum())
+    return n_sites
+
+
+@pytest.fixture(scope="module")
+def workload(rig):
+    """bench.py's default workload: 100 Mb contig at 30x, generated on the GPU, 8 regions of 12.5 Mb."""
+    import torch
+    from nanosnp_b200.shard import plan_regions
+    from nanosnp_b200.synth import generate_device
+    cfg = bench_cfg()
+    ref, reads = generate_device(cfg, rig["eng"].device)
+    regions = plan_regions([(cfg.contig, cfg.contig_len)], 12_500_000)
+    pos_host = reads.pos.cpu().numpy()
+    max_span = int(cfg.len_max * 1.3) + 1000
+    return {"cfg": cfg, "ref": ref, "reads": reads, "regions": regions, "pos_host": pos_host, "max_span": max_span}
+
+
+def test_bench_region_s1_bit_exact_and_model_at_scale(rig, workload, orc, tmp_path):
+    """Region 0 of the bench workload (12.5 Mb, ~520 k sites): s1 bit-exact on the whole region, then the region's own
+    windows through the multi-chunk / multi-wave tensor-core model."""
+    import torch
+    from nanosnp_b200.reads import PackedReads
+    w = workload
+    rg = w["regions"][0]
+    rd = region_reads(w["reads"], w["pos_host"], rg, w["max_span"])
+    out = rig["runner"].run_device(rd, w["ref"], rg)
+    torch.cuda.synchronize()
+    rd_host = rd.to_numpy()
+    ref_host = w["ref"][: rg.end + w["max_span"] + 128].cpu().numpy()
+    n_checked = check_span(orc, rig["runner"], out, rg, rd_host, ref_host, rg.start, rg.end, w["max_span"], tmp_path)
+    assert n_checked >= 0.99 * out.n and out.n > 400_000, (n_checked, out.n)
+
+    # ---- s2 at scale: >= 3 host chunks of 75 776 sites, an odd number of 128-site tiles in the last chunk ----
+    n = out.n if ((out.n + 127) // 128) % 2 == 1 else out.n - 128
+    assert n > 3 * 75_776
+    x = out.x[:n]
+    gt = out.gt[:n].clone(); zy = out.zy[:n].clone()           # what the runner computed inside run_device (F16X3)
+    g2, z2 = rig["tc"](x)                                        # the same sites again, different n: chunk / tile edges move
+    torch.cuda.synchronize()
+    if n == out.n:
+        assert torch.equal(g2, gt) and torch.equal(z2, zy)
+    g32, z32 = rig["f32"](x)
+    torch.cuda.synchronize()
+    d = max(float((g2 - g32).abs().max()), float((z2 - z32).abs().max()))
+    assert d < F16X3_ATOL, d
+    assert torch.equal(g2.argmax(1), g32.argmax(1)) or float((g2.max(1).values - g32.max(1).values).abs().max()) < F16X3_ATOL
+    # float64 oracle network on a strided sample that hits every chunk and wave, plus both ends of every chunk
+    from oracle.s2_restate import PileupModelOracle
+    idx = np.unique(np.concatenate([np.arange(0, n, max(1, n // 21_000)),
+                                    *[np.arange(max(0, k - 130), min(n, k + 130)) for k in range(0, n + 75_776, 75_776)],
+                                    np.arange(n - 300, n)]))
+    idx = idx[(idx >= 0) & (idx < n)]
+    assert idx.size >= 20_000
+    torch.set_num_threads(os.cpu_count() or 1)
+    from conftest import GOLDEN
+    from oracle.s2_restate import load_weights_npz
+    m = PileupModelOracle(*load_weights_npz(GOLDEN / "ont_pileup_weights.npz"))
+    ti = torch.from_numpy(idx).to(x.device)
+    xs = x[ti].cpu().numpy()
+    g0, z0 = m.predict64(xs)
+    gs, zs = g2[ti].cpu(), z2[ti].cpu()
+    err = max(float((gs - g0).abs().max()), float((zs - z0).abs().max()))
+    assert err < F16X3_ATOL, err
+    assert torch.equal(gs.argmax(1), g0.argmax(1)) and torch.equal(zs.argmax(1), z0.argmax(1))
+
+    # ---- compact site records (GPU numeric record logic) vs the array formatter, whole region ----
+    import ctypes as C
+    from nanosnp_b200 import _lib
+    lib = _lib.load()
+    rec = rig["eng"].site_records(g2, z2, x, out.refbase[:n], out.pos0[:n], n).cpu().numpy()
+    cov8 = np.ascontiguousarray(x[:, 16, [0, 1, 2, 3, 9, 10, 11, 12]].to(torch.float32).cpu().numpy())
+    pos1 = np.ascontiguousarray(out.pos0[:n].cpu().numpy() + 1).astype(np.int32)
+    refb = np.ascontiguousarray(out.refbase[:n].cpu().numpy())
+    gh, zh = np.ascontiguousarray(g2.cpu().numpy()), np.ascontiguousarray(z2.cpu().numpy())
+    cap = n * 96 + 4096
+    b1 = C.create_string_buffer(cap); b2 = C.create_string_buffer(cap)
+    n1 = lib.nsnp_vcf_format_contig_records(b"ctg1", n, rec.ctypes.data, 1000, 8, C.addressof(b1), cap)
+    n2 = lib.nsnp_vcf_format_contig(b"ctg1", n, pos1.ctypes.data, refb.ctypes.data, gh.ctypes.data, zh.ctypes.data, cov8.ctypes.data,
+                                    1000, 8, C.addressof(b2), cap)
+    assert n1 > 0 and n1 == n2 and b1.raw[:n1] == b2.raw[:n2]
+
+
+def test_bench_last_region_tail_bit_exact(rig, workload, orc, tmp_path):
+    """Last region of the contig (positions near 1e8, reads truncated at the contig end): last 2 Mb bit-exact."""
+    import torch
+    w = workload
+    rg = w["regions"][-1]
+    rd = region_reads(w["reads"], w["pos_host"], rg, w["max_span"])
+    out = rig["runner"].run_device(rd, w["ref"], rg)
+    torch.cuda.synchronize()
+    rd_host = rd.to_numpy()
+    ref_host = w["ref"].cpu().numpy()
+    n = check_span(orc, rig["runner"], out, rg, rd_host, ref_host, rg.end - 2_000_000, rg.end, w["max_span"], tmp_path)
+    assert n > 50_000
+
+
+@pytest.mark.parametrize("coverage", [10.0, 60.0])
+def test_coverage_sweep_regions_bit_exact(rig, orc, tmp_path, coverage):
+    """BASELINE configs[2]: the 10x and 60x workloads (100 Mb contig), one 3 Mb region each, bit-exact."""
+    import torch
+    from nanosnp_b200.shard import Region
+    from nanosnp_b200.synth import generate_device
+    cfg = bench_cfg(coverage)
+    ref, reads = generate_device(cfg, rig["eng"].device)
+    pos_host = reads.pos.cpu().numpy()
+    max_span = int(cfg.len_max * 1.3) + 1000
+    rg = Region(cfg.contig, 0, cfg.contig_len, 40_000_000, 43_000_000)
+    rd = region_reads(reads, pos_host, rg, max_span)
+    del reads
+    out = rig["runner"].run_device(rd, ref, rg)
+    torch.cuda.synchronize()
+    rd_host = rd.to_numpy()
+    ref_host = ref[: rg.end + max_span + 128].cpu().numpy()
+    n = check_span(orc, rig["runner"], out, rg, rd_host, ref_host, rg.start, rg.end, max_span, tmp_path)
+    assert n >= 0.99 * out.n and out.n > (300_000 if coverage < 20 else 5_000), (n, out.n)
+    # the model on this coverage regime: tensor-core path vs fp32 path on every site
+    g32, z32 = rig["f32"](out.x)
+    assert float((out.gt - g32).abs().max()) < F16X3_ATOL and float((out.zy - z32).abs().max()) < F16X3_ATOL

@@ -15,14 +15,13 @@
 //       - indel events are chained per position (exact grouping for I1/D1 by length / sequence identity)
 //       - epilogue: prefix sums -> 18 channels + AF gate (IEEE double, tensor_maker.cpp:195-228)
 //         -> rows staged in shared memory -> coalesced 16-byte stores of the int32 [T][18] block.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace nsnp {
 namespace {
 
 constexpr int kCkShift = 5;                 // checkpoint every 32 ops
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kReadList = 1024;             // overlapping reads handled per round
 
 struct Event {                               // 16 bytes, lives in the per-CTA global slab (L2 resident)
@@ -140,8 +139,8 @@ struct TileSmem {
     uint32_t refx[T / 16 + 2];    // 01 at non-ACGT reference positions (forces a "mismatch" event)
     uint32_t skipcov[T / 32];     // positions inside a reference skip (N op)
     int32_t  thr_snp[kGateTab], thr_indel[kGateTab];   // smallest count c with (double)c / den >= min_af
-    int32_t  rlist[kReadList];
-    int32_t  warp_tot[kWarps][4];
+    int32_t  rlist[T];                                  // >= kReadList; reused as per-warp walk lists (T / warps each)
+    int32_t  warp_tot[T / 128][4];
     int32_t  n_rlist, next_task, n_events, tile, ref_has_x;
 };
 
@@ -320,6 +319,183 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Variant 2 of the per-read walk: TWO consecutive CIGAR ops per lane (64 ops per warp iteration, one packed scan for
+// both), 32-bit read-relative sequence coordinates, and per-lane comparison loops with rolling word registers instead of
+// the flattened word list (its scan + binary search + four broadcasts cost more than the lanes it saved: ONT aligned runs
+// average 14 bases, i.e. one or two 16-base words).  Runs longer than kSelfWords words -- HiFi-like reads -- finish
+// warp-cooperatively, one word per lane.  In strictly alternating CIGARs (M indel M indel ...) each of the two slots is
+// type-uniform across the warp, so the aligned-run code and the indel code run without divergence.
+constexpr uint32_t kRefOps = 0x18Du;        // M D N = X consume the reference   (bits 0 2 3 7 8)
+constexpr uint32_t kQryOps = 0x193u;        // M I S = X consume the query       (bits 0 1 4 7 8)
+constexpr uint32_t kAlnOps = 0x181u;        // M = X are aligned runs
+constexpr int kSelfWords = 8;
+
+template <int T>
+__device__ __forceinline__ void count_mismatches(TileSmem<T>& sm, uint32_t* __restrict__ bs, const uint32_t* __restrict__ nmr,
+                                                 uint32_t sw, uint32_t rw, uint32_t xw, int pw, int qb, int m, bool ref_has_x, uint32_t sinc)
+{
+    uint32_t x = sw ^ rw;
+    uint32_t mm = (x | (x >> 1)) & 0x55555555u;
+    if (ref_has_x) mm |= xw;
+    if (m < 16) mm &= (1u << (2 * m)) - 1u;
+    if (nmr) {
+        uint32_t nb = bits16_g(nmr, qb);
+        if (m < 16) nb &= (1u << m) - 1u;
+        if (nb) {
+            mm &= ~spread16(nb);
+            while (nb) { const int q = __ffs(nb) - 1; nb &= nb - 1; atomicAdd(&sm.nn[pw + q], sinc); }
+        }
+    }
+    while (mm) {
+        const int j2 = __ffs(mm) - 1; mm &= mm - 1;
+        const uint32_t bcode = (sw >> j2) & 3u;
+        atomicAdd(bs + (bcode >> 1) * T + pw + (j2 >> 1), 1u << (16 * (bcode & 1u)));
+    }
+}
+
+template <int T>
+__device__ __forceinline__ void process_read2(TileSmem<T>& sm, const nsnp_reads_t& rd, const Workspace& ws, Event* slab,
+                                              int r, const ReadMeta& meta, int ts, int te, bool deep, int32_t* status)
+{
+    const int lane = lane_id();
+    const int rpos = meta.rpos;
+    const int strand = meta.strand;
+    const uint32_t sinc = 1u << (16 * strand);
+    const int n_ops = (int)(meta.c1 - meta.c0);
+    const int nchunks = (n_ops + 31) >> kCkShift;
+    const bool ref_has_x = sm.ref_has_x != 0;                       // tile-uniform
+    const int32_t* ckr = ws.ck_ref + ((meta.c0 >> kCkShift) + r);
+    const int32_t* ckq = ws.ck_q + ((meta.c0 >> kCkShift) + r);
+    if (lane == 0) atomicAdd(&sm.ms[max(rpos - ts, 0)], sinc);
+    if (lane == 1 && meta.rend < te) atomicSub(&sm.ms[meta.rend - ts], sinc);
+    int lo = 0, hi = nchunks;
+    if (rpos < ts) {
+        while (hi - lo > 1) {
+            const int step = (hi - lo + 31) >> 5;
+            const int c = lo + lane * step;
+            const bool le = c < hi && __ldg(ckr + c) <= ts;
+            const int cnt = __popc(__ballot_sync(0xffffffffu, le));
+            lo = lo + (cnt - 1) * step;
+            hi = min(hi, lo + step);
+        }
+    }
+    const int chunk = lo;
+    int R = __ldg(ckr + chunk), Q = __ldg(ckq + chunk);
+    // read-relative sequence addressing: word pointer of the read's first base + a small offset, everything else 32-bit
+    const int sb_lo = (int)(meta.sbase & 15);
+    const uint32_t* seqr = reinterpret_cast<const uint32_t*>(rd.seq2) + (meta.sbase >> 4);
+    const int nb_lo = (int)(meta.sbase & 31);
+    const uint32_t* nmr = rd.nmask ? reinterpret_cast<const uint32_t*>(rd.nmask) + (meta.sbase >> 5) : nullptr;
+    uint32_t* bs = &sm.base[strand * 2][0];
+
+    const uint32_t* cgp = rd.cigar + meta.c0 + ((int64_t)chunk << kCkShift);
+    int left = n_ops - (chunk << kCkShift);
+    uint32_t nx0 = 2 * lane < left ? __ldg(cgp + 2 * lane) : 6u;
+    uint32_t nx1 = 2 * lane + 1 < left ? __ldg(cgp + 2 * lane + 1) : 6u;
+    for (; left > 0 && R <= te; left -= 64, cgp += 64) {
+        const uint32_t cgv[2] = {nx0, nx1};
+        nx0 = (64 + 2 * lane < left) ? __ldg(cgp + 64 + 2 * lane) : 6u;
+        nx1 = (65 + 2 * lane < left) ? __ldg(cgp + 65 + 2 * lane) : 6u;
+        const int op0 = cgv[0] & 15, len0 = cgv[0] >> 4, op1 = cgv[1] & 15, len1 = cgv[1] >> 4;
+        const int rl0 = ((kRefOps >> op0) & 1u) ? len0 : 0, ql0 = ((kQryOps >> op0) & 1u) ? len0 : 0;
+        const int rl1 = ((kRefOps >> op1) & 1u) ? len1 : 0, ql1 = ((kQryOps >> op1) & 1u) ? len1 : 0;
+        const int rl = rl0 + rl1, ql = ql0 + ql1;
+        int ri, qi;
+        if (!__any_sync(0xffffffffu, (len0 | len1) >= 1024)) {          // 64 lengths below 1024: both prefix sums fit 16 bits
+            const int pk = warp_incl_scan(rl | (ql << 16));
+            ri = pk & 0xFFFF; qi = (int)((uint32_t)pk >> 16);
+        } else {
+            ri = warp_incl_scan(rl); qi = warp_incl_scan(ql);
+        }
+        const int rsv[2] = {R + ri - rl, R + ri - rl + rl0};
+        const int qsv[2] = {Q + qi - ql, Q + qi - ql + ql0};
+        R += __shfl_sync(0xffffffffu, ri, 31);
+        Q += __shfl_sync(0xffffffffu, qi, 31);
+
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int op = cgv[s] & 15, len = cgv[s] >> 4, rs = rsv[s], qs = qsv[s];
+            const int a = max(rs, ts), b = min(rs + len, te);                 // clipped reference span
+            // ---- aligned run: bit-parallel mismatch detection, this lane's own run, 16 bases per step ----
+            const int n = (((kAlnOps >> op) & 1u) && a < b) ? (b - a) : 0;
+            const int pa = a - ts;
+            const int qa = qs + (a - rs) + sb_lo;                            // offset (bases) from the read's first seq word
+            if (n > 0) {
+                const uint32_t* sp = seqr + (qa >> 4);
+                const uint32_t* rp = sm.ref2 + (pa >> 4);
+                const uint32_t* xp = sm.refx + (pa >> 4);
+                const int ssh = (qa & 15) * 2, rsh = (pa & 15) * 2;
+                uint32_t s_lo = __ldg(sp), r_lo = rp[0], x_lo = ref_has_x ? xp[0] : 0u;
+                const int ne = min(n, 16 * kSelfWords);
+                for (int o = 0; o < ne; o += 16) {
+                    ++sp; ++rp; ++xp;
+                    const uint32_t s_hi = __ldg(sp), r_hi = rp[0], x_hi = ref_has_x ? xp[0] : 0u;
+                    count_mismatches<T>(sm, bs, nmr, __funnelshift_r(s_lo, s_hi, ssh), __funnelshift_r(r_lo, r_hi, rsh),
+                                        __funnelshift_r(x_lo, x_hi, rsh), pa + o, qa + o - sb_lo + nb_lo, n - o, ref_has_x, sinc);
+                    s_lo = s_hi; r_lo = r_hi; x_lo = x_hi;
+                }
+            }
+            // long runs: the remaining words one per lane
+            for (uint32_t lm = __ballot_sync(0xffffffffu, n > 16 * kSelfWords); lm; lm &= lm - 1) {
+                const int j = __ffs(lm) - 1;
+                const int pa_j = __shfl_sync(0xffffffffu, pa, j), n_j = __shfl_sync(0xffffffffu, n, j), qa_j = __shfl_sync(0xffffffffu, qa, j);
+                for (int o = 16 * (kSelfWords + lane); o < n_j; o += 16 * 32) {
+                    const int pw = pa_j + o, qw = qa_j + o;
+                    count_mismatches<T>(sm, bs, nmr, bases16_g(seqr, qw), bases16(sm.ref2, pw), ref_has_x ? bases16(sm.refx, pw) : 0u,
+                                        pw, qw - sb_lo + nb_lo, n_j - o, ref_has_x, sinc);
+                }
+            }
+            // ---- indel event anchored at the preceding reference position (appendix A.8 iii/iv) ----
+            const bool isins = op == 1, isdel = op == 2;
+            if (isins || isdel) {
+                const int anchor = rs - 1;
+                const bool ev = len <= NSNP_MAX_INDEL && rs > rpos && anchor >= ts && anchor < te;
+                const bool fastdel = ev && isdel && len <= 2 && !deep;
+                if (isdel && a < b && !fastdel) {
+                    atomicAdd(&sm.ds[a - ts], sinc);
+                    if (b < te) atomicSub(&sm.ds[b - ts], sinc);
+                }
+                if (ev) {
+                    const int cls = (isdel ? 2 : 0) + strand;
+                    const int ap = anchor - ts;
+                    atomicAdd(&sm.cnt4[ap], 1u << (8 * cls));
+                    bool chain = true;
+                    if (fastdel) {
+                        atomicAdd(&sm.dfast[ap], 1u << (8 * (2 * strand + len - 1)));
+                        chain = false;
+                    } else if (isins && len == 1 && !deep) {                  // 1-base insertion: fast counter unless the base is N
+                        const int qi1 = qs + sb_lo;
+                        const uint32_t iword = __ldg(seqr + (qi1 >> 4));
+                        const int qn = qs + nb_lo;
+                        const uint32_t inbit = nmr ? (__ldg(nmr + (qn >> 5)) >> (qn & 31)) & 1u : 0u;
+                        if (!inbit) {
+                            atomicAdd(&sm.ifast[strand][ap], 1u << (8 * ((iword >> (2 * (qi1 & 15))) & 3u)));
+                            chain = false;
+                        }
+                    }
+                    if (chain) {
+                        const int e = atomicAdd(&sm.n_events, 1);
+                        if (e < ws.slab_cap) {
+                            Event evr;
+                            evr.next = atomicExch(&sm.head[ap], (uint32_t)e);
+                            evr.info = (uint32_t)len | ((uint32_t)cls << 8);
+                            evr.seq = (uint64_t)(meta.sbase + qs);
+                            slab[e] = evr;
+                        } else {
+                            dev_fail(status, DEV_E_INDEL_SLAB, sm.tile);
+                        }
+                    }
+                }
+            } else if (op == 3 && a < b) {                                    // reference skip: covered, nothing counted
+                atomicSub(&sm.ms[a - ts], sinc);
+                if (b < te) atomicAdd(&sm.ms[b - ts], sinc);
+                for (int p = a; p < b; ++p) atomicOr(&sm.skipcov[(p - ts) >> 5], 1u << ((p - ts) & 31));
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ bool same_insert(const uint32_t* seqw, const uint32_t* nmw, uint64_t g1, uint64_t g2, int len) {
     for (int o = 0; o < len; o += 16) {
         const int m = min(16, len - o);
@@ -347,12 +523,14 @@ __device__ __forceinline__ int min_count_for_af(double af, int den) {
     return c;
 }
 
-template <int T>
-__global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t rd, nsnp_params_t prm, const uint8_t* __restrict__ ref,
+template <int T, int V>
+__global__ void __launch_bounds__(T / 4, 4096 / T) pileup_tile_kernel(nsnp_reads_t rd, nsnp_params_t prm, const uint8_t* __restrict__ ref,
                                                                int64_t region_start, int64_t region_len, int n_tiles,
                                                                Workspace ws, int32_t* __restrict__ counts,
                                                                uint8_t* __restrict__ flags, int32_t* status)
 {
+    constexpr int kThreads = T / 4, kWarps = kThreads / 32;       // one thread packs 4 reference bases
+    static_assert(T >= kReadList, "read list");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem<T>& sm = *reinterpret_cast<TileSmem<T>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -390,7 +568,6 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
             for (int i = tid; i < T / 32; i += kThreads) sm.skipcov[i] = 0u;
             if (tid == 0) { sm.n_events = 0; }
             // 4 reference bases per thread -> one byte of the 2-bit tile and of the non-ACGT mask
-            static_assert(T == 4 * kThreads, "one thread packs 4 reference bases");
             uint32_t r2 = 0, rx = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -437,7 +614,8 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
                 ReadMeta mnext = {};
                 int rn = 0;
                 if (tn < nr) { rn = sm.rlist[tn]; mnext = load_meta(rd, ws, rn); }
-                process_read<T>(sm, rd, ws, slab, r, meta, ts, te, deep, status);
+                if (V == 2) process_read2<T>(sm, rd, ws, slab, r, meta, ts, te, deep, status);
+                else process_read<T>(sm, rd, ws, slab, r, meta, ts, te, deep, status);
                 t = tn; r = rn; meta = mnext;
             }
         }
@@ -638,7 +816,12 @@ __global__ void __launch_bounds__(kThreads, 4) pileup_tile_kernel(nsnp_reads_t r
     }
 }
 
-int tile_shift_for(int64_t region_len) { (void)region_len; return 10; }     // T = 1024
+int tile_shift_for(int64_t region_len) {                                    // T = 1024 (default) or 2048 (NSNP_PILEUP_TILE=2048)
+    (void)region_len;
+    static int shift = 0;
+    if (!shift) { const char* e = getenv("NSNP_PILEUP_TILE"); shift = (e && atoi(e) == 2048) ? 11 : 10; }
+    return shift;
+}
 
 }  // namespace
 }  // namespace nsnp
@@ -710,21 +893,27 @@ int nsnp_pileup_counts(const nsnp_reads_t* reads, const uint8_t* ref_dev, int64_
         if (int e = cuda_status("read_scan_kernel")) return e;
     }
     {
-        constexpr int T = 1024;
-        const size_t smem = sizeof(TileSmem<T>);
+        static int variant = -1;
+        if (variant < 0) { const char* e = getenv("NSNP_PILEUP_VARIANT"); variant = (e && atoi(e) == 1) ? 1 : 2; }
+        using kern_t = void (*)(nsnp_reads_t, nsnp_params_t, const uint8_t*, int64_t, int64_t, int, Workspace, int32_t*, uint8_t*, int32_t*);
+        const int T = 1 << tile_shift;
+        const kern_t kern = T == 2048 ? (variant == 1 ? (kern_t)pileup_tile_kernel<2048, 1> : (kern_t)pileup_tile_kernel<2048, 2>)
+                                      : (variant == 1 ? (kern_t)pileup_tile_kernel<1024, 1> : (kern_t)pileup_tile_kernel<1024, 2>);
+        const size_t smem = T == 2048 ? sizeof(TileSmem<2048>) : sizeof(TileSmem<1024>);
+        const int threads = T / 4;
         static bool attr_done = false;
         if (!attr_done) {
-            if (cudaFuncSetAttribute(pileup_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return cuda_status("cudaFuncSetAttribute(pileup_tile_kernel)");
             attr_done = true;
         }
         int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pileup_tile_kernel<T>, kThreads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
         if (occ < 1) occ = 1; if (occ > 4) occ = 4;
         int grid = kNumSMs * occ; if (grid > n_tiles) grid = n_tiles; if (grid > kMaxCtas) grid = kMaxCtas;
         ProfScope prof(NSNP_PROF_PILEUP_TILE, stream);
-        pileup_tile_kernel<T><<<grid, kThreads, smem, stream>>>(*reads, *params, ref_dev, region_start, region_len, n_tiles, w,
-                                                              counts_dev, flags_dev, status_dev);
+        kern<<<grid, threads, smem, stream>>>(*reads, *params, ref_dev, region_start, region_len, n_tiles, w,
+                                              counts_dev, flags_dev, status_dev);
         if (int e = cuda_status("pileup_tile_kernel")) return e;
     }
     return NSNP_OK;

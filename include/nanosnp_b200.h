@@ -33,7 +33,7 @@ extern "C" {
 #define NSNP_E_WORKSPACE     -3   /* caller workspace too small */
 #define NSNP_E_OVERFLOW      -4   /* a device-side capacity was exceeded (> 16383 reads over one 1024-bp tile, indel slab full) */
 #define NSNP_E_NO_DEVICE     -5   /* no CUDA device: there is deliberately no CPU fallback */
-#define NSNP_E_UNSUPPORTED   -6
+#define NSNP_E_UNSUPPORTED   -6   /* e.g. a CIGAR with P pads or unmerged adjacent I I / D D ops (nsnp_bam_fill merges them) */
 
 /* channel order of the count tensor: reference dna_sv_tensor/src/common/tensor.hpp:6-26 */
 enum {
@@ -55,6 +55,9 @@ enum {
  * Aligned reads of ONE contig region as flat packed arrays (what a host BAM decoder produces;
  * replaces the BAM -> `samtools mpileup` text hand-off of make_predict_data.sh:117,151).
  * Reads must be sorted by pos (coordinate-sorted BAM order); ties keep file order.
+ * CIGARs must be canonical: adjacent ops of the same indel type merged ("1D2D" -> "3D", as htslib reports them), no P ops;
+ * anything else is refused with NSNP_E_UNSUPPORTED.  Leading / trailing / adjacent I-D ops, N skips, S/H clips and =/X are
+ * handled as `samtools mpileup` reports them (hand-worked cases in tests/golden/cigar_cases.txt).
  */
 typedef struct nsnp_reads {
     int64_t         n_reads;
@@ -78,7 +81,7 @@ typedef struct nsnp_params {
     int32_t  min_coverage;   /* 6 */
     int32_t  min_mapq;       /* 20   (--min-MQ) */
     uint32_t excl_flags;     /* 2316 (--excl-flags) */
-    int32_t  reserved;
+    int32_t  max_depth;      /* 144  (--max-depth): htslib's streaming depth cap; <= 0 disables it */
 } nsnp_params_t;
 
 void        nsnp_default_params(nsnp_params_t* p);
@@ -166,13 +169,13 @@ int nsnp_debug_lstm_tc_gates(const void* blob_dev, const int32_t* x_i32_dev, int
  * nsnp_profile_read synchronises, adds the elapsed times per kernel slot into ms_out[NSNP_PROF_SLOTS] and
  * launches_out[NSNP_PROF_SLOTS], and clears the pending events.  Slots: */
 enum { NSNP_PROF_READ_SCAN = 0, NSNP_PROF_PILEUP_TILE, NSNP_PROF_SELECT, NSNP_PROF_GATHER, NSNP_PROF_LSTM0, NSNP_PROF_LSTM1,
-       NSNP_PROF_TAIL, NSNP_PROF_RECORDS, NSNP_PROF_SLOTS };
+       NSNP_PROF_TAIL, NSNP_PROF_RECORDS, NSNP_PROF_VCF_TEXT, NSNP_PROF_SLOTS };
 void nsnp_profile_enable(int on);
 int  nsnp_profile_read(double* ms_out, int64_t* launches_out);
 
 /* ---- status / utilities ----------------------------------------------------------------------- */
-/* copies status_dev[0..3] to the host (synchronises the stream) and maps it to an NSNP_E_* code */
-int nsnp_check_status(const int32_t* status_dev, void* stream);
+/* copies status_dev[0..3] to the host (synchronises the stream), maps it to an NSNP_E_* code and, after an error, clears it */
+int nsnp_check_status(int32_t* status_dev, void* stream);
 
 /* ---- s2 host side: VCF record formatting ----------------------------------------------------------
  * Replaces the per-site loop of PileupModel/predict.py:66-194 for ONE batch (<= batch_size sites of
@@ -204,6 +207,30 @@ int nsnp_site_records(const float* gt_prob_dev, const float* zy_prob_dev, const 
 int64_t nsnp_vcf_format_contig_records(const char* contig, int64_t n, const nsnp_site_record_t* rec, int64_t batch_size,
                                        int n_threads, char* out, int64_t out_capacity);
 
+/* ---- s2: VCF record TEXT on the GPU (csrc/vcf_dev.cu) ---------------------------------------------------------------
+ * Replaces the text half of predict.py:66-194 for records [first_index, first_index + n) of one contig file; the bytes are
+ * those of nsnp_vcf_format_contig_records.  `gt_output[ti]` (predict.py:106,119) reads the genotype argmax of the first ten
+ * sites of the record's batch_size-site batch:
+ *   heads_dev == NULL: first_index must be a multiple of batch_size and the batch heads are taken from rec_dev itself
+ *   heads_dev != NULL: u8 [n_batches][10] table of the contig (255 = the batch has no such site), filled by
+ *                      nsnp_vcf_batch_heads by whoever owns those sites (multi-GPU: completed with one MIN all-reduce)
+ * text_len_dev [1] int64 receives the text length (> text_capacity: nothing usable was written).  Records whose QUAL the
+ * device flagged as a 2-decimal rounding tie are listed in the workspace (nsnp_vcf_text_ties); after copying text and list to
+ * the host, nsnp_vcf_text_patch_ties re-evaluates them with libc -- the result is byte-identical to the host formatter. */
+size_t  nsnp_vcf_text_workspace_bytes(int64_t n);
+int64_t nsnp_vcf_text_capacity(int64_t n, const char* contig);     /* upper bound of the text of n records */
+int nsnp_vcf_text_records(const char* contig, const nsnp_site_record_t* rec_dev, int64_t n, const int32_t* n_dev, int64_t first_index,
+                          int64_t batch_size, const uint8_t* heads_dev, char* text_dev, int64_t text_capacity, int64_t* text_len_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+int nsnp_vcf_text_ties(const void* workspace_dev, int64_t n, const void** count_dev, const void** entries_dev, int32_t* capacity);
+int nsnp_vcf_batch_heads(const nsnp_site_record_t* rec_dev, int64_t n, const int32_t* n_dev, int64_t first_index, int64_t batch_size,
+                         uint8_t* heads_dev, void* stream);
+int64_t nsnp_vcf_text_patch_ties(const char* contig, char* text_host, int64_t text_len, int64_t text_capacity, const void* ties_host,
+                                 int32_t n_ties);
+/* host twin of the device formatter (same source compiled for the host; tests, fall-backs of the callers) */
+int64_t nsnp_vcf_format_records_at(const char* contig, const nsnp_site_record_t* rec, int64_t n, int64_t first_index, int64_t batch_size,
+                                   const uint8_t* heads, char* out, int64_t out_capacity);
+
 /* Whole contig file: consecutive batches of batch_size sites (predict.py:43 DataLoader(batch_size, shuffle=False)),
  * formatted on n_threads host threads with hand-rolled number formatting (same bytes as nsnp_vcf_format_batch). */
 int64_t nsnp_vcf_format_contig(const char* contig, int64_t n, const int32_t* pos1, const uint8_t* refbase,
@@ -218,6 +245,30 @@ int64_t nsnp_bam_count(const uint8_t* data, int64_t n_bytes, int64_t first_recor
 int64_t nsnp_bam_fill(const uint8_t* data, int64_t n_bytes, int64_t first_record_offset, int32_t ref_id,
                       int32_t* pos, uint16_t* flag, uint8_t* mapq, int64_t* cigar_off, uint32_t* cigar, int64_t* seq_off,
                       uint8_t* seq2, uint8_t* nmask);
+
+/* ---- host: streaming BAM reader (csrc/bam_stream.cu) -------------------------------------------------------------
+ * BGZF blocks are inflated on n_threads host threads, <= 32 MB at a time, while the previous batch is parsed; records
+ * are decoded contig by contig (file order) or, with a .bai next to the file, region by region through the linear
+ * index, so a rank of a multi-GPU run only inflates the byte range of its own regions.  CIGAR runs of one op type are
+ * merged ("1D2D" -> "3D"), '=' / IUPAC bases count as N.  The reader owns the arrays of the contig / region it decoded
+ * last; nsnp_bam_take copies them into caller buffers sized from the returned counts (seq2: n_bases_padded / 4 + 16
+ * bytes, nmask: n_bases_padded / 8 + 16, cigar_off: n_reads + 1).  Errors: NULL / negative return + nsnp_last_error(). */
+typedef struct nsnp_bam_reader nsnp_bam_reader_t;
+nsnp_bam_reader_t* nsnp_bam_open(const char* path, int n_threads);
+void        nsnp_bam_close(nsnp_bam_reader_t* r);
+int32_t     nsnp_bam_n_ref(const nsnp_bam_reader_t* r);
+const char* nsnp_bam_ref_name(const nsnp_bam_reader_t* r, int32_t i);
+int64_t     nsnp_bam_ref_len(const nsnp_bam_reader_t* r, int32_t i);
+int         nsnp_bam_has_index(const nsnp_bam_reader_t* r);
+int64_t     nsnp_bam_inflated_bytes(const nsnp_bam_reader_t* r);
+/* next reference (file order) that has reads and whose want[ref_id] != 0 (want may be NULL = all): returns its id, -1 at
+ * the end of the file, -2 on a malformed file */
+int32_t nsnp_bam_next_contig(nsnp_bam_reader_t* r, const int8_t* want, int64_t* n_reads, int64_t* n_cigar, int64_t* n_bases_padded);
+/* reads of ref_id that start before `end` and overlap [beg, end) (needs the .bai); returns ref_id or -2 */
+int32_t nsnp_bam_fetch(nsnp_bam_reader_t* r, int32_t ref_id, int64_t beg, int64_t end, int64_t* n_reads, int64_t* n_cigar,
+                       int64_t* n_bases_padded);
+int nsnp_bam_take(nsnp_bam_reader_t* r, int32_t* pos, uint16_t* flag, uint8_t* mapq, int64_t* cigar_off, uint32_t* cigar,
+                  int64_t* seq_off, uint8_t* seq2, uint8_t* nmask, int32_t* any_n);
 
 /* ---- synthetic inputs (bench / tests) --------------------------------------- */
 typedef struct nsnp_synth_cfg {

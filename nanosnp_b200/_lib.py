@@ -18,7 +18,7 @@ CHANNELS, FLANK, WINDOW = 18, 16, 33
 GT_CLASSES, ZY_CLASSES = 21, 3
 F_COVERED, F_GATE = 1, 2
 PREC_FP32, PREC_F16X3 = 0, 1
-PROF_SLOTS = ("read_scan_kernel", "pileup_tile_kernel", "select_kernels", "gather_kernel", "lstm_layer0", "lstm_layer1", "tail_kernel", "site_record_kernel")
+PROF_SLOTS = ("read_scan_kernel", "pileup_tile_kernel", "select_kernels", "gather_kernel", "lstm_layer0", "lstm_layer1", "tail_kernel", "site_record_kernel", "vcf_text_kernels")
 
 
 class NsnpError(RuntimeError):
@@ -41,7 +41,7 @@ class Params(C.Structure):
     _fields_ = [
         ("snp_min_af", C.c_double), ("indel_min_af", C.c_double),
         ("min_coverage", C.c_int32), ("min_mapq", C.c_int32),
-        ("excl_flags", C.c_uint32), ("reserved", C.c_int32),
+        ("excl_flags", C.c_uint32), ("max_depth", C.c_int32),
     ]
 
 
@@ -94,8 +94,25 @@ SYMBOLS = {
     "nsnp_site_records": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "nsnp_vcf_format_contig_records": (_I64, [C.c_char_p, _I64, _P, _I64, C.c_int, _P, _I64]),
     "nsnp_vcf_format_contig": (_I64, [C.c_char_p, _I64, _P, _P, _P, _P, _P, _I64, C.c_int, _P, _I64]),
+    "nsnp_vcf_text_workspace_bytes": (_SZ, [_I64]),
+    "nsnp_vcf_text_capacity": (_I64, [_I64, C.c_char_p]),
+    "nsnp_vcf_text_records": (C.c_int, [C.c_char_p, _P, _I64, _P, _I64, _I64, _P, _P, _I64, _P, _P, _SZ, _P]),
+    "nsnp_vcf_text_ties": (C.c_int, [_P, _I64, _P, _P, _P]),
+    "nsnp_vcf_batch_heads": (C.c_int, [_P, _I64, _P, _I64, _I64, _P, _P]),
+    "nsnp_vcf_text_patch_ties": (_I64, [C.c_char_p, _P, _I64, _I64, _P, _I32]),
+    "nsnp_vcf_format_records_at": (_I64, [C.c_char_p, _P, _I64, _I64, _I64, _P, _P, _I64]),
     "nsnp_bam_count": (_I64, [_P, _I64, _I64, _I32, _P, _P]),
     "nsnp_bam_fill": (_I64, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nsnp_bam_open": (_P, [C.c_char_p, C.c_int]),
+    "nsnp_bam_close": (None, [_P]),
+    "nsnp_bam_n_ref": (_I32, [_P]),
+    "nsnp_bam_ref_name": (C.c_char_p, [_P, _I32]),
+    "nsnp_bam_ref_len": (_I64, [_P, _I32]),
+    "nsnp_bam_has_index": (C.c_int, [_P]),
+    "nsnp_bam_inflated_bytes": (_I64, [_P]),
+    "nsnp_bam_next_contig": (_I32, [_P, _P, _P, _P, _P]),
+    "nsnp_bam_fetch": (_I32, [_P, _I32, _I64, _I64, _P, _P, _P]),
+    "nsnp_bam_take": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nsnp_synth_ref_host": (C.c_int, [C.POINTER(SynthCfg), _P]),
     "nsnp_synth_count_host": (C.c_int, [C.POINTER(SynthCfg), _P, _P, _P, _P, _P]),
     "nsnp_synth_fill_host": (C.c_int, [C.POINTER(SynthCfg), _P, _P, _P, _P, _P]),

@@ -81,7 +81,7 @@ void nsnp_default_params(nsnp_params_t* p) {
     p->min_coverage = 6;       // make_predict_data.sh:124
     p->min_mapq = 20;          // make_predict_data.sh:117 --min-MQ 20
     p->excl_flags = 2316;      // make_predict_data.sh:117 --excl-flags 2316
-    p->reserved = 0;
+    p->max_depth = 144;        // make_predict_data.sh:117 --max-depth 144
 }
 
 int nsnp_device_count(void) {
@@ -90,18 +90,23 @@ int nsnp_device_count(void) {
     return n;
 }
 
-int nsnp_check_status(const int32_t* status_dev, void* stream) {
+int nsnp_check_status(int32_t* status_dev, void* stream) {
     if (!status_dev) return nsnp::set_error(NSNP_E_INVALID, "nsnp_check_status: null status");
     int32_t h[4] = {0, 0, 0, 0};
     cudaError_t e = cudaMemcpyAsync(h, status_dev, sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
     if (e != cudaSuccess) return nsnp::set_error(NSNP_E_CUDA, "nsnp_check_status: %s", cudaGetErrorString(e));
+    if (h[nsnp::ST_ERR] != nsnp::DEV_OK) {                      // report once: the next call starts from a clean status word
+        cudaMemsetAsync(status_dev, 0, sizeof h, (cudaStream_t)stream);
+        cudaStreamSynchronize((cudaStream_t)stream);
+    }
     switch (h[nsnp::ST_ERR]) {
         case nsnp::DEV_OK: return NSNP_OK;
-        case nsnp::DEV_E_DEPTH: return nsnp::set_error(NSNP_E_OVERFLOW, "column depth exceeds 65535 near position %d", h[1]);
+        case nsnp::DEV_E_DEPTH: return nsnp::set_error(NSNP_E_OVERFLOW, "more than 16383 reads overlap the 1024-bp tile at position %d", h[1]);
         case nsnp::DEV_E_INDEL_SLAB: return nsnp::set_error(NSNP_E_OVERFLOW, "indel event slab overflow in tile %d", h[1]);
         case nsnp::DEV_E_SEQ_SPAN: return nsnp::set_error(NSNP_E_OVERFLOW, "reads over one tile span >= 2^32 bases (tile %d)", h[1]);
         case nsnp::DEV_E_CAND_CAP: return nsnp::set_error(NSNP_E_OVERFLOW, "candidate buffer too small: %d sites", h[1]);
+        case nsnp::DEV_E_CIGAR: return nsnp::set_error(NSNP_E_UNSUPPORTED, "read %d: CIGAR is not canonical (P op, or adjacent I I / D D not merged)", h[1]);
         case nsnp::DEV_E_UNSORTED: return nsnp::set_error(NSNP_E_INVALID, "reads are not sorted by position (read %d)", h[1]);
         default: return nsnp::set_error(NSNP_E_CUDA, "unknown device status %d", h[0]);
     }

@@ -62,6 +62,17 @@ inline void real_cigar(const Rec& r, const uint8_t** cig, uint32_t* n) {
     }
 }
 
+// copies a record's CIGAR, merging adjacent ops of the same type; returns the number of ops written
+inline uint32_t copy_cigar_merged(uint32_t* dst, const uint8_t* src, uint32_t n) {
+    uint32_t w = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t c = rd_u32(src + 4ull * k);
+        if (w && (dst[w - 1] & 15u) == (c & 15u)) dst[w - 1] += c & ~15u;
+        else dst[w++] = c;
+    }
+    return w;
+}
+
 }  // namespace
 
 extern "C" {
@@ -109,7 +120,7 @@ int64_t nsnp_bam_fill(const uint8_t* data, int64_t n_bytes, int64_t first_record
         if (r.ref_id == ref_id) {
             const uint8_t* cg; uint32_t nc; real_cigar(r, &cg, &nc);
             pos[i] = r.pos; flag[i] = (uint16_t)r.flag; mapq[i] = (uint8_t)r.mapq;
-            memcpy(cigar + oi, cg, 4ull * nc); oi += nc;
+            oi += copy_cigar_merged(cigar + oi, cg, nc);         // "1D2D" -> "3D": one indel, as htslib reports it
             cigar_off[i + 1] = oi;
             seq_off[i] = bi;
             for (uint32_t k = 0; k < r.l_seq; ++k) {

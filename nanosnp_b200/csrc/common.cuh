@@ -22,7 +22,7 @@ constexpr int kNumSMs = 148;                     // B200: 2 dies x 74 SMs
 
 // device-side status words (status_dev[4])
 enum { ST_ERR = 0, ST_DETAIL = 1, ST_AUX0 = 2, ST_AUX1 = 3 };
-enum { DEV_OK = 0, DEV_E_DEPTH = 1, DEV_E_INDEL_SLAB = 2, DEV_E_SEQ_SPAN = 3, DEV_E_CAND_CAP = 4, DEV_E_UNSORTED = 5 };
+enum { DEV_OK = 0, DEV_E_DEPTH = 1, DEV_E_INDEL_SLAB = 2, DEV_E_SEQ_SPAN = 3, DEV_E_CAND_CAP = 4, DEV_E_UNSORTED = 5, DEV_E_CIGAR = 6 };
 
 __device__ __forceinline__ void dev_fail(int32_t* status, int code, int detail) {
     if (atomicCAS(&status[ST_ERR], 0, code) == 0) status[ST_DETAIL] = detail;

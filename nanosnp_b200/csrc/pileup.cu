@@ -36,7 +36,9 @@ struct Workspace {
     int32_t* ck_q;        // [n_slots]
     int32_t* tile_lo;     // [n_tiles]
     int32_t* tile_hi;     // [n_tiles]
-    int32_t* counters;    // [16]  0: tile ticket
+    int32_t* counters;    // [16]  0: tile ticket, 1: depth-cap fast check (max buffered reads), 2: reads dropped by the cap
+    int32_t* cap_end;     // [n_reads] exclusive end of every passing read (INT32_MIN: filtered)
+    int32_t* cap_heap;    // [n_reads] min-heap of the slow path
     Event*   slabs;       // [n_ctas][slab_cap]
     int64_t  slab_cap;
 };
@@ -74,7 +76,7 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {     // bit j -> bit 2
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) read_scan_kernel(nsnp_reads_t rd, nsnp_params_t prm, int64_t region_start,
-                                                        int64_t region_end, int tile_shift, Workspace ws)
+                                                        int64_t region_end, int tile_shift, Workspace ws, int32_t* status)
 {
     const int lane = lane_id();
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -83,10 +85,11 @@ __global__ void __launch_bounds__(256) read_scan_kernel(nsnp_reads_t rd, nsnp_pa
         const int32_t pos = rd.pos[r];
         const uint32_t flag = rd.flag[r];
         const bool pass = !(flag & 4u) && !(flag & prm.excl_flags) && (int)rd.mapq[r] >= prm.min_mapq;   // appendix B.1
-        if (!pass) { if (lane == 0) ws.rend[r] = INT32_MIN; continue; }          // never overlaps any tile
+        if (!pass) { if (lane == 0) { ws.rend[r] = INT32_MIN; ws.cap_end[r] = INT32_MIN; } continue; }          // never overlaps any tile
         const int64_t c0 = rd.cigar_off[r], c1 = rd.cigar_off[r + 1];
         const int64_t slot0 = (c0 >> kCkShift) + r;
         int32_t R = pos, Q = 0;
+        uint32_t bad = 0u, carry_i = 0u, carry_d = 0u;                            // carry: the previous chunk's last op was I / D
         // kUnroll chunks of 32 ops per iteration: the loads are independent, so a long read (thousands of ops: the
         // critical path of this kernel) keeps kUnroll loads in flight instead of one
         constexpr int kUnroll = 8;
@@ -99,12 +102,28 @@ __global__ void __launch_bounds__(256) read_scan_kernel(nsnp_reads_t rd, nsnp_pa
             for (int j = 0; j < kUnroll; ++j) {
                 const int op = cg[j] & 15, len = cg[j] >> 4;
                 const int rl = op_ref(op) ? len : 0, ql = op_query(op) ? len : 0;
+                // canonical CIGARs only: adjacent I I / D D must arrive merged (htslib reports them as ONE indel) and
+                // pads inside insertions are not modelled -- refuse loudly instead of counting something else.
+                // Three votes and a few warp-uniform bit operations per 32 ops (pad lanes carry op 6 but lie beyond c1).
+                {
+                    const int64_t nv = c1 - (k + 32 * j);
+                    const uint32_t vm = nv >= 32 ? 0xffffffffu : nv > 0 ? (1u << nv) - 1u : 0u;
+                    const uint32_t mi = __ballot_sync(0xffffffffu, op == 1), md = __ballot_sync(0xffffffffu, op == 2);
+                    const uint32_t mp = __ballot_sync(0xffffffffu, op == 6) & vm;
+                    bad |= mp | (mi & ((mi << 1) | carry_i)) | (md & ((md << 1) | carry_d));
+                    carry_i = mi >> 31; carry_d = md >> 31;
+                }
                 if (lane == j && k + 32 * j < c1) { ws.ck_ref[s + j] = R; ws.ck_q[s + j] = Q; }
                 R += __reduce_add_sync(0xffffffffu, rl);
                 Q += __reduce_add_sync(0xffffffffu, ql);
             }
         }
-        if (lane == 0) ws.rend[r] = R;
+        if (lane == 0) {
+            ws.rend[r] = R;
+            ws.cap_end[r] = max(R, pos + 1);                                      // bam_endpos: at least pos + 1
+            atomicMax(&ws.counters[4], max(R, pos + 1) - pos);                    // longest reference span of the call
+        }
+        if (bad && lane == 0) dev_fail(status, DEV_E_CIGAR, (int)r);
         // tiles this read overlaps
         const int64_t a = pos > region_start ? pos : region_start;
         const int64_t b = R < region_end ? R : region_end;
@@ -113,6 +132,86 @@ __global__ void __launch_bounds__(256) read_scan_kernel(nsnp_reads_t rd, nsnp_pa
             for (int t = t0 + lane; t <= t1; t += 32) { atomicMin(&ws.tile_lo[t], (int)r); atomicMax(&ws.tile_hi[t], (int)r + 1); }
         }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// htslib streaming depth cap (`samtools mpileup --max-depth 144`, make_predict_data.sh:117).
+// The pileup engine refuses a read at push time iff it is already assembling the read's own start column (an earlier
+// passing read starts there too) and its node pool holds more than max_depth nodes: every pushed read whose exclusive
+// end is >= that column, plus two bookkeeping nodes.  The rule is sequential in file order, so it runs in three steps:
+//   read_scan_kernel   exclusive end of every passing read, longest reference span
+//   cap_kernel         upper bound of the pool size seen by any read if nothing were dropped (sampled, then exact): when
+//                      it never exceeds the cap (every 10-60x data set) nothing is dropped; otherwise one thread replays
+//                      the push order with a min-heap of ends and marks dropped reads as filtered.
+// Exact for the read set of one call; across region shards it is exact as long as no read of the lead-in window before
+// the region is itself affected by the cap (SURVEY 8e caveat).
+// counters: [1] sampled bound, [3] exact bound, [4] longest reference span (read_scan), [2] reads dropped.
+// alive(b) = earlier passing reads with end >= pos[b]; alive(b) <= alive(b - 1) + 1, so counting every kCapStride-th read
+// bounds all of them: the full per-read count only runs when that bound is not conclusive.
+constexpr int kCapStride = 16;
+// one warp per read: the lanes share the backward scan
+__device__ __forceinline__ int cap_alive(const nsnp_reads_t& rd, const Workspace& ws, int64_t b, int limit) {
+    const int lane = lane_id();
+    const int32_t P = rd.pos[b];
+    const int32_t far = P - ws.counters[4];                     // no read starting before this can reach P
+    int cnt = 0;
+    for (int64_t r0 = b - 1; r0 >= 0 && cnt < limit; r0 -= 32) {
+        const int64_t r = r0 - lane;
+        const bool in = r >= 0 && rd.pos[r] >= far;
+        cnt += __popc(__ballot_sync(0xffffffffu, in && ws.cap_end[r] >= P));
+        if (!__all_sync(0xffffffffu, in)) break;
+    }
+    return cnt;
+}
+// One launch: every warp counts one sampled read; the last block to finish looks at the bound and -- only when it is not
+// conclusive -- counts every read exactly and, if the pool can really fill, replays the push order on one thread.
+__global__ void __launch_bounds__(256) cap_kernel(nsnp_reads_t rd, Workspace ws, int max_depth)
+{
+    __shared__ int last;
+    const int lane = lane_id();
+    {
+        const int64_t b = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kCapStride;
+        if (b < rd.n_reads) {
+            const int cnt = cap_alive(rd, ws, b, max_depth);                  // the sampled bound holds for any read index
+            if (cnt > 0 && lane == 0) atomicMax(&ws.counters[1], cnt);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&ws.counters[5], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (*(volatile int32_t*)&ws.counters[1] + kCapStride + 2 <= max_depth) return;     // the pool never fills: nothing is dropped
+    for (int64_t b = threadIdx.x >> 5; b < rd.n_reads; b += blockDim.x >> 5) {          // exact bound (rare: > ~125x deep data)
+        if (ws.cap_end[b] == INT32_MIN) continue;
+        const int cnt = cap_alive(rd, ws, b, max_depth);
+        if (cnt > 0 && lane == 0) atomicMax(&ws.counters[3], cnt);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x != 0 || *(volatile int32_t*)&ws.counters[3] + 2 <= max_depth) return;
+    int32_t* h = ws.cap_heap;
+    int hn = 0, dropped = 0;
+    int64_t last_pos = -1;
+    for (int64_t i = 0; i < rd.n_reads; ++i) {
+        const int32_t e = ws.cap_end[i];
+        if (e == INT32_MIN) continue;
+        const int32_t P = rd.pos[i];
+        while (hn && h[0] < P) {                                // columns < P are done: their reads left the pool
+            const int32_t v = h[--hn];
+            int k = 0;
+            for (;;) { int c = 2 * k + 1; if (c >= hn) break; if (c + 1 < hn && h[c + 1] < h[c]) ++c; if (h[c] >= v) break; h[k] = h[c]; k = c; }
+            if (hn) h[k] = v;
+        }
+        if (last_pos == P && hn + 2 > max_depth) { ws.rend[i] = INT32_MIN; ++dropped; continue; }
+        int k = hn++;
+        while (k > 0 && h[(k - 1) >> 1] > e) { h[k] = h[(k - 1) >> 1]; k = (k - 1) >> 1; }
+        h[k] = e;
+        last_pos = P;
+    }
+    ws.counters[2] = dropped;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -844,6 +943,8 @@ static void carve(void* base, int64_t n_reads, int64_t n_cigar, int64_t region_l
     w->tile_lo = (int32_t*)take((size_t)(n_tiles + 1) * 4);
     w->tile_hi = (int32_t*)take((size_t)(n_tiles + 1) * 4);
     w->counters = (int32_t*)take(64);
+    w->cap_end = (int32_t*)take((size_t)(n_reads + 1) * 4);
+    w->cap_heap = (int32_t*)take((size_t)(n_reads + 1) * 4);
     w->slabs = (Event*)take((size_t)kMaxCtas * (size_t)cap * sizeof(Event));
     w->slab_cap = cap;
     *total = off;
@@ -889,8 +990,12 @@ int nsnp_pileup_counts(const nsnp_reads_t* reads, const uint8_t* ref_dev, int64_
         const int64_t warps = reads->n_reads;
         int blocks = (int)((warps + 7) / 8); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
         ProfScope prof(NSNP_PROF_READ_SCAN, stream);
-        read_scan_kernel<<<blocks, 256, 0, stream>>>(*reads, *params, region_start, region_start + region_len, tile_shift, w);
+        read_scan_kernel<<<blocks, 256, 0, stream>>>(*reads, *params, region_start, region_start + region_len, tile_shift, w, status_dev);
         if (int e = cuda_status("read_scan_kernel")) return e;
+        if (params->max_depth > 0) {
+            cap_kernel<<<(int)((reads->n_reads / kCapStride + 8) / 8), 256, 0, stream>>>(*reads, w, params->max_depth);
+            if (int e = cuda_status("depth cap kernels")) return e;
+        }
     }
     {
         static int variant = -1;

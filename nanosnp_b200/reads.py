@@ -127,6 +127,27 @@ def slice_reads(reads: "PackedReads", lo: int, hi: int) -> "PackedReads":
                        reads.cigar_off[lo:hi + 1] - c0, np.ascontiguousarray(reads.cigar[c0:c1]), reads.seq_off[lo:hi] - b0, seq2, nmask)
 
 
+def canonicalize_cigars(reads: "PackedReads") -> "PackedReads":
+    """Merges adjacent CIGAR ops of the same type ("1D2D" -> "3D", "1I2I" -> "3I"): `samtools mpileup` reports such runs as
+    ONE indel, and the GPU path refuses unmerged runs (include/nanosnp_b200.h).  nsnp_bam_fill already does this while
+    decoding; this is the numpy equivalent for hand-made inputs.  Host arrays only."""
+    assert isinstance(reads.pos, np.ndarray)
+    cg = reads.cigar.astype(np.uint32)
+    if cg.shape[0] == 0:
+        return reads
+    ops = cg & 15
+    first = np.ones(cg.shape[0], bool)
+    first[1:] = ops[1:] != ops[:-1]
+    first[reads.cigar_off[:-1][reads.cigar_off[:-1] < cg.shape[0]]] = True          # a read's first op always starts a group
+    if first.all():
+        return reads
+    starts = np.nonzero(first)[0]
+    lens = np.add.reduceat((cg >> 4).astype(np.int64), starts)
+    merged = ((lens << 4) | ops[starts]).astype(np.uint32)
+    new_off = np.concatenate([[0], np.cumsum(first)])[reads.cigar_off].astype(np.int64)
+    return PackedReads(reads.pos, reads.flag, reads.mapq, new_off, merged, reads.seq_off, reads.seq2, reads.nmask)
+
+
 def max_reference_span(reads: "PackedReads") -> int:
     """Longest reference span of any read (host arrays): bounds how far back a region must look for overlapping reads."""
     ops = reads.cigar & 15

@@ -6,8 +6,19 @@
  * samtools/htslib 1.15.1 (Dockerfile:7-8) is a third-party dependency that is NOT vendored under
  * /root/reference and is not installed here, so this file restates its documented output format
  * (SURVEY.md appendix B.1-B.3).  PARITY UNPINNED at this boundary: there is no samtools to compare
- * with and the reference has no tests.  Inputs are kept inside the CIGAR subset of appendix B.4
- * ([S] M {(I|D) M}* [S], M may be =/X) where the format is fully determined by the SAM spec.
+ * with and the reference has no tests.  Inside the CIGAR subset of appendix B.4 ([S] M {(I|D) M}* [S],
+ * M may be =/X) the format is fully determined by the SAM spec.  Outside it this file follows htslib's
+ * published pileup logic as the survey restates it (B.2) and as hand-worked in tests/golden/cigar_cases.txt:
+ *   - at the LAST reference column of an op (M/=/X, D or N) the next op is inspected: an insertion run
+ *     (consecutive I, with P pads printed as '*' and counted in the length) is reported as +<n><seq>,
+ *     followed by -<n>N.. when a deletion comes right after the insertion ("1M2I1D" -> T+2AA-1N);
+ *     a deletion run (consecutive D merged) is reported as -<n>N.. unless the current op is itself D;
+ *   - leading I/S/H/P before the first reference-consuming op are never reported;
+ *   - the --max-depth streaming cap (B.3): a read is not pushed iff the pileup engine is already
+ *     assembling the read's own start column (an earlier passing read starts there too) and its node
+ *     pool holds more than max_depth nodes; the pool holds every pushed read whose end (exclusive) is
+ *     >= that column plus two bookkeeping nodes (list tail + dummy head), i.e. the read is dropped iff
+ *     buffered_reads + 2 > max_depth (orc_depth_cap below; max_depth <= 0 disables it).
  *
  * Input: the flat packed read arrays of include/nanosnp_b200.h (host pointers).
  * Output: mpileup text rows `chr \t pos1 \t N \t depth \t bases \t quals`.
@@ -60,9 +71,46 @@ static int seek_first_ref_op(const nsnp_reads_t* r, cursor_t* c) {
 }
 
 /*
+ * htslib streaming depth cap (appendix B.3).  dropped[i] = 1 for every read the pileup engine refuses at push time.
+ * Reads failing the B.1 filter are never pushed and never counted.  Returns the number of dropped reads.
+ */
+int64_t orc_depth_cap(const nsnp_reads_t* r, int32_t min_mapq, uint32_t excl_flags, int32_t max_depth, uint8_t* dropped)
+{
+    const int64_t n = r->n_reads;
+    memset(dropped, 0, (size_t)n);
+    if (max_depth <= 0) return 0;
+    int64_t* ends = NULL; size_t n_alive = 0, cap = 0;      /* exclusive ends of the pushed reads still in the pool */
+    int64_t n_drop = 0, last_pos = -1;                         /* last_pos: start of the most recent PUSHED read */
+    for (int64_t i = 0; i < n; ++i) {
+        if ((r->flag[i] & 4) || (r->flag[i] & excl_flags) || r->mapq[i] < min_mapq) continue;
+        const int64_t P = r->pos[i];
+        int64_t reflen = 0;
+        for (int64_t k = r->cigar_off[i]; k < r->cigar_off[i + 1]; ++k)
+            if (consumes_ref(op_of(r->cigar[k]))) reflen += len_of(r->cigar[k]);
+        const int64_t end = P + (reflen > 0 ? reflen : 1);     /* bam_endpos */
+        if (last_pos == P) {
+            /* the engine has processed every column < P: nodes with end <= P-1 are back in the pool */
+            size_t w = 0;
+            for (size_t k = 0; k < n_alive; ++k) if (ends[k] >= P) ends[w++] = ends[k];
+            n_alive = w;
+            if ((int64_t)n_alive + 2 > max_depth) { dropped[i] = 1; ++n_drop; continue; }
+        }
+        if (n_alive == cap) { cap = cap ? cap * 2 : 256; ends = (int64_t*)realloc(ends, cap * sizeof *ends); }
+        ends[n_alive++] = end;
+        last_pos = P;
+        if (n_alive > 4096) {                                  /* keep the list short when no same-start read prunes it */
+            size_t w = 0;
+            for (size_t k = 0; k < n_alive; ++k) if (ends[k] >= P) ends[w++] = ends[k];
+            n_alive = w;
+        }
+    }
+    free(ends);
+    return n_drop;
+}
+
+/*
  * Writes rows for every covered position of the contig to `path` (append = 0 truncates).
- * Returns the number of rows, or -1 on I/O error, or -2 if a column held more than max_depth reads
- * (the htslib depth cap of B.3 is a streaming rule that we do not model: callers must keep depth below it).
+ * Returns the number of rows, or -1 on I/O error.  max_depth > 0 applies the streaming cap above.
  */
 int64_t orc_mpileup_write(const nsnp_reads_t* r, const char* contig_name, int32_t min_mapq, uint32_t excl_flags,
                           int32_t max_depth, const char* path, int append, int32_t* max_depth_seen)
@@ -76,24 +124,21 @@ int64_t orc_mpileup_write(const nsnp_reads_t* r, const char* contig_name, int32_
     sbuf_t bases = {0, 0, 0};
     int64_t next = 0, rows = 0;
     int64_t p = 0;
-    int deepest = 0, too_deep = 0;
+    int deepest = 0;
     const int64_t n = r->n_reads;
+    uint8_t* capped = (uint8_t*)malloc((size_t)(n > 0 ? n : 1));
+    orc_depth_cap(r, min_mapq, excl_flags, max_depth, capped);
+#define DROPPED(i) ((r->flag[i] & 4) || (r->flag[i] & excl_flags) || r->mapq[i] < min_mapq || capped[i])
 
     while (next < n || n_act > 0) {
         if (n_act == 0) {                     /* jump over uncovered stretches */
-            /* find the next passing read */
-            while (next < n) {
-                const int drop = (r->flag[next] & 4) || (r->flag[next] & excl_flags) || r->mapq[next] < min_mapq;
-                if (!drop) break;
-                ++next;
-            }
+            while (next < n && DROPPED(next)) ++next;
             if (next >= n) break;
             p = r->pos[next];
         }
-        /* push the reads that start at this column (B.1 filter) */
+        /* push the reads that start at this column */
         while (next < n && r->pos[next] <= p) {
-            const int drop = (r->flag[next] & 4) || (r->flag[next] & excl_flags) || r->mapq[next] < min_mapq;
-            if (!drop && r->pos[next] == p) {
+            if (!DROPPED(next) && r->pos[next] == p) {
                 cursor_t c;
                 c.read = next; c.op = r->cigar_off[next]; c.op_end = r->cigar_off[next + 1];
                 c.op_off = 0; c.qpos = r->seq_off[next]; c.first = 1; c.rev = (r->flag[next] & 16) != 0;
@@ -106,7 +151,6 @@ int64_t orc_mpileup_write(const nsnp_reads_t* r, const char* contig_name, int32_
         }
         if (n_act == 0) continue;
         if ((int)n_act > deepest) deepest = (int)n_act;
-        if ((int)n_act > max_depth) too_deep = 1;
 
         /* one column */
         bases.n = 0;
@@ -126,20 +170,35 @@ int64_t orc_mpileup_write(const nsnp_reads_t* r, const char* contig_name, int32_
             ++c.op_off;
             int done = 0;
             if (c.op_off == len) {
-                /* last column of this op: look at what follows */
+                /* last column of this op: peek at what follows (B.2) */
                 int64_t k = c.op + 1;
-                while (k < c.op_end && op_of(r->cigar[k]) == 6) ++k;            /* pads are skipped */
-                if (k < c.op_end && op_of(r->cigar[k]) == 1) {
-                    int tot = 0; int64_t k2 = k;
-                    while (k2 < c.op_end && (op_of(r->cigar[k2]) == 1 || op_of(r->cigar[k2]) == 6)) {
-                        if (op_of(r->cigar[k2]) == 1) tot += len_of(r->cigar[k2]);
-                        ++k2;
+                const int op2 = k < c.op_end ? op_of(r->cigar[k]) : -1;
+                int ins = 0;
+                if (op2 == 1) ins = 1;
+                else if (op2 == 6 && k + 1 < c.op_end) {                    /* pad first: an insertion only if I ops follow the pads */
+                    for (int64_t k2 = k + 1; k2 < c.op_end; ++k2) {
+                        const int o = op_of(r->cigar[k2]);
+                        if (o == 1) { ins = 1; break; }
+                        if (o == 2 || o == 0 || o == 3 || o == 7 || o == 8) break;
                     }
+                }
+                if (ins) {
+                    /* insertion run: consecutive I and P ops; pads print as '*' and count in the length */
+                    int tot = 0; int64_t k2 = k;
+                    while (k2 < c.op_end && (op_of(r->cigar[k2]) == 1 || op_of(r->cigar[k2]) == 6)) { tot += len_of(r->cigar[k2]); ++k2; }
                     sb_put(&bases, '+'); sb_int(&bases, tot);
-                    for (int j = 0; j < tot; ++j) sb_put(&bases, base_char(r, c.qpos + j, c.rev));
-                    c.qpos += tot;
-                    k = k2;
-                } else if (k < c.op_end && op_of(r->cigar[k]) == 2 && op != 2) {
+                    int64_t q = c.qpos;
+                    for (int64_t k3 = k; k3 < k2; ++k3) {
+                        const int l3 = len_of(r->cigar[k3]);
+                        if (op_of(r->cigar[k3]) == 1) { for (int j = 0; j < l3; ++j) sb_put(&bases, base_char(r, q + j, c.rev)); q += l3; }
+                        else for (int j = 0; j < l3; ++j) sb_put(&bases, '*');
+                    }
+                    if (k2 < c.op_end && op_of(r->cigar[k2]) == 2) {        /* "1M2I1D": the deletion right after the insertion */
+                        const int dl = len_of(r->cigar[k2]);
+                        sb_put(&bases, '-'); sb_int(&bases, dl);
+                        for (int j = 0; j < dl; ++j) sb_put(&bases, c.rev ? 'n' : 'N');
+                    }
+                } else if (op2 == 2 && op != 2) {
                     int tot = 0; int64_t k2 = k;
                     while (k2 < c.op_end && op_of(r->cigar[k2]) == 2) { tot += len_of(r->cigar[k2]); ++k2; }
                     sb_put(&bases, '-'); sb_int(&bases, tot);
@@ -164,10 +223,11 @@ int64_t orc_mpileup_write(const nsnp_reads_t* r, const char* contig_name, int32_
         n_act = w;
         ++p;
     }
-    free(act); free(bases.s);
+#undef DROPPED
+    free(act); free(bases.s); free(capped);
     const int cerr = fclose(out);
     free(iobuf);
     if (cerr != 0) return -1;
     if (max_depth_seen) *max_depth_seen = deepest;
-    return too_deep ? -2 : rows;
+    return rows;
 }

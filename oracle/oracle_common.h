@@ -7,6 +7,8 @@
 int64_t orc_mpileup_write(const nsnp_reads_t* r, const char* contig_name, int32_t min_mapq, uint32_t excl_flags,
                           int32_t max_depth, const char* path, int append, int32_t* max_depth_seen);
 
+int64_t orc_depth_cap(const nsnp_reads_t* r, int32_t min_mapq, uint32_t excl_flags, int32_t max_depth, uint8_t* dropped);
+
 /* s1 restatement: mpileup text -> counts / flags / candidates / windows / .tensor text */
 typedef struct orc_s1_out {
     int32_t* counts;      /* optional [contig_len][18]: the 18-channel row of every mpileup row (else 0) */

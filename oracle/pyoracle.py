@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(str(LIB))
         _lib.orc_mpileup_write.restype = C.c_int64
         _lib.orc_mpileup_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_uint32, C.c_int32, C.c_char_p, C.c_int, C.c_void_p]
+        _lib.orc_depth_cap.restype = C.c_int64
+        _lib.orc_depth_cap.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_int32, C.c_void_p]
         _lib.orc_s1_from_mpileup.restype = C.c_int64
         _lib.orc_s1_from_mpileup.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_double, C.c_double,
                                              C.c_int32, C.c_int32, C.c_void_p, C.c_char_p, C.c_char_p]
@@ -58,16 +60,23 @@ def lib() -> C.CDLL:
 
 def mpileup_text(reads, contig: str, path: str, min_mapq: int = 20, excl_flags: int = 2316, max_depth: int = 144,
                  append: bool = False) -> tuple[int, int]:
-    """reads: nanosnp_b200.reads.PackedReads with numpy arrays.  Returns (rows, deepest column)."""
+    """reads: nanosnp_b200.reads.PackedReads with numpy arrays.  Returns (rows, deepest column).
+    max_depth > 0 applies the htslib streaming depth cap; 0 disables it."""
     st = reads.as_struct()
     deepest = C.c_int32(0)
     rows = lib().orc_mpileup_write(C.addressof(st), contig.encode(), min_mapq, excl_flags, max_depth, path.encode(),
                                    int(append), C.addressof(deepest))
-    if rows == -2:
-        raise RuntimeError(f"column depth {deepest.value} exceeds --max-depth {max_depth}: the htslib depth cap is not modelled")
     if rows < 0:
         raise OSError(f"orc_mpileup_write failed ({rows})")
     return int(rows), int(deepest.value)
+
+
+def depth_cap(reads, min_mapq: int = 20, excl_flags: int = 2316, max_depth: int = 144) -> np.ndarray:
+    """uint8 [n_reads]: 1 where the pileup engine refuses the read at push time (orc_depth_cap)."""
+    st = reads.as_struct()
+    out = np.zeros(max(reads.n_reads, 1), np.uint8)
+    lib().orc_depth_cap(C.addressof(st), min_mapq, excl_flags, max_depth, out.ctypes.data)
+    return out[: reads.n_reads]
 
 
 @dataclass

@@ -50,3 +50,103 @@ def test_long_cigar_in_cg_tag(tmp_path):
     write_bam(path, [("c", 100)], {"c": rd}, long_cigar_as_tag=4)      # first read has 6 ops -> stored in CG:B,I
     _, got = read_bam(path)
     _same(rd, got["c"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Byte-level fixture built here from the SAM/BAM specification (sections 4.1, 4.2), NOT through write_bam.
+def _bgzf_block(payload: bytes, extra_first: bytes = b"") -> bytes:
+    import struct, zlib
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = co.compress(payload) + co.flush()
+    xlen = 6 + len(extra_first)
+    bsize = 12 + xlen + len(comp) + 8 - 1
+    return (struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, xlen) + extra_first + struct.pack("<BBHH", 66, 67, 2, bsize) + comp
+            + struct.pack("<II", zlib.crc32(payload) & 0xFFFFFFFF, len(payload)))
+
+
+def _bam_record(ref_id, pos, mapq, flag, cigar, seq, tags=b"", name=b"q\0"):
+    import struct
+    codes = "=ACMGRSVTWYHKDBN"
+    ops = "MIDNSHP=X"
+    cig = b"".join(struct.pack("<I", (n << 4) | ops.index(o)) for n, o in cigar)
+    nib = [codes.index(c) for c in seq] + ([0] if len(seq) & 1 else [])
+    sq = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))
+    body = struct.pack("<iiBBHHHIiii", ref_id, pos, len(name), mapq, 4680, len(cigar), flag, len(seq), -1, -1, 0)
+    body += name + cig + sq + b"\xff" * len(seq) + tags
+    return struct.pack("<i", len(body)) + body
+
+
+def test_spec_built_fixture(tmp_path):
+    """IUPAC codes and '=' in SEQ count as N, odd lengths, CG:B,I long CIGAR, adjacent D D merged, a BGZF header with an
+    extra subfield before BC, records spanning block boundaries, an empty block in the middle, unplaced reads last."""
+    import struct
+    hdr_text = b"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:cA\tLN:1000\n@SQ\tSN:cB\tLN:500\n"
+    raw = b"BAM\x01" + struct.pack("<i", len(hdr_text)) + hdr_text + struct.pack("<i", 2)
+    for nm, ln in ((b"cA\0", 1000), (b"cB\0", 500)):
+        raw += struct.pack("<i", len(nm)) + nm + struct.pack("<i", ln)
+    r1 = _bam_record(0, 10, 60, 0, [(3, "S"), (4, "M"), (1, "D"), (2, "D"), (2, "="), (1, "X")], "ACGTRYAC=N")     # 10 bases
+    real = [(2, "M"), (1, "I"), (4, "M")]                                                                      # 7 bases, stored in CG
+    cgtag = b"CGBI" + struct.pack("<I", len(real)) + b"".join(struct.pack("<I", (n << 4) | "MIDNSHP=X".index(o)) for n, o in real)
+    r2 = _bam_record(0, 40, 30, 16, [(7, "S"), (6, "N")], "ACGTACG", tags=b"NMCi\x01XZZhello\0" + cgtag)
+    r3 = _bam_record(1, 5, 7, 1024, [(5, "M")], "TTTTT")
+    r4 = _bam_record(-1, -1, 0, 4, [], "ACG")
+    recs = r1 + r2 + r3 + r4
+    stream = raw + recs
+    cut1, cut2 = len(raw) + 17, len(raw) + len(r1) + 9              # block boundaries inside records
+    path = tmp_path / "spec.bam"
+    path.write_bytes(_bgzf_block(stream[:cut1], extra_first=struct.pack("<BBH", 88, 89, 3) + b"abc") + _bgzf_block(b"")
+                     + _bgzf_block(stream[cut1:cut2]) + _bgzf_block(stream[cut2:]) + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    refs, got = read_bam(str(path))
+    assert refs == [("cA", 1000), ("cB", 500)] and set(got) == {"cA", "cB"}
+    a = got["cA"]
+    assert list(a.pos) == [10, 40] and list(a.flag) == [0, 16] and list(a.mapq) == [60, 30]
+    def cig(rd, i):
+        return [(int(c) >> 4, "MIDNSHP=X"[int(c) & 15]) for c in rd.cigar[rd.cigar_off[i]:rd.cigar_off[i + 1]]]
+    assert cig(a, 0) == [(3, "S"), (4, "M"), (3, "D"), (2, "="), (1, "X")]          # 1D2D merged
+    assert cig(a, 1) == real                                                        # from the CG tag
+    def bases(rd, i, n):
+        k = int(rd.seq_off[i]) + np.arange(n)
+        c = (rd.seq2[k >> 2] >> (2 * (k & 3))) & 3
+        isn = ((rd.nmask[k >> 3] >> (k & 7)) & 1).astype(bool) if rd.nmask is not None else np.zeros(n, bool)
+        return "".join("N" if m else "ACGT"[b] for b, m in zip(c, isn))
+    assert bases(a, 0, 10) == "ACGTNNACNN" and bases(a, 1, 7) == "ACGTACG"
+    assert (a.seq_off % 16 == 0).all()
+    # padding after the odd-length read is clean (no N flag leaks from the pad nibble)
+    assert bases(a, 1, 16)[7:] == "A" * 9
+    b = got["cB"]
+    assert list(b.pos) == [5] and list(b.flag) == [1024] and cig(b, 0) == [(5, "M")] and b.nmask is None
+
+
+def test_index_fetch_and_contig_skip(tmp_path):
+    """With a .bai: fetch(ref, beg, end) returns exactly the reads that overlap / start in the window, and
+    contigs(only=...) seeks past unwanted references without inflating them."""
+    from nanosnp_b200.bam import BamReader
+    from nanosnp_b200.reads import max_reference_span
+    cfg = SynthConfig(contig_len=400_000, coverage=8.0, len_median=3000, len_min=200, nbase_rate=0.002)
+    _, rd1 = generate_host(cfg)
+    cfg2 = SynthConfig(contig_len=150_000, coverage=6.0, len_median=2000, len_min=200, seed_reads=9, contig="ctg2")
+    _, rd2 = generate_host(cfg2)
+    path = str(tmp_path / "i.bam")
+    write_bam(path, [("ctg1", 400_000), ("mid", 10), ("ctg2", 150_000)], {"ctg1": rd1, "ctg2": rd2}, index=True)
+    with BamReader(path, threads=4) as r:
+        assert r.has_index
+        whole = {name: rd for _, name, rd in r.contigs()}
+        total = r.inflated_bytes
+    _same(rd1, whole["ctg1"]); _same(rd2, whole["ctg2"])
+    ops = rd1.cigar & 15
+    rl = np.where((ops == 0) | (ops == 2) | (ops == 3) | (ops == 7) | (ops == 8), rd1.cigar >> 4, 0).astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(rl)])
+    ends = rd1.pos + np.maximum(cs[rd1.cigar_off[1:]] - cs[rd1.cigar_off[:-1]], 1)
+    for beg, end in ((0, 50_000), (123_456, 180_000), (390_000, 400_000), (200_000, 200_001)):
+        with BamReader(path) as r:
+            got = r.fetch(0, beg, end)
+            part = r.inflated_bytes
+        sel = np.nonzero((rd1.pos < end) & (ends > beg))[0]
+        assert np.array_equal(got.pos, rd1.pos[sel]), (beg, end)
+        assert np.array_equal(np.diff(got.cigar_off), np.diff(rd1.cigar_off)[sel])
+        assert end - beg > 20_000 or part < total            # a short window only inflates its own byte range (+ read-ahead)
+    with BamReader(path) as r:
+        only = [(name, rd.n_reads) for _, name, rd in r.contigs({"ctg2"})]
+        assert only == [("ctg2", rd2.n_reads)] and r.inflated_bytes < 0.6 * total
+    with BamReader(path) as r:
+        assert r.fetch(1, 0, 10).n_reads == 0

@@ -40,13 +40,47 @@ def write_head(reference_index_file, fwriter):                     # predict.py:
 from .predict_io import ContigVcfAssembler, format_records, format_records_into, vcf_buffer_bytes  # noqa: E402,F401
 
 
+def _read_inputs(testing_paths, only=None):
+    """Yields (contig, reads or None, bam_reader or None, ref_id) per contig of the read inputs, one contig in memory at a time.
+    BAM files are streamed (bam.BamReader); with a .bai the reads are left in the file and fetched region by region."""
+    from .dataset import load_reads_npz
+    for path in testing_paths:
+        if path.endswith(".bam"):
+            from .bam import BamReader
+            reader = BamReader(path)
+            if reader.has_index:
+                for rid, (name, _) in enumerate(reader.refs):
+                    if only is None or name in only:
+                        yield name, None, reader, rid
+            else:
+                for rid, name, reads in reader.contigs(only):
+                    yield name, reads, None, rid
+        elif not path.endswith(".pd"):
+            reads, contig, _ = load_reads_npz(path)
+            if only is None or contig in only:
+                yield contig, reads, None, -1
+
+
+def _region_reads(reads, reader, rid, regions):
+    from .reads import max_reference_span, slice_reads
+    from .shard import read_range_for_region
+    if reader is not None:
+        return [reader.fetch(rid, rg.start, rg.end) for rg in regions]
+    span = max_reference_span(reads) + 1
+    return [slice_reads(reads, *read_range_for_region(reads.pos, span, rg)) for rg in regions]
+
+
 def predict(model: LSTMNetwork, testing_paths, reference_index_file, batch_size, output_file, device, reference=None, region_len=12_500_000):
     """predict.py:37-195.  `.pd` text files: windows -> model -> records.  Read inputs (`.bam`, `.reads.npz`): the whole
-    s1 + s2 path runs on the GPU region by region (caller.call_contig)."""
-    from .caller import call_contig
-    from .dataset import load_fasta, load_reads_npz
+    s1 + s2 path incl. the VCF text runs on the GPU region by region (caller.call_contig_text); under torchrun every rank
+    computes and formats its LPT share of the regions and writes its own segments of the one output file
+    (caller.write_sharded_vcf)."""
+    import io
+    from .caller import call_contig_text, write_sharded_vcf, _pinned
+    from .dataset import load_fasta
     from .pipeline import PileupEngine
     from .runner import RegionRunner
+    from .shard import assign_lpt, plan_regions
     runner = None
     fasta = None
 
@@ -56,48 +90,48 @@ def predict(model: LSTMNetwork, testing_paths, reference_index_file, batch_size,
             runner = RegionRunner(PileupEngine(device), model._forward(), records=True)
         return runner
 
+    head = io.StringIO(); write_head(reference_index_file, head)
+    header = head.getvalue().encode()
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
+    model.eval()
     if world > 1:
-        # one process per GPU (torchrun): every rank decodes the reads, computes its LPT share of the regions, rank 0
-        # merges the records in (contig, position) order and writes the file (caller.call_contigs_sharded)
-        from .caller import call_contigs_sharded, records_of_regions
+        # one process per GPU (torchrun): the contigs come from the reference index (every rank plans the same regions);
+        # a rank only decodes the contigs / byte ranges of its own regions
         if any(f.endswith(".pd") for f in testing_paths):
             raise NotImplementedError("multi-GPU runs take read inputs (.bam / .reads.npz); .pd files hold ready-made windows")
         if reference is None:
             raise ValueError("read inputs need the reference FASTA")
         fasta = load_fasta(reference)
-        todo = []
-        for testing_file in testing_paths:
-            if testing_file.endswith(".bam"):
-                from .bam import read_bam
-                refs, by_contig = read_bam(testing_file)
-                todo += [(name, by_contig[name]) for name, _ in refs if name in by_contig]
-            else:
-                reads, contig, _ = load_reads_npz(testing_file)
-                todo.append((contig, reads))
-        for contig, _ in todo:
-            if contig not in fasta:
-                raise KeyError(f"contig {contig} is not in the reference")
-        contigs = [(contig, len(fasta[contig])) for contig, _ in todo]
-        model.eval()
-
-        def produce(ci, rgs):
-            return records_of_regions(get_runner(), todo[ci][1], fasta[todo[ci][0]], rgs)
-        import contextlib, io
-        with (open(output_file, "wb") if rank == 0 else contextlib.nullcontext()) as fwriter:
-            if rank == 0:
-                head = io.StringIO(); write_head(reference_index_file, head)
-                fwriter.write(head.getvalue().encode())
-            call_contigs_sharded(contigs, produce, fwriter, batch_size, region_len)
+        with open(reference_index_file) as f:
+            contigs = [(l.split()[0], int(l.split()[1])) for l in f if l.strip()]
+        regions = plan_regions(contigs, region_len)
+        mine = assign_lpt(regions, world)[rank]
+        need = {regions[i].contig for i in mine}
+        index_of = {name: ci for ci, (name, _) in enumerate(contigs)}
+        recs = {}
+        for contig, reads, reader, rid in _read_inputs(testing_paths, need):
+            ci = index_of.get(contig)
+            if ci is None:
+                raise KeyError(f"contig {contig} is not in the reference index")
+            idx = [i for i in mine if regions[i].contig_index == ci]
+            if not idx:
+                continue
+            rgs = [regions[i] for i in idx]
+            host = [_pinned(r) for r in _region_reads(reads, reader, rid, rgs)]
+            ref_dev = torch.from_numpy(np.ascontiguousarray(fasta[contig])).to(device)
+            r = get_runner()
+            for i, rg, hr in zip(idx, rgs, host):
+                out = r.run_device(r.upload(hr), ref_dev, rg)
+                recs[i] = out.rec.clone()                    # records stay on this GPU until the text is made
+        for i in mine:
+            recs.setdefault(i, torch.zeros((0, 32), dtype=torch.uint8, device=device))
+        write_sharded_vcf(output_file, header, contigs, regions, recs, batch_size, device)
         return
 
     with open(output_file, "wb") as fwriter:
-        import io
-        head = io.StringIO(); write_head(reference_index_file, head)
-        fwriter.write(head.getvalue().encode())
-        model.eval()
+        fwriter.write(header)
         for testing_file in testing_paths:
             if testing_file.endswith(".pd"):
                 dataset = PredictDataset(datapath=testing_file, reference=reference, device=device)
@@ -111,22 +145,19 @@ def predict(model: LSTMNetwork, testing_paths, reference_index_file, batch_size,
                 cov8 = x[:, 16, COV_CHANNELS].to(torch.float32)
                 fwriter.write(format_records(names[0], dataset.positions, dataset.reference_bases, gt.cpu().numpy(), zy.cpu().numpy(),
                                              cov8.cpu().numpy(), batch_size))
-                continue
-            if fasta is None:
-                if reference is None:
-                    raise ValueError("read inputs need the reference FASTA")
-                fasta = load_fasta(reference)
-            if testing_file.endswith(".bam"):
-                from .bam import read_bam
-                refs, by_contig = read_bam(testing_file)
-                todo = [(name, by_contig[name]) for name, _ in refs if name in by_contig]
-            else:
-                reads, contig, _ = load_reads_npz(testing_file)
-                todo = [(contig, reads)]
-            for contig, reads in todo:
+        read_paths = [f for f in testing_paths if not f.endswith(".pd")]
+        if read_paths:
+            if reference is None:
+                raise ValueError("read inputs need the reference FASTA")
+            fasta = load_fasta(reference)
+            for contig, reads, reader, rid in _read_inputs(read_paths):
                 if contig not in fasta:
-                    raise KeyError(f"contig {contig} of {testing_file} is not in the reference")
-                call_contig(get_runner(), reads, fasta[contig], contig, fwriter, batch_size, region_len)
+                    if reader is not None:
+                        continue                              # an indexed BAM lists every @SQ; only contigs of the FASTA are called
+                    raise KeyError(f"contig {contig} is not in the reference")
+                regions = plan_regions([(contig, len(fasta[contig]))], region_len)
+                call_contig_text(get_runner(), reads, fasta[contig], contig, fwriter, batch_size, region_len, regions,
+                                 _region_reads(reads, reader, rid, regions))
 
 
 def main(argv=None):
@@ -148,11 +179,15 @@ def main(argv=None):
     device = torch.device("cuda")
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:              # torchrun: one process per GPU, NCCL only gathers the call lists
         import torch.distributed as dist
-        local = int(os.environ.get("LOCAL_RANK", "0"))
+        local = int(os.environ.get("LOCAL_RANK", "0")) % max(1, torch.cuda.device_count())
         torch.cuda.set_device(local)
         device = torch.device("cuda", local)
         os.environ.setdefault("NCCL_DEBUG", "WARN")
-        dist.init_process_group("nccl", device_id=device)
+        backend = os.environ.get("NSNP_DIST_BACKEND", "nccl")       # gloo: several ranks may share one GPU (tests)
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=device)
+        else:
+            dist.init_process_group(backend)
     config = AttrDict(yaml.load(open(opt.config), Loader=yaml.FullLoader))
     pred_model = LSTMNetwork(config.model, precision=opt.precision).to(device)
     if opt.model_path.endswith(".npz"):

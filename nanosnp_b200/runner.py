@@ -206,6 +206,87 @@ class RegionRunner:
         release(n_reg - 2); release(n_reg - 1)
         return total
 
+    # ---- host-buffer mode with the VCF text assembled on the GPU ---------------------------------------------------------
+    def run_host_text(self, host_regions, regions, ref: torch.Tensor, textgen, write) -> int:
+        """Pinned host read arrays of consecutive regions of ONE contig -> H2D -> kernels -> compact records -> VCF text on
+        the GPU (vcf_text.GpuVcfText, which carries partial 1000-site batches across regions) -> D2H of the text.
+        write(memoryview) receives the text chunks in order.  H2D of region k+1 and D2H of chunk k-1 overlap the kernels of
+        region k; the host does no per-record work.  Returns the site count."""
+        assert self.records, "run_host_text needs a RegionRunner(records=True)"
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        up_s, down_s = self._copy_streams
+        n_reg = len(regions)
+        up_done = [None] * n_reg
+        comp_done = [None] * n_reg
+        dev_reads = [None] * n_reg
+
+        def start_upload(k):
+            with torch.cuda.stream(up_s):
+                if k >= 2:
+                    up_s.wait_event(comp_done[k - 2])
+                dev_reads[k] = self.upload(host_regions[k], key=f"reads{k % 2}")
+                ev = torch.cuda.Event(); ev.record(up_s); up_done[k] = ev
+
+        up_s.wait_stream(main)
+        if n_reg:
+            start_upload(0)
+        total = 0
+        pending = None
+        for k in range(n_reg):
+            if k + 1 < n_reg:
+                start_upload(k + 1)
+            main.wait_event(up_done[k])
+            out = self.run_device(dev_reads[k], ref, regions[k])
+            chunk = textgen.push(out.rec) if out.n else None        # copies the records: the work buffers are free again
+            self.launches += 3 if chunk is not None else 0
+            ev = torch.cuda.Event(); ev.record(main); comp_done[k] = ev
+            total += out.n
+            if pending is not None:                                   # its kernels finished before run_device's site-count sync
+                write(textgen.fetch(pending, down_s))
+            pending = chunk
+        if pending is not None:
+            write(textgen.fetch(pending, down_s))
+        last = textgen.flush()
+        if last is not None:
+            self.launches += 3
+            write(textgen.fetch(last, down_s))
+        return total
+
+    # ---- host-buffer mode, records kept on the device (multi-GPU: the text is made after the count / head exchange) ----------
+    def run_host_collect(self, host_regions, regions, refs) -> list:
+        """Pinned host reads of arbitrary regions (refs[k]: the device reference of region k's contig) -> H2D -> kernels ->
+        compact records, returned as one device tensor per region.  The H2D of region k+1 overlaps the kernels of region k."""
+        assert self.records
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        up_s, _ = self._copy_streams
+        n_reg = len(regions)
+        up_done, comp_done, dev_reads, out = [None] * n_reg, [None] * n_reg, [None] * n_reg, [None] * n_reg
+
+        def start_upload(k):
+            with torch.cuda.stream(up_s):
+                if k >= 2:
+                    up_s.wait_event(comp_done[k - 2])
+                dev_reads[k] = self.upload(host_regions[k], key=f"reads{k % 2}")
+                ev = torch.cuda.Event(); ev.record(up_s); up_done[k] = ev
+
+        up_s.wait_stream(main)
+        if n_reg:
+            start_upload(0)
+        for k in range(n_reg):
+            if k + 1 < n_reg:
+                start_upload(k + 1)
+            main.wait_event(up_done[k])
+            o = self.run_device(dev_reads[k], refs[k], regions[k])
+            out[k] = o.rec.clone()
+            ev = torch.cuda.Event(); ev.record(main); comp_done[k] = ev
+        return out
+
     # ---- host-buffer mode: what a caller holding decoded reads in (pinned) host memory pays -------------
     def upload(self, host_reads: PackedReads, key: str = "reads") -> PackedReads:
         out = []

@@ -112,3 +112,51 @@ def test_gpu_site_records_give_identical_vcf_bytes(golden_weights, small_case):
         call_contig(runner, small_case["reads"], small_case["ref"], "ctg1", sink, 1000, 9_000)
         outs.append(sink.getvalue())
     assert outs[0] == outs[1] and len(outs[0]) > 100_000
+
+
+def test_gpu_text_path_equals_host_text_path(golden_weights, small_case):
+    """VCF text assembled on the GPU (vcf_dev.cu, partial batches carried across regions) == host text of the same records."""
+    import io
+    from nanosnp_b200.caller import call_contig, call_contig_text
+    from nanosnp_b200.pipeline import PileupEngine, PileupModelForward, PileupModelWeights
+    from nanosnp_b200.runner import RegionRunner
+    w = PileupModelWeights(*golden_weights, device="cuda:0")
+    runner = RegionRunner(PileupEngine("cuda:0"), PileupModelForward(w, 1), records=True)
+    want = io.BytesIO()
+    call_contig(runner, small_case["reads"], small_case["ref"], "ctg1", want, 1000, 9_000)
+    for region_len in (1 << 30, 9_000, 1_500):
+        got = io.BytesIO()
+        info = call_contig_text(runner, small_case["reads"], small_case["ref"], "ctg1", got, 1000, region_len)
+        assert got.getvalue() == want.getvalue(), region_len
+        assert info["sites"] == len(small_case["site_pos"]) and info["vcf_bytes"] == len(want.getvalue())
+
+
+def test_predict_cli_indexed_bam_and_two_ranks(tmp_path, golden):
+    """(a) an indexed BAM is read region by region through the .bai (only the byte range of each region is inflated);
+    (b) two ranks (gloo, sharing this GPU) write the same bytes as one process: each formats and pwrite()s its own regions."""
+    import os, subprocess, sys
+    from nanosnp_b200 import predict as P
+    from nanosnp_b200.bam import write_bam
+    from nanosnp_b200.synth import SynthConfig, generate_host
+    from oracle.pyoracle import write_fasta
+    refs, reads = {}, {}
+    for i, (name, L) in enumerate([("ctgA", 300_000), ("ctgB", 90_000), ("ctgC", 170_000)]):
+        cfg = SynthConfig(contig_len=L, coverage=22.0, contig=name, seed_ref=31 + i, seed_var=41 + i, seed_reads=51 + i, len_median=4000, len_min=300)
+        refs[name], reads[name] = generate_host(cfg)
+    fa = str(tmp_path / "ref.fa")
+    write_fasta(fa, refs)
+    cfgp = str(P.__file__).replace("predict.py", "config/ont_pileup.yaml")
+    base = ["-config", cfgp, "-model_path", str(golden / "ont_pileup_weights.npz"), "-reference", fa, "--region_len", "50000"]
+    plain = str(tmp_path / "plain.bam"); write_bam(plain, [(n, len(r)) for n, r in refs.items()], reads)
+    idx = str(tmp_path / "idx.bam"); write_bam(idx, [(n, len(r)) for n, r in refs.items()], reads, index=True)
+    o1, o2, o3 = (str(tmp_path / f"{k}.vcf") for k in "abc")
+    P.main(base + ["-data", plain, "-output", o1])
+    P.main(base + ["-data", idx, "-output", o2])
+    a = open(o1, "rb").read()
+    assert a == open(o2, "rb").read() and a.count(b"\n") > 10_000
+    env = dict(os.environ, NSNP_DIST_BACKEND="gloo", PYTHONPATH=str(golden.parent.parent))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", "-m", "nanosnp_b200.predict"] + base + ["-data", idx, "-output", o3]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(o3, "rb").read() == a

@@ -160,3 +160,59 @@ def test_sharded_predict_driver_two_ranks_equals_one():
         assert p.exitcode == 0
     assert res2["world"] == 2 and res2["sites"] == res1["sites"]
     assert text2 == sink.getvalue() and len(text2) > 100_000
+
+
+# ---- write_sharded_vcf: records never leave their rank; counts, batch heads and text lengths are all-reduced and every rank
+#      pwrite()s its own segments into one ordered file ----
+def _sharded_writer_worker(rank, world, port, path):
+    import torch.distributed as dist
+    from nanosnp_b200.caller import write_sharded_vcf
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    regs = plan_regions(_SH_CONTIGS, 40_000)
+    mine = assign_lpt(regs, world)[rank]
+    recs = {}
+    for ci in sorted({regs[i].contig_index for i in mine}):
+        idx = [i for i in mine if regs[i].contig_index == ci]
+        for i, r in zip(idx, _fake_produce(ci, [regs[i] for i in idx])):
+            recs[i] = r
+    res = write_sharded_vcf(path, b"##header\n", _SH_CONTIGS, regs, recs, batch_size=1000)
+    assert res["world"] == world
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_writer_equals_single_process_formatter(tmp_path, world):
+    import ctypes as C
+    from nanosnp_b200 import _lib
+    from nanosnp_b200.caller import write_sharded_vcf
+    lib = _lib.load()
+    # expectation: every contig formatted in one piece by the host contig formatter
+    want = b"##header\n"
+    for ci, (name, L) in enumerate(_SH_CONTIGS):
+        rec = _fake_records(ci, L)
+        cap = len(rec) * 160 + 1024
+        buf = C.create_string_buffer(cap)
+        n = lib.nsnp_vcf_format_contig_records(name.encode(), len(rec), rec.ctypes.data, 1000, 2, C.addressof(buf), cap)
+        want += buf.raw[:n]
+    # one process
+    regs = plan_regions(_SH_CONTIGS, 40_000)
+    recs = {}
+    for ci in range(len(_SH_CONTIGS)):
+        idx = [i for i, r in enumerate(regs) if r.contig_index == ci]
+        for i, r in zip(idx, _fake_produce(ci, [regs[i] for i in idx])):
+            recs[i] = r
+    p1 = str(tmp_path / "one.vcf")
+    write_sharded_vcf(p1, b"##header\n", _SH_CONTIGS, regs, recs, batch_size=1000)
+    assert open(p1, "rb").read() == want
+    # `world` gloo ranks
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    pn = str(tmp_path / "n.vcf")
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_sharded_writer_worker, args=(r, world, port, pn)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert open(pn, "rb").read() == want

@@ -194,7 +194,7 @@ def main_ours(args):
     import torch
     import torch.distributed as dist
     from nanosnp_b200 import _lib
-    from nanosnp_b200.caller import write_sharded_vcf
+    from nanosnp_b200.caller import ShardedVcfWriter
     from nanosnp_b200.pipeline import PileupEngine, PileupModelForward, PileupModelWeights
     from nanosnp_b200.predict_io import ContigVcfAssembler
     from nanosnp_b200.reads import FIELDS, PackedReads
@@ -211,8 +211,19 @@ def main_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line (NCCL prints its version at INFO/VERSION)
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version on stdout while the communicator is created: route that to stderr so that stdout carries
+        # the one JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     K, W = args.steps, max(args.warmup, 3)
     lib = _lib.load()
     eng = PileupEngine(dev)
@@ -382,10 +393,11 @@ def main_ours(args):
             out_path = f"/dev/shm/nsnp_bench_{os.environ.get('MASTER_PORT', '0')}.vcf"
             header = b"##fileformat=VCFv4.3\n" + b"".join(f"##contig=<ID={n},length={L}>\n".encode() for n, L in contigs)
             info = {}
+            writer = ShardedVcfWriter(contigs, regions, 1000, dev)
 
             def step_host():
                 recs = runner_e2e.run_host_collect(host_regions, rgs, refs)
-                info.update(write_sharded_vcf(out_path, header, contigs, regions, dict(zip(idx, recs)), 1000, dev))
+                info.update(writer.write(out_path, header, dict(zip(idx, recs))))
                 return sum(int(r.shape[0]) for r in recs)
             e2e_ms, n_e2e = time_e2e(step_host, steps)
             res["e2e"] = {"ms": e2e_ms, "sites": n_e2e, "h2d": h2d, "d2h": 0, "vcf_bytes": info.get("vcf_bytes", 0)}

@@ -150,102 +150,234 @@ def _all_reduce(t, op):
     return t
 
 
-def write_sharded_vcf(out_path: str, header: bytes, contigs, regions, records_by_region: dict, batch_size: int = 1000, device=None) -> dict:
-    """Every rank holds the compact site records of ITS regions (records_by_region: region index -> uint8 [n,32] torch tensor
-    on `device`, or a host RECORD_DTYPE / uint8 array) and writes their text itself, at the right place of ONE ordered file:
+class ShardedVcfWriter:
+    """Every rank holds the compact site records of ITS regions and writes their text itself, at the right place of ONE
+    ordered file (see write()).  Buffers (device text / workspaces / batch-head table, pinned host text) persist across calls."""
 
-      1. SUM all-reduce of the per-region site counts  -> every region's first site index inside its contig file;
-      2. MIN all-reduce of the batch-head table        -> the genotype argmax of the first ten sites of every 1000-site batch of
-                                                          every contig (what predict.py's `gt_output[ti]` reads; 10 bytes per batch);
-      3. each rank formats its regions (GPU kernels for device records, the host twin otherwise) -- byte-identical to one
-         process formatting the merged list, because batches are counted from the contig's first site either way;
-      4. SUM all-reduce of the per-region text lengths -> file offsets; every rank pwrite()s its segments, rank 0 the header.
+    def __init__(self, contigs, regions, batch_size: int = 1000, device=None):
+        from . import _lib
+        self.lib = _lib.load()
+        self.contigs, self.regions, self.batch, self.device = list(contigs), list(regions), int(batch_size), device
+        self._dev = {}
+        self._host = {}
+        self._pool = None
+        self.write_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
 
-    No record ever crosses ranks (the r01 path pickled all of them to rank 0 and formatted there)."""
-    import ctypes as C
-    import torch.distributed as dist
-    from . import _lib
-    from .predict_io import RECORD_DTYPE
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
-    n_reg = len(regions)
-    counts = torch.zeros(n_reg, dtype=torch.int64)
-    for i, rec in records_by_region.items():
-        counts[i] = int(rec.shape[0])
-    counts = _all_reduce(counts, dist.ReduceOp.SUM if world > 1 else None)
-    first = [0] * n_reg                                        # first site index of each region inside its contig
-    tot = {}
-    for i, rg in enumerate(regions):
-        first[i] = tot.get(rg.contig_index, 0)
-        tot[rg.contig_index] = first[i] + int(counts[i])
-    nb = {ci: (n + batch_size - 1) // batch_size for ci, n in tot.items()}
-    hoff, o = {}, 0
-    for ci in sorted(nb):
-        hoff[ci] = o; o += nb[ci]
-    on_gpu = any(isinstance(r, torch.Tensor) and r.is_cuda for r in records_by_region.values())
-    lib = _lib.load()
-    gens = {}
-    if on_gpu:
-        from .vcf_text import GpuVcfText
-        heads = torch.full((max(o, 1), 10), 255, dtype=torch.uint8, device=device)
+    def _dbuf(self, key, nbytes, dtype=torch.uint8):
+        t = self._dev.get(key)
+        if t is None or t.numel() * t.element_size() < nbytes:
+            t = torch.empty(int(nbytes * 1.15) // torch.empty((), dtype=dtype).element_size() + 64, dtype=dtype, device=self.device)
+            self._dev[key] = t
+        return t
+
+    def _hbuf(self, key, n, dtype=torch.uint8):
+        t = self._host.get(key)
+        if t is None or t.numel() < n:
+            t = torch.empty(int(n * 1.15) + 64, dtype=dtype).pin_memory()
+            self._host[key] = t
+        return t
+
+    def write(self, out_path: str, header: bytes, records_by_region: dict) -> dict:
+        """records_by_region: region index -> uint8 [n,32] torch tensor on `device`, or a host RECORD_DTYPE / uint8 array.
+
+          1. SUM all-reduce of the per-region site counts  -> every region's first site index inside its contig file;
+          2. MIN all-reduce of the batch-head table        -> the genotype argmax of the first ten sites of every 1000-site batch
+                                                              of every contig (what predict.py's `gt_output[ti]` reads; 10 B per batch);
+          3. each rank formats its regions (GPU kernels for device records, all regions enqueued back to back; the host twin
+             otherwise) -- byte-identical to one process formatting the merged list, because batches are counted from the
+             contig's first site either way;
+          4. SUM all-reduce of the per-region text lengths -> file offsets; every rank pwrite()s its segments, rank 0 the header.
+
+        No record ever crosses ranks (the r01 path pickled all of them to rank 0 and formatted there)."""
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib
+        from .predict_io import RECORD_DTYPE
+        lib, regions, contigs, batch = self.lib, self.regions, self.contigs, self.batch
+        import time
+        tr = [("start", time.perf_counter())]
+        mark = lambda name: tr.append((name, time.perf_counter()))
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        n_reg = len(regions)
+        counts = torch.zeros(n_reg, dtype=torch.int64)
         for i, rec in records_by_region.items():
-            ci = regions[i].contig_index
-            g = gens.setdefault(ci, GpuVcfText(device, contigs[ci][0], batch_size))
-            if rec.shape[0]:
-                g.batch_heads(rec, first[i], heads[hoff[ci]:hoff[ci] + nb[ci]])
-        if world > 1:
-            if dist.get_backend() == "nccl":
-                dist.all_reduce(heads, op=dist.ReduceOp.MIN)
-            else:
-                heads.copy_(_all_reduce(heads.cpu(), dist.ReduceOp.MIN))
-    else:
-        heads_np = np.full((max(o, 1), 10), 255, np.uint8)
-        for i, rec in records_by_region.items():
-            ci = regions[i].contig_index
-            r = np.ascontiguousarray(rec).view(RECORD_DTYPE).reshape(-1)
-            g = first[i] + np.arange(len(r))
-            sel = (g % batch_size) < 10
-            heads_np[hoff[ci] + g[sel] // batch_size, g[sel] % batch_size] = r["gt"][sel]
-        heads_np = _all_reduce(torch.from_numpy(heads_np), dist.ReduceOp.MIN if world > 1 else None).numpy()
-    # 3. text of my regions
-    texts = {}
-    for i in sorted(records_by_region):
-        rec = records_by_region[i]
-        ci = regions[i].contig_index
-        if rec.shape[0] == 0:
-            texts[i] = b""
-        elif on_gpu:
-            g = gens[ci]
-            texts[i] = bytes(g.fetch(g.format_at(rec, first[i], heads[hoff[ci]:hoff[ci] + nb[ci]])))
+            counts[i] = int(rec.shape[0])
+        counts = _all_reduce(counts, dist.ReduceOp.SUM if world > 1 else None)
+        mark("counts")
+        first = [0] * n_reg                                        # first site index of each region inside its contig
+        tot = {}
+        for i, rg in enumerate(regions):
+            first[i] = tot.get(rg.contig_index, 0)
+            tot[rg.contig_index] = first[i] + int(counts[i])
+        nb = {ci: (n + batch - 1) // batch for ci, n in tot.items()}
+        hoff, o = {}, 0
+        for ci in sorted(nb):
+            hoff[ci] = o; o += nb[ci]
+        mine = sorted(records_by_region)
+        on_gpu = any(isinstance(r, torch.Tensor) and r.is_cuda for r in records_by_region.values())
+        texts = {}                                                 # region index -> memoryview / bytes
+        if on_gpu:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            heads = self._dbuf("heads", max(o, 1) * 10)[: max(o, 1) * 10].view(-1, 10)
+            heads.fill_(255)
+            with torch.cuda.device(self.device):
+                for i in mine:
+                    rec = records_by_region[i]
+                    ci = regions[i].contig_index
+                    if rec.shape[0]:
+                        _lib.check(lib.nsnp_vcf_batch_heads(rec.data_ptr(), int(rec.shape[0]), 0, first[i], batch,
+                                                            heads[hoff[ci]:].data_ptr(), stream))
+            if world > 1:
+                if dist.get_backend() == "nccl":
+                    dist.all_reduce(heads, op=dist.ReduceOp.MIN)
+                else:
+                    heads.copy_(_all_reduce(heads.cpu(), dist.ReduceOp.MIN))
+            mark("heads")
+            # all text kernels of my regions back to back, each into its own slice of one device buffer
+            caps = [int(lib.nsnp_vcf_text_capacity(int(records_by_region[i].shape[0]), contigs[regions[i].contig_index][0].encode())) for i in mine]
+            wss = [(int(lib.nsnp_vcf_text_workspace_bytes(int(records_by_region[i].shape[0]))) + 255) // 256 * 256 for i in mine]
+            toff = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
+            woff = np.concatenate([[0], np.cumsum(wss)]).astype(np.int64)
+            text_dev = self._dbuf("text", int(toff[-1]) + 256)
+            ws_dev = self._dbuf("ws", int(woff[-1]) + 256)
+            meta_dev = self._dbuf("meta", 8 * (len(mine) + 1), torch.int64)
+            tie_cnt_off, tie_ent_off = [], []
+            with torch.cuda.device(self.device):
+                for k, i in enumerate(mine):
+                    rec = records_by_region[i]
+                    ci = regions[i].contig_index
+                    n = int(rec.shape[0])
+                    wp = ws_dev.data_ptr() + int(woff[k])
+                    _lib.check(lib.nsnp_vcf_text_records(contigs[ci][0].encode(), rec.data_ptr() if n else 0, n, 0, first[i], batch,
+                                                         heads[hoff[ci]:].data_ptr(), text_dev.data_ptr() + int(toff[k]), caps[k],
+                                                         meta_dev.data_ptr() + 8 * k, wp, wss[k], stream))
+                    cp = C.c_void_p(); ep = C.c_void_p(); cap = C.c_int32(0)
+                    lib.nsnp_vcf_text_ties(wp, n, C.byref(cp), C.byref(ep), C.byref(cap))
+                    tie_cnt_off.append((cp.value or wp) - ws_dev.data_ptr()); tie_ent_off.append((ep.value or wp) - ws_dev.data_ptr())
+            meta_h = self._hbuf("meta", len(mine) + 1, torch.int64)
+            ties_n = self._hbuf("ties_n", len(mine) + 1, torch.int32)
+            meta_h[:len(mine)].copy_(meta_dev[:len(mine)], non_blocking=True)
+            for k, i in enumerate(mine):
+                if records_by_region[i].shape[0]:
+                    ties_n[k:k + 1].copy_(ws_dev[tie_cnt_off[k]:tie_cnt_off[k] + 4].view(torch.int32), non_blocking=True)
+                else:
+                    ties_n[k] = 0
+            torch.cuda.current_stream(self.device).synchronize()
+            mark("text kernels")
+            lens = [int(meta_h[k]) if records_by_region[i].shape[0] else 0 for k, i in enumerate(mine)]
+            for k, ln in enumerate(lens):
+                if ln > caps[k]:
+                    raise _lib.NsnpError(_lib.E_WORKSPACE, "VCF text buffer too small")
+            slack = 64                                             # a tie fix-up can lengthen a record by a digit
+            hoffs = np.concatenate([[0], np.cumsum([ln + slack for ln in lens])]).astype(np.int64)
+            text_h = self._hbuf("text", int(hoffs[-1]) + 64)
+            ties_h = self._hbuf("ties", 64 * 4096 * max(1, sum(1 for k in range(len(mine)) if int(ties_n[k]) > 0)))
+            tie_slot = {}
+            for k, ln in enumerate(lens):
+                if ln:
+                    text_h[int(hoffs[k]):int(hoffs[k]) + ln].copy_(text_dev[int(toff[k]):int(toff[k]) + ln], non_blocking=True)
+                nt = int(ties_n[k])
+                if nt > 4096:
+                    raise _lib.NsnpError(_lib.E_OVERFLOW, f"{nt} rounding-tie records in one region")
+                if nt > 0:
+                    slot = len(tie_slot) * 64 * 4096
+                    tie_slot[k] = slot
+                    ties_h[slot:slot + 64 * nt].copy_(ws_dev[tie_ent_off[k]:tie_ent_off[k] + 64 * nt], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            mark("d2h")
+            mv = memoryview(text_h.numpy())
+            for k, i in enumerate(mine):
+                ln = lens[k]
+                if k in tie_slot:
+                    ci = regions[i].contig_index
+                    w = lib.nsnp_vcf_text_patch_ties(contigs[ci][0].encode(), text_h.data_ptr() + int(hoffs[k]), ln, ln + slack,
+                                                     ties_h.data_ptr() + tie_slot[k], int(ties_n[k]))
+                    if w <= 0 and ln > 0:
+                        raise _lib.NsnpError(_lib.E_WORKSPACE, "tie fix-up of the VCF text failed")
+                    ln = int(w)
+                texts[i] = mv[int(hoffs[k]):int(hoffs[k]) + ln]
         else:
-            r = np.ascontiguousarray(rec).view(RECORD_DTYPE).reshape(-1)
-            cap = len(r) * (96 + len(contigs[ci][0])) + 256
-            buf = np.empty(cap, np.uint8)
-            h = np.ascontiguousarray(heads_np[hoff[ci]:hoff[ci] + nb[ci]])
-            w = lib.nsnp_vcf_format_records_at(contigs[ci][0].encode(), r.ctypes.data, len(r), first[i], batch_size, h.ctypes.data,
-                                               buf.ctypes.data, cap)
-            if w < 0:
-                raise _lib.NsnpError(_lib.E_WORKSPACE, "VCF text buffer too small")
-            texts[i] = buf[:w].tobytes()
-    # 4. offsets, ordered file
-    lens = torch.zeros(n_reg, dtype=torch.int64)
-    for i, t in texts.items():
-        lens[i] = len(t)
-    lens = _all_reduce(lens, dist.ReduceOp.SUM if world > 1 else None)
-    offs = np.concatenate([[len(header)], len(header) + np.cumsum(lens.numpy())])
-    if rank == 0:
-        with open(out_path, "wb") as f:
-            f.write(header)
-            f.truncate(int(offs[-1]))
-    if world > 1:
-        dist.barrier()
-    fd = os.open(out_path, os.O_WRONLY)
-    try:
+            heads_np = np.full((max(o, 1), 10), 255, np.uint8)
+            for i in mine:
+                ci = regions[i].contig_index
+                r = np.ascontiguousarray(records_by_region[i]).view(RECORD_DTYPE).reshape(-1)
+                g = first[i] + np.arange(len(r))
+                sel = (g % batch) < 10
+                heads_np[hoff[ci] + g[sel] // batch, g[sel] % batch] = r["gt"][sel]
+            heads_np = _all_reduce(torch.from_numpy(heads_np), dist.ReduceOp.MIN if world > 1 else None).numpy()
+            for i in mine:
+                ci = regions[i].contig_index
+                r = np.ascontiguousarray(records_by_region[i]).view(RECORD_DTYPE).reshape(-1)
+                if len(r) == 0:
+                    texts[i] = b""
+                    continue
+                cap = len(r) * (96 + len(contigs[ci][0])) + 256
+                buf = np.empty(cap, np.uint8)
+                h = np.ascontiguousarray(heads_np[hoff[ci]:hoff[ci] + nb[ci]])
+                w = lib.nsnp_vcf_format_records_at(contigs[ci][0].encode(), r.ctypes.data, len(r), first[i], batch, h.ctypes.data,
+                                                   buf.ctypes.data, cap)
+                if w < 0:
+                    raise _lib.NsnpError(_lib.E_WORKSPACE, "VCF text buffer too small")
+                texts[i] = buf[:w].tobytes()
+        mark("patch")
+        # 4. offsets, ordered file
+        lens_t = torch.zeros(n_reg, dtype=torch.int64)
         for i, t in texts.items():
-            if t:
-                os.pwrite(fd, t, int(offs[i]))
-    finally:
-        os.close(fd)
-    if world > 1:
-        dist.barrier()
-    return {"sites": int(counts.sum()), "vcf_bytes": int(offs[-1]) - len(header), "regions": n_reg, "world": world}
+            lens_t[i] = len(t)
+        lens_t = _all_reduce(lens_t, dist.ReduceOp.SUM if world > 1 else None)
+        offs = np.concatenate([[len(header)], len(header) + np.cumsum(lens_t.numpy())])
+        mark("lengths")
+        if rank == 0:
+            # an existing file keeps its pages: only its size changes (a fresh tmpfs / page-cache allocation costs more than the copy)
+            fd0 = os.open(out_path, os.O_WRONLY | os.O_CREAT, 0o644)
+            try:
+                os.ftruncate(fd0, int(offs[-1]))
+                os.pwrite(fd0, header, 0)
+            finally:
+                os.close(fd0)
+        if world > 1:
+            dist.barrier()
+        mark("create")
+        # every rank copies its segments into a shared mapping of the file: concurrent pwrite()s to one file serialise on the
+        # inode lock (3 GB/s for the whole box), page-wise copies into a mapping do not.  ctypes.memmove releases the GIL.
+        import ctypes as C2
+        import mmap
+        segs = [(t, int(offs[i])) for i, t in texts.items() if len(t)]
+        if segs:
+            fd = os.open(out_path, os.O_RDWR)
+            try:
+                mm = mmap.mmap(fd, int(offs[-1]), mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+            finally:
+                os.close(fd)
+            try:
+                base = C2.addressof(C2.c_char.from_buffer(mm))
+                jobs = []
+                for t, o_ in segs:
+                    src = np.frombuffer(t, np.uint8)
+                    for c in range(0, len(src), 8 << 20):
+                        jobs.append((base + o_ + c, src[c:c + (8 << 20)]))
+                move = lambda j: C2.memmove(j[0], j[1].ctypes.data, j[1].shape[0])
+                if len(jobs) > 1 and self.write_threads > 1:
+                    from concurrent.futures import ThreadPoolExecutor
+                    if self._pool is None:
+                        self._pool = ThreadPoolExecutor(self.write_threads)
+                    list(self._pool.map(move, jobs))
+                else:
+                    for j in jobs:
+                        move(j)
+                del base
+            finally:
+                mm.close()
+        mark("pwrite")
+        if world > 1:
+            dist.barrier()
+        if os.environ.get("NSNP_TRACE") and rank == 0:
+            import sys
+            print("ShardedVcfWriter " + " ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.1f}ms" for a, b in zip(tr[:-1], tr[1:])), file=sys.stderr)
+        return {"sites": int(counts.sum()), "vcf_bytes": int(offs[-1]) - len(header), "regions": n_reg, "world": world}
+
+
+def write_sharded_vcf(out_path: str, header: bytes, contigs, regions, records_by_region: dict, batch_size: int = 1000, device=None) -> dict:
+    """One-shot form of ShardedVcfWriter.write."""
+    return ShardedVcfWriter(contigs, regions, batch_size, device).write(out_path, header, records_by_region)

@@ -182,7 +182,8 @@ def main(argv=None):
         local = int(os.environ.get("LOCAL_RANK", "0")) % max(1, torch.cuda.device_count())
         torch.cuda.set_device(local)
         device = torch.device("cuda", local)
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         backend = os.environ.get("NSNP_DIST_BACKEND", "nccl")       # gloo: several ranks may share one GPU (tests)
         if backend == "nccl":
             dist.init_process_group("nccl", device_id=device)

@@ -193,7 +193,7 @@ typedef struct nsnp_site_record {        /* 32 bytes */
     int32_t pos1;                        /* 1-based position */
     int32_t q100_gt, q100_zy;            /* round(QUAL * 100) of the genotype / zygosity probability */
     int32_t depth;                       /* DP */
-    int32_t af_q;                        /* AF * 1e6 rounded like '%f', or NSNP_AF_ONE / NSNP_AF_NAN */
+    int32_t af_q;                        /* AF * 1e6 rounded like '%f', or NSNP_AF_ONE / NSNP_AF_NAN / NSNP_AF_NEG_INF / negative code */
     float   p_gt, p_zy;                  /* the max probabilities (host recomputes flagged rounding ties) */
 } nsnp_site_record_t;
 #define NSNP_REC_DROP    1               /* predict.py would raise for this site: no record */
@@ -201,6 +201,9 @@ typedef struct nsnp_site_record {        /* 32 bytes */
 #define NSNP_REC_TIE_ZY  4
 #define NSNP_AF_ONE      1000001
 #define NSNP_AF_NAN      (-1)
+#define NSNP_AF_NEG_INF  (-2)            /* '%f' of -inf (positive support over a depth of -0.0) */
+/* af_q <= -3: a negative quotient (negative support: impossible for gate-passing counts, the ABI accepts any x);
+ * -(af_q + 3) = |AF| * 1e6 rounded like '%f', printed with a leading '-' */
 int nsnp_site_records(const float* gt_prob_dev, const float* zy_prob_dev, const int32_t* x_i32_dev, const uint8_t* refbase_dev,
                       const int32_t* pos_dev, int64_t n, const int32_t* n_dev, nsnp_site_record_t* rec_dev, void* stream);
 /* host: text of all records of consecutive batch_size-site batches from compact records (same bytes as the two below) */

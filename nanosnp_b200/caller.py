@@ -177,8 +177,9 @@ class ShardedVcfWriter:
             self._host[key] = t
         return t
 
-    def write(self, out_path: str, header: bytes, records_by_region: dict) -> dict:
-        """records_by_region: region index -> uint8 [n,32] torch tensor on `device`, or a host RECORD_DTYPE / uint8 array.
+    def write(self, out_path: Optional[str], header: bytes, records_by_region: dict) -> dict:
+        """out_path None: stop once every rank holds its text segments in pinned host memory and knows their file offsets
+        (self.segments: [(memoryview, offset)]); the caller places them.  records_by_region: region index -> uint8 [n,32] torch tensor on `device`, or a host RECORD_DTYPE / uint8 array.
 
           1. SUM all-reduce of the per-region site counts  -> every region's first site index inside its contig file;
           2. MIN all-reduce of the batch-head table        -> the genotype argmax of the first ten sites of every 1000-site batch
@@ -328,6 +329,9 @@ class ShardedVcfWriter:
         lens_t = _all_reduce(lens_t, dist.ReduceOp.SUM if world > 1 else None)
         offs = np.concatenate([[len(header)], len(header) + np.cumsum(lens_t.numpy())])
         mark("lengths")
+        self.segments = [(t, int(offs[i])) for i, t in texts.items() if len(t)]
+        if out_path is None:
+            return {"sites": int(counts.sum()), "vcf_bytes": int(offs[-1]) - len(header), "regions": n_reg, "world": world}
         if rank == 0:
             # an existing file keeps its pages: only its size changes (a fresh tmpfs / page-cache allocation costs more than the copy)
             fd0 = os.open(out_path, os.O_WRONLY | os.O_CREAT, 0o644)

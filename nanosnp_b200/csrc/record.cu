@@ -71,11 +71,14 @@ __global__ void __launch_bounds__(256) site_record_kernel(const float* __restric
             const float af = __fdiv_rn(support, depth);                  // float32 quotient: 0/0 -> nan, x/0 -> inf
             if (af > 1.0f) r.af_q = NSNP_AF_ONE;                          // predict.py:83-84
             else if (af != af) r.af_q = NSNP_AF_NAN;
+            else if (af == -INFINITY) r.af_q = NSNP_AF_NEG_INF;
             else {
-                const double m = (double)af * 1.0e6;                      // exact: 24-bit significand x 20-bit integer
+                const bool neg = signbit(af);
+                const double m = fabs((double)af) * 1.0e6;                // exact: 24-bit significand x 20-bit integer
                 double q = floor(m); const double fr = m - q;
                 if (fr > 0.5 || (fr == 0.5 && fmod(q, 2.0) == 1.0)) q += 1.0;   // printf('%f') rounds the exact value, ties to even
-                r.af_q = (m >= 0.0) ? (int32_t)q : NSNP_AF_NAN;
+                if (q > 2.0e9) q = 2.0e9;
+                r.af_q = neg ? -(int32_t)q - 3 : (int32_t)q;
             }
             bool tie = false;
             if (!score_q100(gm, kScale, &r.q100_gt, &tie)) r.flags |= NSNP_REC_DROP; else if (tie) r.flags |= NSNP_REC_TIE_GT;

@@ -460,7 +460,9 @@ inline char* put_record_q(char* p, const char* contig, size_t clen, long long po
     *p++ = ':';
     if (af_q == NSNP_AF_ONE) { memcpy(p, "1.000000", 8); p += 8; }
     else if (af_q == NSNP_AF_NAN) { memcpy(p, "nan", 3); p += 3; }
+    else if (af_q == NSNP_AF_NEG_INF) { memcpy(p, "-inf", 4); p += 4; }
     else {
+        if (af_q <= -3) { *p++ = '-'; af_q = -(af_q + 3); }
         const uint32_t u = (uint32_t)af_q, ipa = u / 1000000u, f = u - ipa * 1000000u;
         p = put_u32(p, ipa);
         *p++ = '.';

@@ -108,8 +108,11 @@ __host__ __device__ inline int format_record(char* out, const char* contig, int 
     *p++ = ':';
     if (r.af_q == NSNP_AF_ONE) { const char f[] = "1.000000"; for (int i = 0; i < 8; ++i) *p++ = f[i]; }
     else if (r.af_q == NSNP_AF_NAN) { *p++ = 'n'; *p++ = 'a'; *p++ = 'n'; }
+    else if (r.af_q == NSNP_AF_NEG_INF) { *p++ = '-'; *p++ = 'i'; *p++ = 'n'; *p++ = 'f'; }
     else {
-        const uint32_t u = (uint32_t)r.af_q, ipa = u / 1000000u; uint32_t f = u - ipa * 1000000u;
+        int32_t aq = r.af_q;
+        if (aq <= -3) { *p++ = '-'; aq = -(aq + 3); }
+        const uint32_t u = (uint32_t)aq, ipa = u / 1000000u; uint32_t f = u - ipa * 1000000u;
         p = put_dec(p, ipa); *p++ = '.';
         char d[6]; for (int i = 5; i >= 0; --i) { d[i] = (char)('0' + f % 10); f /= 10; }
         for (int i = 0; i < 6; ++i) *p++ = d[i];

@@ -81,8 +81,31 @@ class PredictDataset:
             self.reference_bases = refbase.cpu().numpy().astype(np.int64)
             self.contig_names = [contig] * len(self.positions)
         elif datapath.endswith(".bin"):
-            raise NotImplementedError("PyTables .bin files need the `tables` package, which is absent: pass the .pd text "
-                                      "(same content) or packed reads (.reads.npz)")
+            # predict.py:215 lists `bin_predict_data/<chr>.pd.bin` (PyTables HDF5, make_bin_predict_data.py:90-100).  With
+            # PyTables installed the file is read as the reference does; without it the `.pd` text it was made from
+            # (make_predict_data.sh step 4 leaves it in ../predict_data/) carries the same arrays.
+            try:
+                import tables                                    # noqa: F401
+            except ImportError:
+                tables = None
+            if tables is not None:
+                with tables.open_file(datapath, "r") as f:       # dataset.py:121-139
+                    self.position_matrix = np.asarray(f.root.position_matrix, np.int32)
+                    meta = [r[0].decode().split(":") for r in f.root.position]
+                self.contig_names = [m[0] for m in meta]
+                self.positions = np.asarray([int(m[1]) for m in meta], np.int64)
+                self.reference_bases = np.asarray([ord(m[2][16]) for m in meta], np.int64)
+            else:
+                import os
+                base = os.path.basename(datapath)[:-4]
+                d = os.path.dirname(os.path.abspath(datapath))
+                for cand in (datapath[:-4], os.path.join(d, "..", "predict_data", base)):
+                    if cand.endswith(".pd") and os.path.exists(cand):
+                        self.position_matrix, self.contig_names, self.positions, self.reference_bases = parse_pd_text(cand)
+                        break
+                else:
+                    raise NotImplementedError("PyTables .bin files need the `tables` package, which is absent, and no `.pd` text of the "
+                                              f"same name was found next to {datapath} or in ../predict_data/")
         else:
             raise ValueError(f"unrecognised predict data file: {datapath}")
 

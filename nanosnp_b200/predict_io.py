@@ -40,7 +40,7 @@ RECORD_DTYPE = np.dtype([("gt", np.uint8), ("zy", np.uint8), ("flags", np.uint8)
                          ("q100_gt", np.int32), ("q100_zy", np.int32), ("depth", np.int32), ("af_q", np.int32),
                          ("p_gt", np.float32), ("p_zy", np.float32)])          # struct nsnp_site_record (32 bytes)
 assert RECORD_DTYPE.itemsize == 32
-REC_DROP, REC_TIE_GT, REC_TIE_ZY, AF_ONE, AF_NAN = 1, 2, 4, 1000001, -1
+REC_DROP, REC_TIE_GT, REC_TIE_ZY, AF_ONE, AF_NAN, AF_NEG_INF = 1, 2, 4, 1000001, -1, -2
 
 
 def format_compact_records_into(buf: np.ndarray, contig: str, rec: np.ndarray, batch_size: int, n_threads: int = 0) -> int:
@@ -86,12 +86,14 @@ def records_reference(positions1, reference_bases, gt, zy, cov8) -> np.ndarray:
                 rec["af_q"][j] = AF_ONE
             elif af != af:
                 rec["af_q"][j] = AF_NAN
+            elif np.isneginf(af):
+                rec["af_q"][j] = AF_NEG_INF
             else:
-                m = float(af) * 1.0e6
+                m = abs(float(af)) * 1.0e6
                 q = np.floor(m); fr = m - q
                 if fr > 0.5 or (fr == 0.5 and q % 2 == 1):
                     q += 1
-                rec["af_q"][j] = int(q)
+                rec["af_q"][j] = -int(q) - 3 if np.signbit(af) else int(q)
             flags = 0
             for name, p, tiebit in (("q100_gt", rec["p_gt"][j], REC_TIE_GT), ("q100_zy", rec["p_zy"][j], REC_TIE_ZY)):
                 r = np.float32(np.float32(1.0) - p) / np.float32(p)

@@ -164,6 +164,33 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
 int nsnp_debug_lstm_tc_gates(const void* blob_dev, const int32_t* x_i32_dev, int layer, int dir, int cg, const void* h0_dev,
                              float* gates_out_dev, int64_t m, void* stream);
 
+/* ---- BASELINE configs[4]: HaplotypeModel s5 (csrc/haplotype.cu) ---------------------------------------------------------
+ * nsnp_hap_features replaces get_frequency_feature + the reference-code row (HaplotypeModel/dataset_dev.py:11-87,337-349):
+ *   seq / bq / mq / hp  int32 [n][depth][L]  read x position matrices as write_to_bins.py:15-63 stores them
+ *                       (base 1..4, deletion -1, absent 0, pad rows -2; HP tag 1 / 2, untagged 3)
+ *   refcode             int32 [n][L]         A1 C2 G3 T4, everything else 0 (dataset_dev.py:104-118)
+ *   out                 float [n][105][L]    bit-identical to the reference's float64 features after `.type(FloatTensor)`
+ * nsnp_hap_model_forward replaces LSTMNetwork.predict (HaplotypeModel/model_dev.py:133-143): x_pileup [n][105][33],
+ * x_haplotype [n][105][11] -> softmaxed genotype [n][10] / zygosity [n][3].  fp32.  Weights: PyTorch layouts, gate order i,f,g,o;
+ * index [encoder 0 pileup / 1 haplotype][layer 0..2][direction]. */
+typedef struct nsnp_hap_weights {
+    const float* w_ih[2][3][2];    /* [1024][105] (layer 0) / [1024][512] */
+    const float* w_hh[2][3][2];    /* [1024][256] */
+    const float* b_ih[2][3][2];    /* [1024] */
+    const float* b_hh[2][3][2];
+    const float* proj_w[2]; const float* proj_b[2];      /* output_proj [256][512], [256] */
+    const float* dense_w;  const float* dense_b;         /* [256][512], [256] */
+    const float* gt_w;     const float* gt_b;            /* [10][256], [10] */
+    const float* zy_w;     const float* zy_b;            /* [3][256], [3] */
+} nsnp_hap_weights_t;
+int nsnp_hap_features(const int32_t* seq_dev, const int32_t* bq_dev, const int32_t* mq_dev, const int32_t* hp_dev, const int32_t* refcode_dev,
+                      int64_t n, int32_t depth, int32_t L, float* out_dev, void* stream);
+size_t nsnp_hap_model_blob_bytes(void);
+int nsnp_hap_model_pack_weights(const nsnp_hap_weights_t* w, void* host_blob, size_t blob_bytes);
+size_t nsnp_hap_model_workspace_bytes(int64_t n);
+int nsnp_hap_model_forward(const void* blob_dev, const float* xp_dev, const float* xh_dev, int64_t n, float* gt_prob_dev, float* zy_prob_dev,
+                           void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* ---- per-kernel timing (bench.py) ---------------------------------------------------------------
  * When enabled, every kernel launch of this library is bracketed by cudaEventRecord on the launching stream.
  * nsnp_profile_read synchronises, adds the elapsed times per kernel slot into ms_out[NSNP_PROF_SLOTS] and

@@ -53,6 +53,12 @@ class ModelWeights(C.Structure):
     ]
 
 
+class HapWeights(C.Structure):
+    _fields_ = [("w_ih", C.c_void_p * 12), ("w_hh", C.c_void_p * 12), ("b_ih", C.c_void_p * 12), ("b_hh", C.c_void_p * 12),
+                ("proj_w", C.c_void_p * 2), ("proj_b", C.c_void_p * 2), ("dense_w", C.c_void_p), ("dense_b", C.c_void_p),
+                ("gt_w", C.c_void_p), ("gt_b", C.c_void_p), ("zy_w", C.c_void_p), ("zy_b", C.c_void_p)]
+
+
 class SynthCfg(C.Structure):
     _fields_ = [
         ("seed_ref", C.c_uint64), ("seed_var", C.c_uint64), ("seed_reads", C.c_uint64),
@@ -87,6 +93,11 @@ SYMBOLS = {
     "nsnp_model_workspace_bytes": (_SZ, [_I64]),
     "nsnp_pileup_model_forward": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _SZ, C.c_int, _P]),
     "nsnp_debug_lstm_tc_gates": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _I64, _P]),
+    "nsnp_hap_features": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P]),
+    "nsnp_hap_model_blob_bytes": (_SZ, []),
+    "nsnp_hap_model_pack_weights": (C.c_int, [C.POINTER(HapWeights), _P, _SZ]),
+    "nsnp_hap_model_workspace_bytes": (_SZ, [_I64]),
+    "nsnp_hap_model_forward": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
     "nsnp_profile_enable": (None, [C.c_int]),
     "nsnp_profile_read": (C.c_int, [_P, _P]),
     "nsnp_check_status": (C.c_int, [_P, _P]),

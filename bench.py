@@ -231,7 +231,7 @@ def main_ours(args):
     enc, fwd = load_weights()
     prec = _lib.PREC_FP32 if args.precision == "fp32" else _lib.PREC_F16X3
     model = PileupModelForward(PileupModelWeights(enc, fwd, device=dev), precision=prec)
-    runner = RegionRunner(eng, model)
+    runner = RegionRunner(eng, model, records=True)        # device-resident result = compact site records (fused s1 -> s2 hand-off)
     # few host cores per rank: host waits sleep on blocking events instead of spinning in cudaStreamSynchronize
     runner_e2e = RegionRunner(eng, model, records=True, blocking_sync=(os.cpu_count() or 1) <= 4 * world)
 
@@ -309,6 +309,21 @@ def main_ours(args):
         lib.nsnp_profile_enable(0)
         res["kernel_ms"] = {k: kms[i] for i, k in enumerate(_lib.PROF_SLOTS)}
         res["kernel_launches"] = {k: int(kln[i]) for i, k in enumerate(_lib.PROF_SLOTS)}
+        if rank == 0:
+            # the window-gather kernel of the dataset seam (B2), timed alone on the first region: it is no longer on the fused path
+            rgath = RegionRunner(eng, model, keep_windows=True)
+            o = rgath.run_device(dev_regions[0], ref, regions[0])
+            cnt = rgath._bufs["counts"][: regions[0].length * 18].view(regions[0].length, 18)
+            xg = torch.empty((o.n, 33, 18), dtype=torch.int32, device=dev); rb = torch.empty(o.n, dtype=torch.uint8, device=dev)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for it in range(4):
+                if it == 1:
+                    g0.record()
+                eng.gather(cnt, ref, regions[0].start, o.pos0, None, o.n, x_i32=xg, refbase=rb)
+            g1.record(); torch.cuda.synchronize()
+            res["gather_standalone"] = {"ms": g0.elapsed_time(g1) / 3, "sites": o.n}
+            del rgath, o, cnt, xg, rb
+            torch.cuda.empty_cache()
         if with_e2e:
             host_regions = [pinned(rd) for rd in dev_regions]
             h2d = sum(h.nbytes() for h in host_regions)
@@ -469,8 +484,15 @@ def main_ours(args):
     stages = {
         "pileup": hbm("pileup", alg["pileup"], traffic.get("pileup_tile_kernel", {}).get("dram_bytes_per_position", 0) * Lr or None),
         "select": hbm("select", 1.0 * Lr + 4.0 * n_sites),
-        "gather": hbm("gather", 4753.0 * n_sites, traffic.get("gather_kernel", {}).get("dram_bytes_per_site", 0) * n_sites or None),
     }
+    if main_res.get("gather_standalone"):
+        gs = main_res["gather_standalone"]
+        a = 4753.0 * gs["sites"] / (gs["ms"] * 1e-3) / 1e9
+        stages["gather"] = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak, "ms_per_launch": gs["ms"],
+                            "sites_per_launch": gs["sites"], "algorithmic_bytes_per_launch": 4753.0 * gs["sites"],
+                            "traffic": traffic.get("gather_kernel", {}).get("dram_bytes_per_site", 0) * gs["sites"] or None,
+                            "note": "the dataset-seam kernel (nsnp_gather_windows), timed alone on one region outside the timed step: the fused "
+                                    "path reads windows straight from the count tensor and never launches it"}
     # ---- roofline of the dominant kernel (largest share of the timed region), timed live with CUDA events around
     #      each of its launches on the launching stream (nsnp_profile_*); rank 0's kernels ----
     flop_per_site = {"lstm_layer0": 2 * 1385472.0, "lstm_layer1": 2 * 1671168.0, "tail_kernel": 2 * 55296.0}

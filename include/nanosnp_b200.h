@@ -156,6 +156,12 @@ size_t nsnp_model_workspace_bytes(int64_t n_sites);
 int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, const float* x_f32_dev,
                               int64_t n, const int32_t* n_dev, float* gt_prob_dev, float* zy_prob_dev,
                               void* workspace_dev, size_t workspace_bytes, int precision, void* stream);
+/* Same network, reading each site's window straight from the count tensor of its region: a window is the contiguous row span
+ * counts[pos - 16 .. pos + 16] (create_pileup_tensor, main.cpp:220-251), so the [n][33][18] tensor of the dataset seam need not
+ * be materialised between s1 and s2 (saves one 4.7 KB/site gather and its read-back).  NSNP_PREC_F16X3 only. */
+int nsnp_pileup_model_forward_sites(const void* blob_dev, const int32_t* counts_dev, int64_t region_start, int64_t region_len,
+                                    const int32_t* pos_dev, int64_t n, const int32_t* n_dev, float* gt_prob_dev, float* zy_prob_dev,
+                                    void* workspace_dev, size_t workspace_bytes, int precision, void* stream);
 #define NSNP_PREC_FP32    0   /* fp32 FFMA everywhere (parity path) */
 #define NSNP_PREC_F16X3   1   /* tcgen05 tensor-core path: fp16 hi/lo split operands (3 MMAs per product), fp32 accumulate */
 
@@ -233,6 +239,10 @@ typedef struct nsnp_site_record {        /* 32 bytes */
  * -(af_q + 3) = |AF| * 1e6 rounded like '%f', printed with a leading '-' */
 int nsnp_site_records(const float* gt_prob_dev, const float* zy_prob_dev, const int32_t* x_i32_dev, const uint8_t* refbase_dev,
                       const int32_t* pos_dev, int64_t n, const int32_t* n_dev, nsnp_site_record_t* rec_dev, void* stream);
+/* the same records with the centre row read from the count tensor and the reference base from the contig (no window tensor) */
+int nsnp_site_records_sites(const float* gt_prob_dev, const float* zy_prob_dev, const int32_t* counts_dev, int64_t region_start,
+                            const uint8_t* ref_dev, const int32_t* pos_dev, int64_t n, const int32_t* n_dev, nsnp_site_record_t* rec_dev,
+                            void* stream);
 /* host: text of all records of consecutive batch_size-site batches from compact records (same bytes as the two below) */
 int64_t nsnp_vcf_format_contig_records(const char* contig, int64_t n, const nsnp_site_record_t* rec, int64_t batch_size,
                                        int n_threads, char* out, int64_t out_capacity);

@@ -303,9 +303,31 @@ size_t nsnp_model_workspace_bytes(int64_t n_sites) {
     return (size_t)ch * kT * 128 * sizeof(float) + (size_t)np * 128 * sizeof(float) + 256;
 }
 
+static int model_forward(const void* blob_dev, const int32_t* x_i32_dev, const float* x_f32_dev, int64_t n,
+                         const int32_t* n_dev, float* gt_prob_dev, float* zy_prob_dev, void* workspace_dev,
+                         size_t workspace_bytes, int precision, const int32_t* pos_dev, int64_t pos_bias, void* stream_);
+
 int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, const float* x_f32_dev, int64_t n,
                               const int32_t* n_dev, float* gt_prob_dev, float* zy_prob_dev, void* workspace_dev,
                               size_t workspace_bytes, int precision, void* stream_)
+{
+    return model_forward(blob_dev, x_i32_dev, x_f32_dev, n, n_dev, gt_prob_dev, zy_prob_dev, workspace_dev, workspace_bytes, precision, nullptr, 0, stream_);
+}
+
+int nsnp_pileup_model_forward_sites(const void* blob_dev, const int32_t* counts_dev, int64_t region_start, int64_t region_len,
+                                    const int32_t* pos_dev, int64_t n, const int32_t* n_dev, float* gt_prob_dev, float* zy_prob_dev,
+                                    void* workspace_dev, size_t workspace_bytes, int precision, void* stream_)
+{
+    if (n == 0) return NSNP_OK;
+    if (!counts_dev || !pos_dev || region_len < NSNP_WINDOW) return set_error(NSNP_E_INVALID, "nsnp_pileup_model_forward_sites: bad argument");
+    if (precision != NSNP_PREC_F16X3) return set_error(NSNP_E_UNSUPPORTED, "window reads from the count tensor are built for NSNP_PREC_F16X3; gather the windows for the fp32 path");
+    return model_forward(blob_dev, counts_dev, nullptr, n, n_dev, gt_prob_dev, zy_prob_dev, workspace_dev, workspace_bytes, precision, pos_dev,
+                         region_start + NSNP_FLANK, stream_);
+}
+
+static int model_forward(const void* blob_dev, const int32_t* x_i32_dev, const float* x_f32_dev, int64_t n,
+                         const int32_t* n_dev, float* gt_prob_dev, float* zy_prob_dev, void* workspace_dev,
+                         size_t workspace_bytes, int precision, const int32_t* pos_dev, int64_t pos_bias, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return NSNP_OK;          // empty batch: nothing to launch (pointers of empty tensors may be null)
@@ -336,11 +358,11 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
     for (int64_t off = 0; off < n; off += ch) {
         const int64_t m = (n - off) < ch ? (n - off) : ch;
         const int32_t* nd = (off == 0 && n <= ch) ? n_dev : nullptr;
-        const int32_t* xi = x_i32_dev ? x_i32_dev + off * kT * kF : nullptr;
+        const int32_t* xi = x_i32_dev ? (pos_dev ? x_i32_dev : x_i32_dev + off * kT * kF) : nullptr;       // pos_dev: the count tensor itself
         const float* xf = x_f32_dev ? x_f32_dev + off * kT * kF : nullptr;
         dim3 g0((unsigned)((m + Cfg<0>::S - 1) / Cfg<0>::S), 2), g1((unsigned)((m + Cfg<1>::S - 1) / Cfg<1>::S), 2);
         if (precision == NSNP_PREC_F16X3) {
-            if (int e = launch_lstm_tc(blob_dev, xi, xf, h0, h16 + off * 128, m, stream)) return e;
+            if (int e = launch_lstm_tc(blob_dev, xi, xf, h0, h16 + off * 128, m, pos_dev ? pos_dev + off : nullptr, pos_bias, stream)) return e;
             if (tail_tc) continue;                   // one tensor-core tail launch over all chunks below
         } else {
             { ProfScope prof(NSNP_PROF_LSTM0, stream); lstm_dir_kernel<0><<<g0, 256, smem0, stream>>>(blob, xi, xf, nullptr, h0, m, nd); }

@@ -517,8 +517,10 @@ struct P2Smem {
 
 __global__ void __launch_bounds__(kP2Threads, 1)
 lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict__ xi, const float* __restrict__ xf,
-                   __half* __restrict__ h0_out, int64_t n)
+                   __half* __restrict__ h0_out, int64_t n, const int32_t* __restrict__ pos, int64_t pos_bias)
 {
+    // pos != nullptr: xi is the region's count tensor [L][18] and site j's window is its contiguous row span starting at
+    // pos[j] - pos_bias (pos_bias = region_start + 16): the [n][33][18] feature tensor is never materialised
     using S = P2Smem;
     constexpr int K = kTcK0, IN = kTcIn0, KB = K / 16, RB = 128, UB = 4;
     constexpr uint32_t LBO_A = kRows * 16, LBO_B = RB * 16, SBO = 128;
@@ -574,12 +576,15 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
         for (int u = 0; u < 8; ++u) c[j][u] = 0.f;
 
     int2 xraw[8];
+    int64_t win0 = 0;                                           // first row of this thread's window in the count tensor
     auto load_x = [&](int gstep) {                              // count row of stream element gstep
         const int qi = gstep / kT, st = gstep - qi * kT;
         const int t = dir == 0 ? st : (kT - 1 - st);
         int64_t site = tile_of(qi) * kRows + row;
         if (site >= n) site = n - 1;
-        const int2* g = reinterpret_cast<const int2*>(xi ? (const void*)(xi + (site * kT + t) * kF) : (const void*)(xf + (site * kT + t) * kF));
+        if (pos && st == 0) win0 = (int64_t)__ldg(pos + site) - pos_bias;
+        const int2* g = pos ? reinterpret_cast<const int2*>(xi + (win0 + t) * kF)
+                            : reinterpret_cast<const int2*>(xi ? (const void*)(xi + (site * kT + t) * kF) : (const void*)(xf + (site * kT + t) * kF));
         if (sub == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) xraw[j] = ldg_nc_volatile(g + j);
@@ -713,7 +718,7 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
     if (threadIdx.x < 32) tmem_dealloc<2>(*tmem_slot, 512);
 }
 
-int launch_l0_pair2(const void* blob, const int32_t* xi, const float* xf, void* h0_out, int64_t m, cudaStream_t stream) {
+int launch_l0_pair2(const void* blob, const int32_t* xi, const float* xf, void* h0_out, int64_t m, const int32_t* pos, int64_t pos_bias, cudaStream_t stream) {
     using S = P2Smem;
     static bool attr_done = false;
     if (!attr_done) {
@@ -733,7 +738,7 @@ int launch_l0_pair2(const void* blob, const int32_t* xi, const float* xf, void* 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, lstm0_pair2_kernel, (const unsigned char*)blob, xi, xf, (__half*)h0_out, m);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, lstm0_pair2_kernel, (const unsigned char*)blob, xi, xf, (__half*)h0_out, m, pos, pos_bias);
     if (e != cudaSuccess) return set_error(NSNP_E_CUDA, "lstm0_pair2_kernel: %s", cudaGetErrorString(e));
     return NSNP_OK;
 }
@@ -982,13 +987,14 @@ int launch_tail_tc(const void* blob, const float* h16, int64_t n_max, const int3
     return cuda_status("tail_tc_kernel");
 }
 
-int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, cudaStream_t stream) {
+int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, const int32_t* pos, int64_t pos_bias, cudaStream_t stream) {
     // layer 0: CTA pairs share W (53 KB each) so two CTAs fit per SM and one CTA's MMAs overlap the other's epilogue
     {
         ProfScope prof(NSNP_PROF_LSTM0, stream);
         // default: two alternating groups per CTA (lstm0_pair2_kernel); NSNP_L0_VARIANT=0 selects two independent CTAs per SM
         static const int variant = [] { const char* v = getenv("NSNP_L0_VARIANT"); return v ? atoi(v) : 1; }();
-        if (int e = variant == 1 ? launch_l0_pair2(blob, xi, xf, h0, m, stream)
+        if (pos && variant != 1) return set_error(NSNP_E_UNSUPPORTED, "window reads from the count tensor need the default layer-0 kernel");
+        if (int e = variant == 1 ? launch_l0_pair2(blob, xi, xf, h0, m, pos, pos_bias, stream)
                                  : launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e;
     }
     // layer 1: W only fits split across a CTA pair (2 x 104 KB); one CTA per SM, 16 warps for the epilogue

@@ -35,8 +35,10 @@ __device__ __forceinline__ bool score_q100(float p, double kScale, int32_t* q100
 __global__ void __launch_bounds__(256) site_record_kernel(const float* __restrict__ gt, const float* __restrict__ zy,
                                                          const int32_t* __restrict__ x, const uint8_t* __restrict__ refbase,
                                                          const int32_t* __restrict__ pos0, int64_t n, const int32_t* __restrict__ n_dev,
-                                                         nsnp_site_record_t* __restrict__ rec, double kScale)
+                                                         nsnp_site_record_t* __restrict__ rec, double kScale,
+                                                         const int32_t* __restrict__ counts, int64_t region_start, const uint8_t* __restrict__ ref)
 {
+    // counts != nullptr: the centre row and the reference base come straight from the count tensor / the contig (no window tensor)
     if (n_dev) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         const float* gp = gt + j * NSNP_GT_CLASSES; const float* zp = zy + j * NSNP_ZY_CLASSES;
@@ -47,10 +49,12 @@ __global__ void __launch_bounds__(256) site_record_kernel(const float* __restric
         if (zp[1] > zm) { zm = zp[1]; zi = 1; }
         if (zp[2] > zm) { zm = zp[2]; zi = 2; }
         nsnp_site_record_t r;
-        r.gt = (uint8_t)gi; r.zy = (uint8_t)zi; r.flags = 0; r.ref = refbase[j];
+        uint8_t rb;
+        if (counts) { rb = ref[pos0[j]]; if (rb >= 'a' && rb <= 'z') rb = (uint8_t)(rb - 32); } else rb = refbase[j];
+        r.gt = (uint8_t)gi; r.zy = (uint8_t)zi; r.flags = 0; r.ref = rb;
         r.pos1 = pos0[j] + 1; r.p_gt = gm; r.p_zy = zm; r.q100_gt = 0; r.q100_zy = 0; r.depth = 0; r.af_q = 0;
         // centre row, channels [A C G T a c g t] (predict.py:63)
-        const int32_t* row = x + (j * NSNP_WINDOW + NSNP_FLANK) * NSNP_CHANNELS;
+        const int32_t* row = counts ? counts + ((int64_t)pos0[j] - region_start) * NSNP_CHANNELS : x + (j * NSNP_WINDOW + NSNP_FLANK) * NSNP_CHANNELS;
         float cov[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { cov[k] = (float)row[k]; cov[4 + k] = (float)row[9 + k]; }
@@ -105,6 +109,22 @@ extern "C" int nsnp_site_records(const float* gt_prob_dev, const float* zy_prob_
     int64_t blocks = (n + 255) / 256; if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     ProfScope prof(NSNP_PROF_RECORDS, stream);
     const double kScale = -10.0 * (1.0 / log(10.0));          // -10 * log(e, 10) exactly as the host formatter (vcf.cu) forms it
-    site_record_kernel<<<(int)blocks, 256, 0, stream>>>(gt_prob_dev, zy_prob_dev, x_i32_dev, refbase_dev, pos_dev, n, n_dev, rec_dev, kScale);
+    site_record_kernel<<<(int)blocks, 256, 0, stream>>>(gt_prob_dev, zy_prob_dev, x_i32_dev, refbase_dev, pos_dev, n, n_dev, rec_dev, kScale, nullptr, 0, nullptr);
+    return cuda_status("site_record_kernel");
+}
+
+extern "C" int nsnp_site_records_sites(const float* gt_prob_dev, const float* zy_prob_dev, const int32_t* counts_dev, int64_t region_start,
+                                       const uint8_t* ref_dev, const int32_t* pos_dev, int64_t n, const int32_t* n_dev, nsnp_site_record_t* rec_dev,
+                                       void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return NSNP_OK;
+    if (!gt_prob_dev || !zy_prob_dev || !counts_dev || !ref_dev || !pos_dev || !rec_dev || n < 0)
+        return set_error(NSNP_E_INVALID, "nsnp_site_records_sites: null argument");
+    if (nsnp_device_count() == 0) return set_error(NSNP_E_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    int64_t blocks = (n + 255) / 256; if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    ProfScope prof(NSNP_PROF_RECORDS, stream);
+    const double kScale = -10.0 * (1.0 / log(10.0));
+    site_record_kernel<<<(int)blocks, 256, 0, stream>>>(gt_prob_dev, zy_prob_dev, nullptr, nullptr, pos_dev, n, n_dev, rec_dev, kScale, counts_dev, region_start, ref_dev);
     return cuda_status("site_record_kernel");
 }

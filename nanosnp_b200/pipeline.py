@@ -126,6 +126,16 @@ class PileupEngine:
                                                   rec.data_ptr(), _stream(self.device)))
         return rec[:n]
 
+    def site_records_from_counts(self, gt: torch.Tensor, zy: torch.Tensor, counts: torch.Tensor, region_start: int, ref: torch.Tensor,
+                                 pos: torch.Tensor, n: int, rec: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """site_records with the centre row read from the count tensor and the reference base from the contig."""
+        if rec is None:
+            rec = torch.empty((max(n, 1), 32), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nsnp_site_records_sites(gt.data_ptr(), zy.data_ptr(), counts.data_ptr(), region_start, ref.data_ptr(),
+                                                        pos.data_ptr(), n, 0, rec.data_ptr(), _stream(self.device)))
+        return rec[:n]
+
     # -- s1 for a whole region ---------------------------------------------------------------------
     def candidate_windows(self, reads: PackedReads, ref: torch.Tensor, region_start: int = 0, region_len: Optional[int] = None,
                           emit_start: Optional[int] = None, emit_end: Optional[int] = None, capacity: Optional[int] = None):
@@ -205,4 +215,21 @@ class PileupModelForward:
             _lib.check(self.lib.nsnp_pileup_model_forward(self.w.blob.data_ptr(), xi, xf, n, 0 if n_dev is None else n_dev.data_ptr(),
                                                           gt.data_ptr(), zy.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                                           self.precision, _stream(self.device)))
+        return gt, zy
+
+    def from_counts(self, counts: torch.Tensor, region_start: int, pos: torch.Tensor, n: int, gt=None, zy=None):
+        """The same forward pass with every site's window read straight from the region's count tensor [L,18] (a window is the
+        contiguous row span counts[pos-16 .. pos+16]): no [n,33,18] tensor is materialised.  Tensor-core path only."""
+        assert counts.is_cuda and counts.is_contiguous() and counts.dtype == torch.int32 and self.precision == _lib.PREC_F16X3
+        if gt is None:
+            gt = torch.empty((n, _lib.GT_CLASSES), dtype=torch.float32, device=self.device)
+        if zy is None:
+            zy = torch.empty((n, _lib.ZY_CLASSES), dtype=torch.float32, device=self.device)
+        need = self.lib.nsnp_model_workspace_bytes(n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nsnp_pileup_model_forward_sites(self.w.blob.data_ptr(), counts.data_ptr(), region_start, int(counts.shape[0]),
+                                                                pos.data_ptr(), n, 0, gt.data_ptr(), zy.data_ptr(), self._ws.data_ptr(),
+                                                                self._ws.numel(), self.precision, _stream(self.device)))
         return gt, zy

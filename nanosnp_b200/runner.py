@@ -65,7 +65,7 @@ class StageTimer:
 
 class RegionRunner:
     def __init__(self, engine: PileupEngine, model: PileupModelForward, keep_windows: bool = False, records: bool = False,
-                 blocking_sync: bool = False):
+                 blocking_sync: bool = False, fused: bool = True):
         """blocking_sync: host waits sleep on a blocking CUDA event instead of spinning in cudaStreamSynchronize.  A
         spinning wait costs one host core per GPU for the whole run; with few cores per GPU (8 ranks on 16 cores) that
         core is better spent on VCF text assembly.  Spinning wakes up a little faster, so it stays the default."""
@@ -75,6 +75,7 @@ class RegionRunner:
         self.device = engine.device
         self.keep_windows = keep_windows
         self.records = records            # numeric record logic on the GPU: 32 bytes/site leave the device instead of 133
+        self.fused = fused                # records mode: no window tensor between s1 and s2 (windows are row spans of the counts)
         self._bufs: Dict[str, torch.Tensor] = {}
         self.launches = 0          # kernels of this library launched so far
 
@@ -114,10 +115,26 @@ class RegionRunner:
         else:
             n = int(n_dev.item())                # the one host sync per region
         eng.check_status()
-        x = self._buf("x", (max(n, 1), _lib.WINDOW, _lib.CHANNELS), torch.int32)[:n]
-        refbase = self._buf("refbase", (max(n, 1),), torch.uint8)[:n]
         gt = self._buf("gt", (max(n, 1), _lib.GT_CLASSES), torch.float32)[:n]
         zy = self._buf("zy", (max(n, 1), _lib.ZY_CLASSES), torch.float32)[:n]
+        # fused s1 -> s2 hand-off: the model (and the record kernel) read each site's rows straight from the count tensor, the
+        # [n,33,18] window tensor of the dataset seam is only materialised when the caller wants it (keep_windows) or for the
+        # fp32 parity path
+        fused = self.fused and self.records and not self.keep_windows and self.model.precision == _lib.PREC_F16X3
+        if fused:
+            if n:
+                timer.start("model")
+                self.model.from_counts(counts, region.start, pos, n, gt=gt, zy=zy)
+                timer.stop()
+                chunks = -(-n // 75776)
+                self.launches += 2 * chunks + 1
+            rec = self._buf("rec", (max(n, 1), 32), torch.uint8)[:n]
+            if n:
+                eng.site_records_from_counts(gt, zy, counts, region.start, ref, pos, n, rec=rec)
+                self.launches += 1
+            return RegionOutput(n, pos[:n], None, None, gt, zy, None, rec)
+        x = self._buf("x", (max(n, 1), _lib.WINDOW, _lib.CHANNELS), torch.int32)[:n]
+        refbase = self._buf("refbase", (max(n, 1),), torch.uint8)[:n]
         if n:
             timer.start("gather")
             eng.gather(counts, ref, region.start, pos, n_dev, n, x_i32=x, refbase=refbase)

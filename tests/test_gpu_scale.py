@@ -192,6 +192,13 @@ def test_bench_region_s1_bit_exact_and_model_at_scale(rig, workload, orc, tmp_pa
                                     1000, 8, C.addressof(b2), cap)
     assert n1 > 0 and n1 == n2 and b1.raw[:n1] == b2.raw[:n2]
 
+    # ---- fused s1 -> s2 hand-off (windows read straight from the count tensor, no gather) == the window-tensor path ----
+    from nanosnp_b200.runner import RegionRunner
+    rec_f = RegionRunner(rig["eng"], rig["tc"], records=True).run_device(rd, w["ref"], rg).rec.clone()
+    rec_u = RegionRunner(rig["eng"], rig["tc"], records=True, fused=False).run_device(rd, w["ref"], rg).rec.clone()
+    torch.cuda.synchronize()
+    assert rec_f.shape[0] == out.n and torch.equal(rec_f, rec_u)
+
 
 def test_bench_last_region_tail_bit_exact(rig, workload, orc, tmp_path):
     """Last region of the contig (positions near 1e8, reads truncated at the contig end): last 2 Mb bit-exact."""

@@ -198,7 +198,7 @@ def main_ours(args):
     from nanosnp_b200.caller import ShardedVcfWriter
     from nanosnp_b200.pipeline import PileupEngine, PileupModelForward, PileupModelWeights
     from nanosnp_b200.predict_io import ContigVcfAssembler
-    from nanosnp_b200.reads import FIELDS, PackedReads
+    from nanosnp_b200.reads import FIELDS, PackedReads, cigar16
     from nanosnp_b200.runner import RegionRunner, StageTimer
     from nanosnp_b200.shard import assign_lpt, plan_regions
     from nanosnp_b200.synth import SynthConfig, generate_device
@@ -241,6 +241,7 @@ def main_ours(args):
         torch.cuda.synchronize()
 
     def pinned(rd):
+        rd = cigar16(rd)                                       # host hand-off ships uint16 CIGAR words (every length < 4096 here)
         return PackedReads(*[None if getattr(rd, f) is None else getattr(rd, f).cpu().pin_memory() for f in FIELDS])
 
     def time_device(work, steps, timer=None, profile=False):
@@ -412,9 +413,11 @@ def main_ours(args):
             writer = ShardedVcfWriter(contigs, regions, 1000, dev)
 
             def step_host(to_file=args.write_vcf):
-                recs = runner_e2e.run_host_collect(host_regions, rgs, refs)
-                info.update(writer.write(out_path if to_file else None, header, dict(zip(idx, recs))))
-                return sum(int(r.shape[0]) for r in recs)
+                # the text of region k is made (deferred batch heads) and copied to the host while region k+1 computes
+                writer.begin()
+                ns = runner_e2e.run_host_collect(host_regions, rgs, refs, on_region=lambda k, o: writer.add_region(idx[k], o.rec))
+                info.update(writer.finish(out_path if to_file else None, header))
+                return sum(ns)
             e2e_ms, n_e2e = time_e2e(step_host, steps)
             step_host(True)                                     # outside the timed region: the file, for the checksum below
             res["e2e"] = {"ms": e2e_ms, "sites": n_e2e, "h2d": h2d, "d2h": 0, "vcf_bytes": info.get("vcf_bytes", 0)}
@@ -560,8 +563,9 @@ def main_ours(args):
                                 "write) -> D2H of the VCF text through RegionRunner.run_host_text; the host only patches the flagged QUAL rounding ties "
                                 "(~4 per million records); copies overlap the kernels of the neighbouring regions; reference FASTA and weights resident"
                                 if world == 1 else
-                                "per rank: pinned host read arrays -> H2D -> kernels -> site records kept on the GPU; then all-reduce of region site counts "
-                                "and batch heads, VCF text kernels per region, D2H of the text, all-reduce of the text lengths: the timed region ends when "
+                                "per rank: pinned host read arrays (uint16 CIGAR words) -> H2D -> kernels -> site records -> VCF text kernels with deferred "
+                                "batch heads -> D2H of region k's text while region k+1 computes; after the last region: all-reduce of region site counts, "
+                                "batch heads and text lengths, one-character ALT fix-ups and QUAL tie fix-ups on the host: the timed region ends when "
                                 "every rank holds its ordered text segments and their file offsets in pinned host memory (the same end point as at N = 1, "
                                 "where the text chunks are handed to the caller's write()); placing them into ONE file (caller.ShardedVcfWriter, shared "
                                 "mapping) is timed only with --write-vcf; the file of one step is still produced and checksummed (config.vcf_sha256); "

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NSNP_ABI_VERSION 1
+#define NSNP_ABI_VERSION 2
 
 /* error codes */
 #define NSNP_OK               0
@@ -65,13 +65,16 @@ typedef struct nsnp_reads {
     const uint16_t* flag;       /* [n] SAM flag; reads with (flag & excl_flags) are dropped */
     const uint8_t*  mapq;       /* [n] reads with mapq < min_mapq are dropped */
     const int64_t*  cigar_off;  /* [n+1] index of the read's first op in cigar[] */
-    const uint32_t* cigar;      /* BAM encoding: len<<4 | op, op = MIDNSHP=X -> 0..8 */
+    const uint32_t* cigar;      /* BAM encoding: len<<4 | op, op = MIDNSHP=X -> 0..8 (uint16 words when cigar_bits == 16) */
     const int64_t*  seq_off;    /* [n] index (in bases) of the read's first SEQ base in seq2/nmask */
     const uint8_t*  seq2;       /* 2-bit bases A0 C1 G2 T3: base k lives in byte k>>2, bits 2*(k&3) */
     const uint8_t*  nmask;      /* optional (may be NULL): bit (k&7) of byte k>>3 set => base k is N */
     const uint8_t*  qual;       /* optional, unused: s1/s2 run with --min-BQ 0 and never read qualities */
     int64_t         n_cigar;    /* total ops  (= cigar_off[n]) */
     int64_t         n_bases;    /* capacity of seq2/nmask in bases */
+    int32_t         cigar_bits; /* 32 (or 0): cigar[] holds uint32 words; 16: the same values as uint16 (every length < 4096) --
+                                   what a host decoder ships when it can: halves the CIGAR bytes on the wire */
+    int32_t         reserved;
 } nsnp_reads_t;
 
 /* s1 parameters; defaults = make_predict_data.sh:117-125 */
@@ -263,6 +266,18 @@ int nsnp_vcf_text_records(const char* contig, const nsnp_site_record_t* rec_dev,
                           int64_t batch_size, const uint8_t* heads_dev, char* text_dev, int64_t text_capacity, int64_t* text_len_dev,
                           void* workspace_dev, size_t workspace_bytes, void* stream);
 int nsnp_vcf_text_ties(const void* workspace_dev, int64_t n, const void** count_dev, const void** entries_dev, int32_t* capacity);
+/* Deferred batch heads (multi-GPU streaming): the text of a region is made as soon as its records exist -- record lengths do not
+ * depend on the heads -- with the one ALT character of every "fix-up" record (predict.py:101-131) left as '?' and listed
+ * (16-byte entries: int64 text offset, int32 record index, u8 zygosity, u8 ref base); once the contig's batch-head table is
+ * complete the host writes those characters (nsnp_vcf_text_patch_heads), then applies the tie fix-up with the table
+ * (nsnp_vcf_text_patch_ties_at).  The result is byte-identical to nsnp_vcf_text_records with the table. */
+int nsnp_vcf_text_records_deferred(const char* contig, const nsnp_site_record_t* rec_dev, int64_t n, const int32_t* n_dev, char* text_dev,
+                                   int64_t text_capacity, int64_t* text_len_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+int nsnp_vcf_text_fixups(const void* workspace_dev, int64_t n, const void** count_dev, const void** entries_dev);
+int nsnp_vcf_text_patch_heads(char* text_host, int64_t text_len, const void* fix_host, int32_t n_fix, int64_t first_index, int64_t batch_size,
+                              const uint8_t* heads_table, int32_t* n_drop);
+int64_t nsnp_vcf_text_patch_ties_at(const char* contig, char* text_host, int64_t text_len, int64_t text_capacity, const void* ties_host,
+                                    int32_t n_ties, int64_t first_index, int64_t batch_size, const uint8_t* heads_table);
 int nsnp_vcf_batch_heads(const nsnp_site_record_t* rec_dev, int64_t n, const int32_t* n_dev, int64_t first_index, int64_t batch_size,
                          uint8_t* heads_dev, void* stream);
 int64_t nsnp_vcf_text_patch_ties(const char* contig, char* text_host, int64_t text_len, int64_t text_capacity, const void* ties_host,

@@ -33,7 +33,7 @@ class Reads(C.Structure):
         ("pos", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p),
         ("cigar_off", C.c_void_p), ("cigar", C.c_void_p),
         ("seq_off", C.c_void_p), ("seq2", C.c_void_p), ("nmask", C.c_void_p), ("qual", C.c_void_p),
-        ("n_cigar", C.c_int64), ("n_bases", C.c_int64),
+        ("n_cigar", C.c_int64), ("n_bases", C.c_int64), ("cigar_bits", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -111,6 +111,10 @@ SYMBOLS = {
     "nsnp_vcf_text_capacity": (_I64, [_I64, C.c_char_p]),
     "nsnp_vcf_text_records": (C.c_int, [C.c_char_p, _P, _I64, _P, _I64, _I64, _P, _P, _I64, _P, _P, _SZ, _P]),
     "nsnp_vcf_text_ties": (C.c_int, [_P, _I64, _P, _P, _P]),
+    "nsnp_vcf_text_records_deferred": (C.c_int, [C.c_char_p, _P, _I64, _P, _P, _I64, _P, _P, _SZ, _P]),
+    "nsnp_vcf_text_fixups": (C.c_int, [_P, _I64, _P, _P]),
+    "nsnp_vcf_text_patch_heads": (C.c_int, [_P, _I64, _P, _I32, _I64, _I64, _P, _P]),
+    "nsnp_vcf_text_patch_ties_at": (_I64, [C.c_char_p, _P, _I64, _I64, _P, _I32, _I64, _I64, _P]),
     "nsnp_vcf_batch_heads": (C.c_int, [_P, _I64, _P, _I64, _I64, _P, _P]),
     "nsnp_vcf_text_patch_ties": (_I64, [C.c_char_p, _P, _I64, _I64, _P, _I32]),
     "nsnp_vcf_format_records_at": (_I64, [C.c_char_p, _P, _I64, _I64, _I64, _P, _P, _I64]),
@@ -152,7 +156,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here = ABI mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.nsnp_abi_version() != 1:
+    if lib.nsnp_abi_version() != 2:
         raise ImportError("nanosnp_b200: ABI version mismatch between _lib.py and the shared object")
     _lib = lib
     return lib

@@ -322,6 +322,14 @@ class ShardedVcfWriter:
                     raise _lib.NsnpError(_lib.E_WORKSPACE, "VCF text buffer too small")
                 texts[i] = buf[:w].tobytes()
         mark("patch")
+        return self._place(out_path, header, texts, counts, n_reg, world, rank, mark, tr)
+
+    def _place(self, out_path, header, texts, counts, n_reg, world, rank, mark=None, tr=None):
+        import torch.distributed as dist
+        if mark is None:
+            import time
+            tr = [("start", time.perf_counter())]
+            mark = lambda name: tr.append((name, time.perf_counter()))
         # 4. offsets, ordered file
         lens_t = torch.zeros(n_reg, dtype=torch.int64)
         for i, t in texts.items():
@@ -380,6 +388,181 @@ class ShardedVcfWriter:
             import sys
             print("ShardedVcfWriter " + " ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.1f}ms" for a, b in zip(tr[:-1], tr[1:])), file=sys.stderr)
         return {"sites": int(counts.sum()), "vcf_bytes": int(offs[-1]) - len(header), "regions": n_reg, "world": world}
+
+
+    # ---- streaming form: text while the regions are still being computed ------------------------------------------------
+    # begin() / add_region(i, rec) right after region i's kernels were enqueued / finish(out_path, header).  A region's text is
+    # made at once with deferred batch heads (nsnp_vcf_text_records_deferred) and copied to pinned host memory while the next
+    # region computes; after the last region only the counts / head table / length all-reduces, the one-character ALT fix-ups
+    # and the tie fix-ups remain.  Same bytes as write().
+    def begin(self):
+        self._st = {"idx": [], "recs": [], "off": [], "len": [], "fix": [], "ties": [], "pending": None, "k": 0, "text_used": 0,
+                    "fix_used": 0, "tie_used": 0}
+        if not hasattr(self, "_down"):
+            self._down = torch.cuda.Stream(self.device)
+
+    def _stage(self, key, used, extra, dtype=torch.uint8):
+        """pinned staging that keeps its content when it grows"""
+        t = self._host.get(key)
+        if t is None or t.numel() < used + extra:
+            self._down.synchronize()
+            n = max(int((used + extra) * 1.5), 64 << 20 if key == "s_text" else 1 << 20)
+            nt = torch.empty(n, dtype=dtype).pin_memory()
+            if t is not None and used:
+                nt[:used].copy_(t[:used])
+            self._host[key] = t = nt
+        return t
+
+    def _collect_pending(self):
+        st = self._st
+        p = st["pending"]
+        if p is None:
+            return
+        st["pending"] = None
+        i, n, bufs, ev, cnt_off, ent_off, fcnt_off, fent_off = p
+        ev.synchronize()
+        meta = self._hbuf("s_meta", 8, torch.int64)
+        cnts = self._hbuf("s_cnts", 8, torch.int32)
+        with torch.cuda.stream(self._down):
+            meta[:1].copy_(bufs["meta"][:1], non_blocking=True)
+            cnts[0:1].copy_(bufs["ws"][cnt_off:cnt_off + 4].view(torch.int32), non_blocking=True)
+            cnts[1:2].copy_(bufs["ws"][fcnt_off:fcnt_off + 4].view(torch.int32), non_blocking=True)
+        self._down.synchronize()
+        ln, nt, nf = int(meta[0]), int(cnts[0]), int(cnts[1])
+        if ln > bufs["text"].numel() or nt > 4096 or nf > n:
+            raise _lib_mod().NsnpError(-4, f"VCF text buffers too small for region {i} ({ln} bytes, {nt} ties, {nf} fix-ups)")
+        slack = 64
+        text_h = self._stage("s_text", st["text_used"], ln + slack)
+        fix_h = self._stage("s_fix", st["fix_used"], 16 * nf)
+        tie_h = self._stage("s_tie", st["tie_used"], 64 * nt)
+        with torch.cuda.stream(self._down):
+            if ln:
+                text_h[st["text_used"]:st["text_used"] + ln].copy_(bufs["text"][:ln], non_blocking=True)
+            if nf:
+                fix_h[st["fix_used"]:st["fix_used"] + 16 * nf].copy_(bufs["ws"][fent_off:fent_off + 16 * nf], non_blocking=True)
+            if nt:
+                tie_h[st["tie_used"]:st["tie_used"] + 64 * nt].copy_(bufs["ws"][ent_off:ent_off + 64 * nt], non_blocking=True)
+            done = torch.cuda.Event(); done.record(self._down)
+        bufs["free"] = done                                     # the device buffers may be overwritten once this copy is done
+        st["off"].append(st["text_used"]); st["len"].append(ln)
+        st["fix"].append((st["fix_used"], nf)); st["ties"].append((st["tie_used"], nt))
+        st["text_used"] += ln + slack; st["fix_used"] += 16 * nf; st["tie_used"] += 64 * nt
+
+    def add_region(self, i: int, rec: torch.Tensor):
+        """rec: uint8 [n,32] device records of region i, just enqueued on the current stream (the buffer may be reused afterwards)."""
+        import ctypes as C
+        lib = self.lib
+        st = self._st
+        self._collect_pending()
+        n = int(rec.shape[0])
+        st["idx"].append(i)
+        st["recs"].append(rec.clone())
+        if n == 0:
+            st["off"].append(st["text_used"]); st["len"].append(0); st["fix"].append((st["fix_used"], 0)); st["ties"].append((st["tie_used"], 0))
+            return
+        contig = self.contigs[self.regions[i].contig_index][0].encode()
+        bufs = self._dev.setdefault(("stream", st["k"] % 2), {})
+        st["k"] += 1
+        cap = int(lib.nsnp_vcf_text_capacity(n, contig)); wsb = int(lib.nsnp_vcf_text_workspace_bytes(n))
+        if "free" in bufs:
+            torch.cuda.current_stream(self.device).wait_event(bufs["free"])
+        if "text" not in bufs or bufs["text"].numel() < cap:
+            bufs["text"] = torch.empty(int(cap * 1.2) + 256, dtype=torch.uint8, device=self.device)
+        if "ws" not in bufs or bufs["ws"].numel() < wsb:
+            bufs["ws"] = torch.empty(int(wsb * 1.2) + 256, dtype=torch.uint8, device=self.device)
+        if "meta" not in bufs:
+            bufs["meta"] = torch.zeros(2, dtype=torch.int64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib_mod().check(lib.nsnp_vcf_text_records_deferred(contig, st["recs"][-1].data_ptr(), n, 0, bufs["text"].data_ptr(), bufs["text"].numel(),
+                                                                bufs["meta"].data_ptr(), bufs["ws"].data_ptr(), bufs["ws"].numel(), stream))
+        cp = C.c_void_p(); ep = C.c_void_p(); cap_t = C.c_int32(0); fc = C.c_void_p(); fe = C.c_void_p()
+        lib.nsnp_vcf_text_ties(bufs["ws"].data_ptr(), n, C.byref(cp), C.byref(ep), C.byref(cap_t))
+        lib.nsnp_vcf_text_fixups(bufs["ws"].data_ptr(), n, C.byref(fc), C.byref(fe))
+        base = bufs["ws"].data_ptr()
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(self.device))
+        st["pending"] = (i, n, bufs, ev, cp.value - base, ep.value - base, fc.value - base, fe.value - base)
+
+    def finish(self, out_path: Optional[str], header: bytes) -> dict:
+        import ctypes as C
+        import torch.distributed as dist
+        lib, regions, contigs, batch = self.lib, self.regions, self.contigs, self.batch
+        st = self._st
+        self._collect_pending()
+        self._down.synchronize()
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        n_reg = len(regions)
+        counts = torch.zeros(n_reg, dtype=torch.int64)
+        for i, rec in zip(st["idx"], st["recs"]):
+            counts[i] = int(rec.shape[0])
+        counts = _all_reduce(counts, dist.ReduceOp.SUM if world > 1 else None)
+        first = [0] * n_reg
+        tot = {}
+        for i, rg in enumerate(regions):
+            first[i] = tot.get(rg.contig_index, 0)
+            tot[rg.contig_index] = first[i] + int(counts[i])
+        nb = {ci: (n + batch - 1) // batch for ci, n in tot.items()}
+        hoff, o = {}, 0
+        for ci in sorted(nb):
+            hoff[ci] = o; o += nb[ci]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        heads = self._dbuf("heads", max(o, 1) * 10)[: max(o, 1) * 10].view(-1, 10)
+        heads.fill_(255)
+        with torch.cuda.device(self.device):
+            for i, rec in zip(st["idx"], st["recs"]):
+                if rec.shape[0]:
+                    _lib_mod().check(lib.nsnp_vcf_batch_heads(rec.data_ptr(), int(rec.shape[0]), 0, first[i], batch,
+                                                              heads[hoff[regions[i].contig_index]:].data_ptr(), stream))
+        if world > 1:
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(heads, op=dist.ReduceOp.MIN)
+            else:
+                heads.copy_(_all_reduce(heads.cpu(), dist.ReduceOp.MIN))
+        heads_h = heads.cpu().numpy()
+        text_h = self._host.get("s_text"); fix_h = self._host.get("s_fix"); tie_h = self._host.get("s_tie")
+        mv = memoryview(text_h.numpy()) if text_h is not None else memoryview(b"")
+        texts = {}
+        for k, i in enumerate(st["idx"]):
+            ln = st["len"][k]
+            if ln == 0:
+                texts[i] = b""
+                continue
+            ci = regions[i].contig_index
+            table = np.ascontiguousarray(heads_h[hoff[ci]:hoff[ci] + nb[ci]])
+            base_ptr = text_h.data_ptr() + st["off"][k]
+            fo, nf = st["fix"][k]
+            drops = C.c_int32(0)
+            if nf:
+                _lib_mod().check(lib.nsnp_vcf_text_patch_heads(base_ptr, ln, fix_h.data_ptr() + fo, nf, first[i], batch, table.ctypes.data, C.byref(drops)))
+            if drops.value:
+                # a fix-up record of a batch with fewer than ten sites (the last batch of a contig): format this region exactly
+                rec = st["recs"][k]
+                g = self._gen_for(ci)
+                texts[i] = bytes(g.fetch(g.format_at(rec, first[i], heads[hoff[ci]:hoff[ci] + nb[ci]])))
+                continue
+            to, nt = st["ties"][k]
+            if nt:
+                w = lib.nsnp_vcf_text_patch_ties_at(contigs[ci][0].encode(), base_ptr, ln, ln + 64, tie_h.data_ptr() + to, nt, first[i], batch, table.ctypes.data)
+                if w <= 0:
+                    raise _lib_mod().NsnpError(-3, "tie fix-up of the VCF text failed")
+                ln = int(w)
+            texts[i] = mv[st["off"][k]:st["off"][k] + ln]
+        st["recs"] = []
+        return self._place(out_path, header, texts, counts, n_reg, world, rank)
+
+    def _gen_for(self, ci):
+        from .vcf_text import GpuVcfText
+        if not hasattr(self, "_gens"):
+            self._gens = {}
+        if ci not in self._gens:
+            self._gens[ci] = GpuVcfText(self.device, self.contigs[ci][0], self.batch)
+        return self._gens[ci]
+
+
+def _lib_mod():
+    from . import _lib
+    return _lib
 
 
 def write_sharded_vcf(out_path: str, header: bytes, contigs, regions, records_by_region: dict, batch_size: int = 1000, device=None) -> dict:

@@ -43,6 +43,12 @@ struct Workspace {
     int64_t  slab_cap;
 };
 
+// CIGAR words: BAM's u32 (len << 4 | op), or the same values as u16 when every length is below 4096 (nsnp_reads.cigar_bits = 16:
+// halves the bytes a host decoder ships per op)
+__device__ __forceinline__ uint32_t ld_cigar(const nsnp_reads_t& rd, int64_t i) {
+    return rd.cigar_bits == 16 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(rd.cigar) + i) : __ldg(rd.cigar + i);
+}
+
 __device__ __forceinline__ bool op_ref(int op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
 __device__ __forceinline__ bool op_query(int op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }
 __device__ __forceinline__ bool op_aligned(int op) { return op == 0 || op == 7 || op == 8; }
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(256) read_scan_kernel(nsnp_reads_t rd, nsnp_pa
         for (int64_t k = c0; k < c1; k += 32 * kUnroll) {
             uint32_t cg[kUnroll];
 #pragma unroll
-            for (int j = 0; j < kUnroll; ++j) cg[j] = (k + 32 * j + lane < c1) ? __ldg(rd.cigar + k + 32 * j + lane) : 6u;   // 6 = pad
+            for (int j = 0; j < kUnroll; ++j) cg[j] = (k + 32 * j + lane < c1) ? ld_cigar(rd, k + 32 * j + lane) : 6u;   // 6 = pad
             const int64_t s = slot0 + ((k - c0) >> kCkShift);
 #pragma unroll
             for (int j = 0; j < kUnroll; ++j) {
@@ -288,12 +294,12 @@ __device__ __forceinline__ void process_read(TileSmem<T>& sm, const nsnp_reads_t
     const uint32_t* seqw = reinterpret_cast<const uint32_t*>(rd.seq2);
     const uint32_t* nmw = reinterpret_cast<const uint32_t*>(rd.nmask);
 
-    const uint32_t* cgp = rd.cigar + c0 + ((int64_t)chunk << kCkShift);
+    int64_t cgp = c0 + ((int64_t)chunk << kCkShift);
     int left = (int)(c1 - c0) - (chunk << kCkShift);                             // ops from this chunk to the end of the read
-    uint32_t cg_next = lane < left ? __ldg(cgp + lane) : 6u;                      // software-pipelined CIGAR loads
+    uint32_t cg_next = lane < left ? ld_cigar(rd, cgp + lane) : 6u;               // software-pipelined CIGAR loads
     for (; left > 0 && R <= te; left -= 32, cgp += 32) {
         const uint32_t cg = cg_next;
-        cg_next = (32 + lane < left) ? __ldg(cgp + 32 + lane) : 6u;
+        cg_next = (32 + lane < left) ? ld_cigar(rd, cgp + 32 + lane) : 6u;
         const int op = cg & 15, len = cg >> 4;                          // 6 = pad: consumes nothing
         const int rl = op_ref(op) ? len : 0, ql = op_query(op) ? len : 0;
         int ri, qi;
@@ -488,14 +494,14 @@ __device__ __forceinline__ void process_read2(TileSmem<T>& sm, const nsnp_reads_
     const uint32_t* nmr = rd.nmask ? reinterpret_cast<const uint32_t*>(rd.nmask) + (meta.sbase >> 5) : nullptr;
     uint32_t* bs = &sm.base[strand * 2][0];
 
-    const uint32_t* cgp = rd.cigar + meta.c0 + ((int64_t)chunk << kCkShift);
+    int64_t cgp = meta.c0 + ((int64_t)chunk << kCkShift);
     int left = n_ops - (chunk << kCkShift);
-    uint32_t nx0 = 2 * lane < left ? __ldg(cgp + 2 * lane) : 6u;
-    uint32_t nx1 = 2 * lane + 1 < left ? __ldg(cgp + 2 * lane + 1) : 6u;
+    uint32_t nx0 = 2 * lane < left ? ld_cigar(rd, cgp + 2 * lane) : 6u;
+    uint32_t nx1 = 2 * lane + 1 < left ? ld_cigar(rd, cgp + 2 * lane + 1) : 6u;
     for (; left > 0 && R <= te; left -= 64, cgp += 64) {
         const uint32_t cgv[2] = {nx0, nx1};
-        nx0 = (64 + 2 * lane < left) ? __ldg(cgp + 64 + 2 * lane) : 6u;
-        nx1 = (65 + 2 * lane < left) ? __ldg(cgp + 65 + 2 * lane) : 6u;
+        nx0 = (64 + 2 * lane < left) ? ld_cigar(rd, cgp + 64 + 2 * lane) : 6u;
+        nx1 = (65 + 2 * lane < left) ? ld_cigar(rd, cgp + 65 + 2 * lane) : 6u;
         const int op0 = cgv[0] & 15, len0 = cgv[0] >> 4, op1 = cgv[1] & 15, len1 = cgv[1] >> 4;
         const int rl0 = ((kRefOps >> op0) & 1u) ? len0 : 0, ql0 = ((kQryOps >> op0) & 1u) ? len0 : 0;
         const int rl1 = ((kRefOps >> op1) & 1u) ? len1 : 0, ql1 = ((kQryOps >> op1) & 1u) ? len1 : 0;
@@ -970,6 +976,8 @@ int nsnp_pileup_counts(const nsnp_reads_t* reads, const uint8_t* ref_dev, int64_
                          (long long)region_start, (long long)region_len, (long long)contig_len);
     if (reads->n_reads < 0 || (reads->n_reads > 0 && (!reads->pos || !reads->flag || !reads->mapq || !reads->cigar_off || !reads->cigar || !reads->seq_off || !reads->seq2)))
         return set_error(NSNP_E_INVALID, "nsnp_pileup_counts: incomplete read arrays");
+    if (reads->cigar_bits != 0 && reads->cigar_bits != 16 && reads->cigar_bits != 32)
+        return set_error(NSNP_E_INVALID, "nsnp_pileup_counts: cigar_bits must be 32 (or 0) or 16");
     if (((uintptr_t)reads->seq2 & 3) || ((uintptr_t)reads->nmask & 3) || ((uintptr_t)counts_dev & 15))
         return set_error(NSNP_E_INVALID, "nsnp_pileup_counts: seq2/nmask must be 4-byte and counts 16-byte aligned");
     if (reads->n_reads > 0x7fffffff - 1) return set_error(NSNP_E_UNSUPPORTED, "more than 2^31 reads in one call");

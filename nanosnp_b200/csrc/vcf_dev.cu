@@ -29,6 +29,10 @@ constexpr int kMaxContigName = 63;
 struct ContigName { char s[kMaxContigName + 1]; int len; };
 struct TieEntry { int64_t off; int32_t j; int32_t len; nsnp_site_record_t rec; uint8_t head[10]; uint8_t pad[6]; };   // 64 bytes
 static_assert(sizeof(TieEntry) == 64, "tie entry layout");
+// deferred batch heads (multi-GPU streaming): the ALT of a fix-up record is one character that depends on the first ten
+// sites of its batch, which may live on another rank; the record is written with a placeholder and listed here
+struct FixEntry { int64_t off; int32_t j; uint8_t zyo, sref, pad[2]; };                                                  // 16 bytes
+static_assert(sizeof(FixEntry) == 16, "fix entry layout");
 
 struct HeadSrc {                            // gt argmax of site ti of the batch that holds global site index g
     const nsnp_site_record_t* rec; int64_t n; int64_t first_index; int64_t batch; const uint8_t* table;
@@ -48,12 +52,33 @@ __host__ __device__ inline char* put_dec(char* p, unsigned long long v) {
 }
 __host__ __device__ inline int base_idx_hd(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
 
+// ALT of a hom / het "fix-up" record (predict.py:101-131): the class whose batch-level argmax is largest among the candidate
+// class indices; 0 when the batch has no such site (IndexError -> the record is dropped)
+__host__ __device__ inline char fixup_alt(int zyo, char sref, const uint8_t* head)
+{
+    const char kGt[10][3] = {"AA", "AC", "AG", "AT", "CC", "CG", "CT", "GG", "GT", "TT"};
+    const int tis_hom[4] = {0, 4, 7, 9};
+    const int tis_het[6] = {1, 2, 3, 5, 6, 8};
+    const int nt = zyo == 1 ? 4 : 6;
+    int max_ti = -1, max_v = -1;
+    for (int q = 0; q < nt; ++q) {
+        const int ti = zyo == 1 ? tis_hom[q] : tis_het[q];
+        if (zyo == 1 && kGt[ti][0] == sref) continue;
+        const int v = head[ti];
+        if (v == 255) return 0;                                               // IndexError on the batch argmax array
+        if (v > max_v) { max_v = v; max_ti = ti; }
+    }
+    return zyo == 1 ? kGt[max_ti][0] : (kGt[max_ti][0] == sref ? kGt[max_ti][1] : kGt[max_ti][0]);
+}
+
 // One record (predict.py:66-194 after the numeric half): returns the text length, 0 when predict.py writes nothing.
 // head[ti] = gt argmax of site ti of the record's batch, 255 when the batch has no such site (IndexError -> dropped).
+// head == nullptr: deferred -- a fix-up record gets the placeholder ALT '?' and *alt_off = its offset in the record.
 __host__ __device__ inline int format_record(char* out, const char* contig, int clen, const nsnp_site_record_t& r, const uint8_t* head,
-                                             long long gt_q, long long zy_q)
+                                             long long gt_q, long long zy_q, int* alt_off = nullptr)
 {
     const char kGt[10][3] = {"AA", "AC", "AG", "AT", "CC", "CG", "CT", "GG", "GT", "TT"};       // options.py:8-17
+    bool placeholder = false;
     const char kZy[3][4] = {"0/0", "1/1", "0/1"};                                              // options.py:30
     const int gt = r.gt, zyo = r.zy;
     if (gt >= 10) return 0;                                                   // predict.py:68
@@ -68,18 +93,8 @@ __host__ __device__ inline int format_record(char* out, const char* contig, int 
     if (na == 0) {
         if (zyo == 0) { alts[0] = sref; nalt = 1; q100 = qual; refcall = true; }
         else {
-            const int tis_hom[4] = {0, 4, 7, 9};
-            const int tis_het[6] = {1, 2, 3, 5, 6, 8};
-            const int nt = zyo == 1 ? 4 : 6;
-            int max_ti = -1, max_v = -1;
-            for (int q = 0; q < nt; ++q) {
-                const int ti = zyo == 1 ? tis_hom[q] : tis_het[q];
-                if (zyo == 1 && kGt[ti][0] == sref) continue;
-                const int v = head[ti];
-                if (v == 255) return 0;                                       // IndexError on the batch argmax array
-                if (v > max_v) { max_v = v; max_ti = ti; }
-            }
-            alts[0] = zyo == 1 ? kGt[max_ti][0] : (kGt[max_ti][0] == sref ? kGt[max_ti][1] : kGt[max_ti][0]);
+            if (head) { alts[0] = fixup_alt(zyo, sref, head); if (!alts[0]) return 0; }
+            else { alts[0] = '?'; placeholder = true; }
             nalt = 1; q100 = zy_q;
         }
     } else {
@@ -93,6 +108,7 @@ __host__ __device__ inline int format_record(char* out, const char* contig, int 
     *p++ = '\t';
     p = put_dec(p, (unsigned long long)(uint32_t)r.pos1);
     *p++ = '\t'; *p++ = '.'; *p++ = '\t'; *p++ = sref; *p++ = '\t';
+    if (alt_off) *alt_off = placeholder ? (int)(p - out) : -1;
     for (int i = 0; i < nalt; ++i) *p++ = alts[i];
     *p++ = '\t';
     const unsigned long long ip = (unsigned long long)(q100 / 100); const int f2 = (int)(q100 - (long long)ip * 100);
@@ -126,7 +142,8 @@ template <bool kWrite>
 __global__ void __launch_bounds__(kTextThreads) vcf_text_kernel(const nsnp_site_record_t* __restrict__ rec, int64_t n, const int32_t* __restrict__ n_dev,
                                                                HeadSrc hs, ContigName name, int64_t* __restrict__ block_off,
                                                                char* __restrict__ text, int64_t capacity, TieEntry* __restrict__ ties,
-                                                               int32_t* __restrict__ tie_count, int tie_cap)
+                                                               int32_t* __restrict__ tie_count, int tie_cap, int deferred,
+                                                               FixEntry* __restrict__ fixes, int32_t* __restrict__ fix_count)
 {
     __shared__ __align__(16) char slot[kTextThreads][kSlot];
     __shared__ int warp_tot[kTextThreads / 32];
@@ -137,11 +154,12 @@ __global__ void __launch_bounds__(kTextThreads) vcf_text_kernel(const nsnp_site_
     int len = 0;
     nsnp_site_record_t r;
     uint8_t head[10];
+    int alt_off = -1;
     if (j < n) {
         r = rec[j];
-        const bool fix = r.gt < 10 && !(r.flags & NSNP_REC_DROP) && r.zy != 0;      // only fix-up records read the batch heads
+        const bool fix = !deferred && r.gt < 10 && !(r.flags & NSNP_REC_DROP) && r.zy != 0;      // only fix-up records read the batch heads
         for (int k = 0; k < 10; ++k) head[k] = fix ? (uint8_t)hs.get(hs.first_index + j, k) : (uint8_t)255;
-        len = format_record(slot[tid], name.s, name.len, r, head, r.q100_gt, r.q100_zy);
+        len = format_record(slot[tid], name.s, name.len, r, deferred ? nullptr : head, r.q100_gt, r.q100_zy, &alt_off);
     }
     int inc = len;
 #pragma unroll
@@ -161,6 +179,11 @@ __global__ void __launch_bounds__(kTextThreads) vcf_text_kernel(const nsnp_site_
             for (int k = 0; k < 6; ++k) e.pad[k] = 0;
             ties[t] = e;
         }
+    }
+    if (len && alt_off >= 0) {
+        const int t = atomicAdd(fix_count, 1);
+        FixEntry e; e.off = base + off + alt_off; e.j = (int32_t)j; e.zyo = r.zy; e.sref = r.ref; e.pad[0] = e.pad[1] = 0;
+        fixes[t] = e;                                           // capacity = n: every record could be a fix-up
     }
     // pack: this thread's record moves to its packed position in a second buffer (reuse of the slots is not possible in
     // place: packed ranges overlap other threads' unread slots), then the block stores its range with coalesced bytes
@@ -209,7 +232,7 @@ __global__ void __launch_bounds__(256) batch_heads_kernel(const nsnp_site_record
     if (j >= 0 && j < n) heads[b * 10 + k] = rec[j].gt;
 }
 
-struct TextWs { int64_t* block_off; int32_t* tie_count; TieEntry* ties; };
+struct TextWs { int64_t* block_off; int32_t* tie_count; TieEntry* ties; int32_t* fix_count; FixEntry* fixes; };
 constexpr int kTieCap = 4096;
 inline size_t carve_text(void* base, int64_t n, TextWs* w) {
     const int64_t nb = (n + kTextThreads - 1) / kTextThreads;
@@ -218,6 +241,8 @@ inline size_t carve_text(void* base, int64_t n, TextWs* w) {
     w->block_off = (int64_t*)take((size_t)(nb + 2) * 8);
     w->tie_count = (int32_t*)take(64);
     w->ties = (TieEntry*)take((size_t)kTieCap * sizeof(TieEntry));
+    w->fix_count = (int32_t*)take(64);
+    w->fixes = (FixEntry*)take((size_t)(n + 1) * sizeof(FixEntry));
     return off;
 }
 
@@ -247,14 +272,32 @@ extern "C" {
 size_t nsnp_vcf_text_workspace_bytes(int64_t n) { TextWs w; return carve_text(nullptr, n < 0 ? 0 : n, &w); }
 int64_t nsnp_vcf_text_capacity(int64_t n, const char* contig) { return n * (int64_t)(88 + (contig ? strlen(contig) : kMaxContigName)) + 256; }
 
+static int text_records_impl(const char* contig, const nsnp_site_record_t* rec_dev, int64_t n, const int32_t* n_dev, int64_t first_index,
+                             int64_t batch_size, const uint8_t* heads_dev, char* text_dev, int64_t text_capacity, int64_t* text_len_dev,
+                             void* workspace_dev, size_t workspace_bytes, int deferred, void* stream_);
+
 int nsnp_vcf_text_records(const char* contig, const nsnp_site_record_t* rec_dev, int64_t n, const int32_t* n_dev, int64_t first_index,
                           int64_t batch_size, const uint8_t* heads_dev, char* text_dev, int64_t text_capacity, int64_t* text_len_dev,
                           void* workspace_dev, size_t workspace_bytes, void* stream_)
 {
+    return text_records_impl(contig, rec_dev, n, n_dev, first_index, batch_size, heads_dev, text_dev, text_capacity, text_len_dev, workspace_dev,
+                             workspace_bytes, 0, stream_);
+}
+
+int nsnp_vcf_text_records_deferred(const char* contig, const nsnp_site_record_t* rec_dev, int64_t n, const int32_t* n_dev, char* text_dev,
+                                   int64_t text_capacity, int64_t* text_len_dev, void* workspace_dev, size_t workspace_bytes, void* stream_)
+{
+    return text_records_impl(contig, rec_dev, n, n_dev, 0, 1000, nullptr, text_dev, text_capacity, text_len_dev, workspace_dev, workspace_bytes, 1, stream_);
+}
+
+static int text_records_impl(const char* contig, const nsnp_site_record_t* rec_dev, int64_t n, const int32_t* n_dev, int64_t first_index,
+                             int64_t batch_size, const uint8_t* heads_dev, char* text_dev, int64_t text_capacity, int64_t* text_len_dev,
+                             void* workspace_dev, size_t workspace_bytes, int deferred, void* stream_)
+{
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!contig || n < 0 || batch_size <= 0 || first_index < 0 || !text_len_dev || (n > 0 && (!rec_dev || !text_dev || !workspace_dev)))
         return set_error(NSNP_E_INVALID, "nsnp_vcf_text_records: bad argument");
-    if (!heads_dev && first_index % batch_size != 0)
+    if (!deferred && !heads_dev && first_index % batch_size != 0)
         return set_error(NSNP_E_INVALID, "nsnp_vcf_text_records: without a batch-head table the records must start on a batch boundary");
     ContigName name;
     const size_t clen = strlen(contig);
@@ -267,10 +310,11 @@ int nsnp_vcf_text_records(const char* contig, const nsnp_site_record_t* rec_dev,
     const int64_t nb = (n + kTextThreads - 1) / kTextThreads;
     HeadSrc hs{rec_dev, n, first_index, batch_size, heads_dev};
     cudaMemsetAsync(w.tie_count, 0, 4, stream);
+    cudaMemsetAsync(w.fix_count, 0, 4, stream);
     ProfScope prof(NSNP_PROF_VCF_TEXT, stream);
-    vcf_text_kernel<false><<<(unsigned)nb, kTextThreads, 0, stream>>>(rec_dev, n, n_dev, hs, name, w.block_off, nullptr, 0, nullptr, nullptr, 0);
+    vcf_text_kernel<false><<<(unsigned)nb, kTextThreads, 0, stream>>>(rec_dev, n, n_dev, hs, name, w.block_off, nullptr, 0, nullptr, nullptr, 0, deferred, nullptr, nullptr);
     block_scan_kernel<<<1, 1024, 0, stream>>>(w.block_off, nb, text_len_dev);
-    vcf_text_kernel<true><<<(unsigned)nb, kTextThreads, 0, stream>>>(rec_dev, n, n_dev, hs, name, w.block_off, text_dev, text_capacity, w.ties, w.tie_count, kTieCap);
+    vcf_text_kernel<true><<<(unsigned)nb, kTextThreads, 0, stream>>>(rec_dev, n, n_dev, hs, name, w.block_off, text_dev, text_capacity, w.ties, w.tie_count, kTieCap, deferred, w.fixes, w.fix_count);
     return cuda_status("vcf_text_kernel");
 }
 
@@ -281,6 +325,33 @@ int nsnp_vcf_text_ties(const void* workspace_dev, int64_t n, const void** count_
     if (count_dev) *count_dev = w.tie_count;
     if (entries_dev) *entries_dev = w.ties;
     if (capacity) *capacity = kTieCap;
+    return NSNP_OK;
+}
+
+/* the fix-up list of the last nsnp_vcf_text_records_deferred call on this workspace: int32 count + 16-byte entries */
+int nsnp_vcf_text_fixups(const void* workspace_dev, int64_t n, const void** count_dev, const void** entries_dev)
+{
+    TextWs w; carve_text(const_cast<void*>(workspace_dev), n < 0 ? 0 : n, &w);
+    if (count_dev) *count_dev = w.fix_count;
+    if (entries_dev) *entries_dev = w.fixes;
+    return NSNP_OK;
+}
+
+/* host: writes the real ALT character of every listed fix-up record once the batch-head table of its contig is complete.
+ * first_index: contig-wide index of the region's first record.  *n_drop counts records whose batch has no such site
+ * (predict.py drops them; only possible in the last, short batch of a contig): the caller re-formats that region exactly. */
+int nsnp_vcf_text_patch_heads(char* text_host, int64_t text_len, const void* fix_host, int32_t n_fix, int64_t first_index, int64_t batch_size,
+                              const uint8_t* heads_table, int32_t* n_drop)
+{
+    if (!text_host || n_fix < 0 || (n_fix > 0 && (!fix_host || !heads_table)) || batch_size <= 0) return set_error(NSNP_E_INVALID, "nsnp_vcf_text_patch_heads: bad argument");
+    const FixEntry* f = (const FixEntry*)fix_host;
+    int32_t drops = 0;
+    for (int32_t i = 0; i < n_fix; ++i) {
+        if (f[i].off < 0 || f[i].off >= text_len) return set_error(NSNP_E_INVALID, "nsnp_vcf_text_patch_heads: offset out of range");
+        const char a = fixup_alt(f[i].zyo, (char)f[i].sref, heads_table + ((first_index + f[i].j) / batch_size) * 10);
+        if (!a) ++drops; else text_host[f[i].off] = a;
+    }
+    if (n_drop) *n_drop = drops;
     return NSNP_OK;
 }
 
@@ -298,9 +369,19 @@ int nsnp_vcf_batch_heads(const nsnp_site_record_t* rec_dev, int64_t n, const int
 
 /* host: re-evaluates the flagged records with libc and splices differing bytes into the text; returns the new length
  * (or the negative of the capacity needed).  ties_host: n_ties 64-byte entries copied from the device list. */
+int64_t nsnp_vcf_text_patch_ties_at(const char* contig, char* text_host, int64_t text_len, int64_t text_capacity, const void* ties_host, int32_t n_ties,
+                                    int64_t first_index, int64_t batch_size, const uint8_t* heads_table);
+
 int64_t nsnp_vcf_text_patch_ties(const char* contig, char* text_host, int64_t text_len, int64_t text_capacity, const void* ties_host, int32_t n_ties)
 {
-    if (!contig || !text_host || text_len < 0 || n_ties < 0 || (n_ties > 0 && !ties_host)) return 0;
+    return nsnp_vcf_text_patch_ties_at(contig, text_host, text_len, text_capacity, ties_host, n_ties, 0, 1, nullptr);
+}
+
+/* heads_table != NULL (deferred text): the listed records carry no batch heads; they are looked up in the contig's table */
+int64_t nsnp_vcf_text_patch_ties_at(const char* contig, char* text_host, int64_t text_len, int64_t text_capacity, const void* ties_host, int32_t n_ties,
+                                    int64_t first_index, int64_t batch_size, const uint8_t* heads_table)
+{
+    if (!contig || !text_host || text_len < 0 || n_ties < 0 || (n_ties > 0 && !ties_host) || batch_size <= 0) return 0;
     const int clen = (int)strlen(contig);
     std::vector<TieEntry> t((const TieEntry*)ties_host, (const TieEntry*)ties_host + n_ties);
     std::sort(t.begin(), t.end(), [](const TieEntry& a, const TieEntry& b) { return a.off > b.off; });     // back to front: offsets stay valid
@@ -310,7 +391,8 @@ int64_t nsnp_vcf_text_patch_ties(const char* contig, char* text_host, int64_t te
         if (e.rec.flags & NSNP_REC_TIE_GT) ok = ok && host_q100(e.rec.p_gt, &gq);
         if (e.rec.flags & NSNP_REC_TIE_ZY) ok = ok && host_q100(e.rec.p_zy, &zq);
         char buf[kSlot + 64];
-        const int len = ok ? format_record(buf, contig, clen, e.rec, e.head, gq, zq) : 0;
+        const uint8_t* head = heads_table ? heads_table + ((first_index + e.j) / batch_size) * 10 : e.head;
+        const int len = ok ? format_record(buf, contig, clen, e.rec, head, gq, zq) : 0;
         if (e.off < 0 || e.off + e.len > text_len) return 0;
         if (len == e.len && memcmp(buf, text_host + e.off, (size_t)len) == 0) continue;
         const int64_t new_len = text_len + (len - e.len);

@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 
 FIELDS = ("pos", "flag", "mapq", "cigar_off", "cigar", "seq_off", "seq2", "nmask")
-DTYPES = {"pos": np.int32, "flag": np.uint16, "mapq": np.uint8, "cigar_off": np.int64, "cigar": np.uint32,
+DTYPES = {"pos": np.int32, "flag": np.uint16, "mapq": np.uint8, "cigar_off": np.int64, "cigar": np.uint32,      # cigar: uint16 when packed by cigar16()
           "seq_off": np.int64, "seq2": np.uint8, "nmask": np.uint8}
 
 CIGAR_OPS = "MIDNSHP=X"
@@ -75,6 +75,7 @@ class PackedReads:
         r.qual = 0
         r.n_cigar = self.n_cigar
         r.n_bases = self.n_bases
+        r.cigar_bits = 16 if self.cigar.dtype in (np.uint16, np.int16) or str(self.cigar.dtype) in ("torch.int16", "torch.uint16") else 32
         return r
 
     def to_torch(self, device, pin: bool = False, non_blocking: bool = False) -> "PackedReads":
@@ -97,7 +98,8 @@ class PackedReads:
         def conv(f, a):
             if a is None or isinstance(a, np.ndarray):
                 return a
-            return a.detach().cpu().numpy().view(DTYPES[f])
+            h = a.detach().cpu().numpy()
+            return h.view(np.uint16) if (f == "cigar" and h.dtype == np.int16) else h.view(DTYPES[f])
         return PackedReads(*[conv(f, getattr(self, f)) for f in FIELDS])
 
     def prefix(self, n: int) -> "PackedReads":
@@ -146,6 +148,25 @@ def canonicalize_cigars(reads: "PackedReads") -> "PackedReads":
     merged = ((lens << 4) | ops[starts]).astype(np.uint32)
     new_off = np.concatenate([[0], np.cumsum(first)])[reads.cigar_off].astype(np.int64)
     return PackedReads(reads.pos, reads.flag, reads.mapq, new_off, merged, reads.seq_off, reads.seq2, reads.nmask)
+
+
+def cigar16(reads: "PackedReads") -> "PackedReads":
+    """The same reads with the CIGAR words as uint16 (struct nsnp_reads.cigar_bits = 16) when every op length is below 4096
+    -- true for ONT / HiFi alignments except the occasional long clip -- else unchanged.  Halves the CIGAR bytes that cross
+    PCIe (16 of the 23.5 bytes per reference position at 30x).  numpy or torch (host / device) arrays."""
+    c = reads.cigar
+    if isinstance(c, np.ndarray):
+        if c.dtype == np.uint16 or (c.size and int(c.max()) >= (4096 << 4)):
+            return reads
+        c16 = c.astype(np.uint16)
+    else:
+        import torch
+        if c.dtype == torch.int16:
+            return reads
+        if c.numel() and (int(c.max()) >= (4096 << 4) or int(c.min()) < 0):
+            return reads
+        c16 = c.to(torch.int16)                       # values < 65536: the bit pattern is the uint16 word
+    return PackedReads(reads.pos, reads.flag, reads.mapq, reads.cigar_off, c16, reads.seq_off, reads.seq2, reads.nmask)
 
 
 def max_reference_span(reads: "PackedReads") -> int:

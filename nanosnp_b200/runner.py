@@ -273,9 +273,10 @@ class RegionRunner:
         return total
 
     # ---- host-buffer mode, records kept on the device (multi-GPU: the text is made after the count / head exchange) ----------
-    def run_host_collect(self, host_regions, regions, refs) -> list:
+    def run_host_collect(self, host_regions, regions, refs, on_region=None) -> list:
         """Pinned host reads of arbitrary regions (refs[k]: the device reference of region k's contig) -> H2D -> kernels ->
-        compact records, returned as one device tensor per region.  The H2D of region k+1 overlaps the kernels of region k."""
+        compact records, returned as one device tensor per region -- or handed to on_region(k, RegionOutput) right after region
+        k's kernels were enqueued (e.g. ShardedVcfWriter.add_region).  The H2D of region k+1 overlaps the kernels of region k."""
         assert self.records
         dev = self.device
         main = torch.cuda.current_stream(dev)
@@ -300,7 +301,11 @@ class RegionRunner:
                 start_upload(k + 1)
             main.wait_event(up_done[k])
             o = self.run_device(dev_reads[k], refs[k], regions[k])
-            out[k] = o.rec.clone()
+            if on_region is not None:
+                on_region(k, o)
+                out[k] = o.n
+            else:
+                out[k] = o.rec.clone()
             ev = torch.cuda.Event(); ev.record(main); comp_done[k] = ev
         return out
 

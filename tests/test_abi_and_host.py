@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.nsnp_abi_version() == 1
+    assert lib.nsnp_abi_version() == 2
     p = _lib.default_params()
     assert (p.snp_min_af, p.indel_min_af, p.min_coverage, p.min_mapq, p.excl_flags) == (0.12, 0.12, 6, 20, 2316)
     assert lib.nsnp_model_blob_bytes() > 700_000

@@ -127,3 +127,27 @@ def test_device_generator_matches_host(engine):
     rd_d = rd_d.to_numpy()
     for f in ("pos", "flag", "mapq", "cigar_off", "cigar", "seq_off", "seq2", "nmask"):
         assert np.array_equal(getattr(rd_h, f), getattr(rd_d, f)), f
+
+
+def test_cigar16_words_give_identical_counts(engine):
+    """struct nsnp_reads.cigar_bits = 16: the same CIGAR values shipped as uint16 (host numpy and device torch packing)."""
+    import torch
+    from nanosnp_b200.reads import cigar16
+    from nanosnp_b200.synth import SynthConfig, generate_host
+    cfg = SynthConfig(contig_len=150_000, coverage=25.0, seed_ref=3, seed_var=4, seed_reads=5, nbase_rate=0.003)
+    ref, reads = generate_host(cfg)
+    want = _run_gpu(engine, reads, ref)
+    r16 = cigar16(reads)
+    assert r16.cigar.dtype == np.uint16 and r16.as_struct().cigar_bits == 16 and reads.as_struct().cigar_bits == 32
+    got = _run_gpu(engine, r16, ref)
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    d16 = cigar16(reads.to_torch(engine.device))
+    assert d16.cigar.dtype == torch.int16 and d16.as_struct().cigar_bits == 16
+    rf = torch.from_numpy(np.ascontiguousarray(ref)).to(engine.device)
+    pos, refbase, x, counts, flags = engine.candidate_windows(d16, rf)
+    assert np.array_equal(counts.cpu().numpy(), want[3]) and np.array_equal(pos.cpu().numpy(), want[0])
+    # a length >= 4096 keeps the 32-bit words
+    from nanosnp_b200.reads import from_records
+    big = from_records([(0, 0, 60, "5000M", "A" * 5000)])
+    assert cigar16(big).cigar.dtype == np.uint32

@@ -129,3 +129,43 @@ def test_gpu_text_streaming_table_and_ties():
     assert g4.push(rd[:7]) is None
     small = bytes(g4.fetch(g4.flush()))
     assert small == host_contig_text(lib, "c", np.ascontiguousarray(rec[:7]))
+
+
+@pytest.mark.gpu
+def test_gpu_sharded_writer_streaming_equals_batch_and_host(tmp_path):
+    """ShardedVcfWriter: begin / add_region / finish (deferred batch heads, text copied out region by region) writes the same
+    file as write() and as the host contig formatter, incl. a contig whose last batch has fewer than ten sites (dropped fix-up
+    records) and rounding ties."""
+    import torch
+    from nanosnp_b200.caller import ShardedVcfWriter
+    from nanosnp_b200.shard import plan_regions
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    contigs = [("cA", 400_000), ("cB", 90_000), ("cC", 150_000)]
+    regions = plan_regions(contigs, 50_000)
+    recs, want = {}, b"##h\n"
+    for ci, (name, L) in enumerate(contigs):
+        n = {0: 61_234, 1: 9_003, 2: 20_000}[ci]              # cB: the last batch holds 3 sites
+        rec = random_records(n, 100 + ci)
+        rec["zy"][-3:] = 1; rec["gt"][-3:] = 0; rec["ref"][-3:] = ord("A"); rec["flags"][-3:] = 0     # fix-up records in the short batch
+        rec["pos1"] = np.sort(np.random.default_rng(ci).choice(L, n, replace=False)).astype(np.int32) + 1
+        rec["flags"] &= ~np.uint8(REC_TIE_GT | REC_TIE_ZY)
+        tie = np.random.default_rng(9 + ci).choice(n, 60, replace=False)
+        rec["flags"][tie] |= REC_TIE_GT
+        rec["q100_gt"][tie[::2]] += 5
+        want += host_contig_text(lib, name, rec)
+        for i, rg in enumerate(regions):
+            if rg.contig_index == ci:
+                sel = (rec["pos1"] - 1 >= rg.emit_start) & (rec["pos1"] - 1 < rg.emit_end)
+                recs[i] = torch.from_numpy(np.ascontiguousarray(rec[sel]).view(np.uint8).reshape(-1, 32)).to(dev)
+    w = ShardedVcfWriter(contigs, regions, 1000, dev)
+    p1 = str(tmp_path / "batch.vcf")
+    w.write(p1, b"##h\n", recs)
+    assert open(p1, "rb").read() == want
+    for rep in range(2):                                        # twice: buffers are reused
+        p2 = str(tmp_path / f"stream{rep}.vcf")
+        w.begin()
+        for i in sorted(recs):
+            w.add_region(i, recs[i])
+        info = w.finish(p2, b"##h\n")
+        assert open(p2, "rb").read() == want and info["sites"] == sum(int(r.shape[0]) for r in recs.values())

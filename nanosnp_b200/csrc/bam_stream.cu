@@ -12,6 +12,7 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <chrono>
 #include <future>
 #include <string>
 #include <thread>
@@ -89,6 +90,8 @@ struct nsnp_bam_reader {
     std::vector<int64_t> cigar_off, seq_off; std::vector<uint32_t> cigar; std::vector<uint8_t> seq2, nmask;
     int64_t n_bases = 0; bool any_n = false;
     int64_t inflated_bytes = 0;
+    double t_wait = 0, t_buf = 0, t_fill = 0;     // seconds: waiting for inflate, buffer upkeep, record fill (NSNP_TRACE)
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
     Batch inflate_batch(size_t from, int max_blocks, size_t* next_out) {
         Batch out;
@@ -151,10 +154,15 @@ struct nsnp_bam_reader {
     bool need(size_t n, bool* err) {
         while (buf.size() - cur < n) {
             if (!pending_valid) { if (at_eof) return false; launch_next(); }
+            double t0 = now();
             Batch b = pending.get(); pending_valid = false;
+            t_wait += now() - t0;
             if (!b.ok) { *err = true; return false; }
+            flush_pending();                                     // queued records point into buf
+            t0 = now();
             if (cur > 0) { buf.erase(buf.begin(), buf.begin() + (ptrdiff_t)cur); cur = 0; }
             buf.insert(buf.end(), b.data.begin(), b.data.end());
+            t_buf += now() - t0;
             inflated_bytes += (int64_t)b.data.size();
             if (b.eof || next_block >= file_len) at_eof = true;
             else launch_next();                                  // the next batch inflates while this one is parsed
@@ -164,6 +172,7 @@ struct nsnp_bam_reader {
 
     void seek(uint64_t voff) {
         if (pending_valid) { pending.get(); pending_valid = false; }
+        flush_pending();
         buf.clear(); cur = 0; at_eof = false; batch_blocks = 8;
         next_block = (size_t)(voff >> 16);
         bool err = false;
@@ -174,11 +183,17 @@ struct nsnp_bam_reader {
 
     void clear_arrays() {
         pos.clear(); flag.clear(); mapq.clear(); cigar_off.assign(1, 0); seq_off.clear(); cigar.clear();
-        seq2.clear(); nmask.clear(); n_bases = 0; any_n = false;
+        seq2.clear(); nmask.clear(); n_bases = 0; any_n = false; pend.clear(); pend_cig = 0; pend_bases = 0; merge_needed = false;
     }
 
-    // appends the record at p (block_size bytes after the 4-byte length) to the arrays; returns its reference length
-    int64_t append(const uint8_t* p, int64_t bs) {
+    // ---- decode: records are indexed sequentially (cheap: header fields only), then filled by all threads ----
+    struct RecRef { const uint8_t* p; const uint8_t* cg; const uint8_t* seq; uint32_t nc, l_seq; int64_t cig_o, base_o; };
+    std::vector<RecRef> pend;
+    int64_t pend_cig = 0, pend_bases = 0;
+    bool merge_needed = false;
+
+    // queues the record at p (block_size bytes after the 4-byte length)
+    void queue(const uint8_t* p, int64_t bs) {
         const uint32_t l_name = p[12], n_cig_rec = rd_u16(p + 16), l_seq = rd_u32(p + 20);
         const uint8_t* q = p + 36 + l_name;
         const uint8_t* cg = q; uint32_t nc = n_cig_rec;
@@ -207,36 +222,91 @@ struct nsnp_bam_reader {
                 }
             }
         }
-        pos.push_back(rd_i32(p + 8)); flag.push_back(rd_u16(p + 18)); mapq.push_back(p[13]);
-        // CIGAR, adjacent ops of one type merged ("1D2D" -> "3D": htslib reports such runs as one indel)
-        int64_t reflen = 0;
-        const size_t c_first = cigar.size();
-        for (uint32_t k = 0; k < nc; ++k) {
-            const uint32_t c = rd_u32(cg + 4ull * k);
-            const uint32_t op = c & 15u;
-            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += c >> 4;
-            if (cigar.size() > c_first && (cigar.back() & 15u) == op) cigar.back() += c & ~15u;
-            else cigar.push_back(c);
+        const int64_t padded = ((int64_t)l_seq + 15) / 16 * 16;     // every read starts on a 16-base boundary of seq2 / nmask
+        pend.push_back(RecRef{p, cg, seq, nc, l_seq, (int64_t)cigar.size() + pend_cig, n_bases + pend_bases});
+        pend_cig += nc; pend_bases += padded;
+    }
+
+    // fills the arrays from the queued records (must run before the bytes they point into are released)
+    void flush_pending() {
+        if (pend.empty()) return;
+        const double t_begin = now();
+        const size_t n0 = pos.size(), nr = pend.size();
+        pos.resize(n0 + nr); flag.resize(n0 + nr); mapq.resize(n0 + nr); seq_off.resize(n0 + nr); cigar_off.resize(n0 + nr + 1);
+        cigar.resize(cigar.size() + (size_t)pend_cig);
+        seq2.resize(seq2.size() + (size_t)pend_bases / 4, 0); nmask.resize(nmask.size() + (size_t)pend_bases / 8, 0);
+        std::atomic<size_t> ticket{0};
+        std::atomic<bool> saw_n{false}, need_merge{false};
+        auto work = [&]() {
+            bool my_n = false, my_merge = false;
+            for (;;) {
+                const size_t i0 = ticket.fetch_add(16);
+                if (i0 >= nr) break;
+                for (size_t i = i0; i < std::min(nr, i0 + 16); ++i) {
+                    const RecRef& r = pend[i];
+                    pos[n0 + i] = rd_i32(r.p + 8); flag[n0 + i] = rd_u16(r.p + 18); mapq[n0 + i] = r.p[13];
+                    seq_off[n0 + i] = r.base_o; cigar_off[n0 + i + 1] = r.cig_o + r.nc;
+                    uint32_t* c = cigar.data() + r.cig_o;
+                    memcpy(c, r.cg, 4ull * r.nc);
+                    for (uint32_t k = 1; k < r.nc; ++k) my_merge |= ((c[k] ^ c[k - 1]) & 15u) == 0;
+                    uint8_t* s2 = seq2.data() + r.base_o / 4; uint8_t* nm = nmask.data() + r.base_o / 8;
+                    const uint32_t nb = (r.l_seq + 1) / 2;
+                    uint32_t nacc = 0, j = 0;
+                    for (; j + 4 <= nb; j += 4) {                        // 8 bases: two seq2 bytes, one nmask byte
+                        const uint32_t v0 = g_lut.v[r.seq[j]], v1 = g_lut.v[r.seq[j + 1]], v2 = g_lut.v[r.seq[j + 2]], v3 = g_lut.v[r.seq[j + 3]];
+                        s2[j >> 1] = (uint8_t)((v0 & 15) | ((v1 & 15) << 4)); s2[(j >> 1) + 1] = (uint8_t)((v2 & 15) | ((v3 & 15) << 4));
+                        const uint32_t nf = (v0 >> 4) | ((v1 >> 4) << 2) | ((v2 >> 4) << 4) | ((v3 >> 4) << 6);
+                        nm[j >> 2] = (uint8_t)nf; nacc |= nf;
+                    }
+                    for (; j < nb; ++j) {
+                        const uint32_t v = g_lut.v[r.seq[j]];
+                        s2[j >> 1] |= (uint8_t)((v & 15) << (4 * (j & 1)));
+                        nm[j >> 2] |= (uint8_t)((v >> 4) << (2 * (j & 3)));
+                        nacc |= v >> 4;
+                    }
+                    if (r.l_seq & 1) {                                  // odd length: the last low nibble is padding, not a base
+                        const uint32_t k = r.l_seq;                     // index of the phantom base
+                        s2[k >> 2] &= (uint8_t)~(3u << (2 * (k & 3)));
+                        const bool was = (nm[k >> 3] >> (k & 7)) & 1u;
+                        nm[k >> 3] &= (uint8_t)~(1u << (k & 7));
+                        if (was) {                                      // recompute: the phantom may have been the only N
+                            nacc = 0;
+                            for (uint32_t q = 0; q < (r.l_seq + 7) / 8; ++q) nacc |= nm[q];
+                        }
+                    }
+                    if (nacc) my_n = true;
+                }
+            }
+            if (my_n) saw_n = true;
+            if (my_merge) need_merge = true;
+        };
+        const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, nr / 32));
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        if (saw_n) any_n = true;
+        if (need_merge) merge_needed = true;
+        n_bases += pend_bases;
+        pend.clear(); pend_cig = 0; pend_bases = 0;
+        t_fill += now() - t_begin;
+    }
+
+    // adjacent ops of one type merged ("1D2D" -> "3D": htslib reports such runs as one indel); rare, so a sequential pass
+    void merge_runs() {
+        if (!merge_needed) return;
+        size_t w = 0;
+        for (size_t r = 0; r + 1 < cigar_off.size(); ++r) {
+            const size_t b = (size_t)cigar_off[r], e = (size_t)cigar_off[r + 1], w0 = w;
+            for (size_t k = b; k < e; ++k) {
+                if (w > w0 && ((cigar[w - 1] ^ cigar[k]) & 15u) == 0) cigar[w - 1] += cigar[k] & ~15u;
+                else cigar[w++] = cigar[k];
+            }
+            cigar_off[r] = (int64_t)w0;
         }
-        cigar_off.push_back((int64_t)cigar.size());
-        // bases: every read starts on a 16-base boundary of seq2 (4 bytes) / nmask (2 bytes)
-        seq_off.push_back(n_bases);
-        const int64_t padded = ((int64_t)l_seq + 15) / 16 * 16;
-        const size_t s0 = seq2.size(), m0 = nmask.size();
-        seq2.resize(s0 + (size_t)padded / 4, 0); nmask.resize(m0 + (size_t)padded / 8, 0);
-        uint8_t* s2 = seq2.data() + s0; uint8_t* nm = nmask.data() + m0;
-        const uint32_t nbytes = (l_seq + 1) / 2;
-        uint32_t nacc = 0;
-        for (uint32_t j = 0; j < nbytes; ++j) {
-            uint8_t v = g_lut.v[seq[j]];
-            if (j == nbytes - 1 && (l_seq & 1)) v &= 0x13;             // odd length: the low nibble is padding
-            s2[j >> 1] |= (uint8_t)((v & 15) << (4 * (j & 1)));
-            nm[j >> 2] |= (uint8_t)((v >> 4) << (2 * (j & 3)));
-            nacc |= v >> 4;
-        }
-        if (nacc) any_n = true;
-        n_bases += padded;
-        return reflen;
+        cigar_off[cigar_off.size() - 1] = (int64_t)w;
+        cigar.resize(w);
+        merge_needed = false;
     }
 };
 
@@ -308,6 +378,7 @@ nsnp_bam_reader_t* nsnp_bam_open(const char* path, int n_threads)
 void nsnp_bam_close(nsnp_bam_reader_t* r)
 {
     if (!r) return;
+    if (getenv("NSNP_TRACE")) fprintf(stderr, "bam reader: inflated %.0f MB; waited for inflate %.3f s, buffer upkeep %.3f s, record fill %.3f s\n", r->inflated_bytes / 1e6, r->t_wait, r->t_buf, r->t_fill);
     if (r->pending_valid) { r->pending.get(); r->pending_valid = false; }
     if (r->file) munmap((void*)r->file, r->file_len);
     if (r->fd >= 0) close(r->fd);
@@ -366,9 +437,11 @@ static int32_t decode_run(nsnp_bam_reader* r, int32_t ref, const int8_t* want, i
             }
             if (pos + std::max<int64_t>(reflen, 1) <= beg) { r->cur += 4 + (size_t)bs; continue; }
         }
-        r->append(p, bs);
+        r->queue(p, bs);
         r->cur += 4 + (size_t)bs;
     }
+    r->flush_pending();
+    r->merge_runs();
     if (err) { nsnp::set_error(NSNP_E_INVALID, "malformed BAM record stream"); return -2; }
     if (cur_ref < 0 || (r->pos.empty() && ref < 0)) return -1;
     return cur_ref;

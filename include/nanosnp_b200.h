@@ -200,6 +200,27 @@ size_t nsnp_hap_model_workspace_bytes(int64_t n);
 int nsnp_hap_model_forward(const void* blob_dev, const float* xp_dev, const float* xh_dev, int64_t n, float* gt_prob_dev, float* zy_prob_dev,
                            void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- BASELINE configs[4]: HaplotypeModel s4, read x position matrices (csrc/hap_groups.cu) -----------------------------
+ * Replaces single_group_pileup_haplotype_feature (HaplotypeModel/create_pileup_haplotype.py:23-216): the two pysam pileup
+ * sweeps + pandas of one sub-group.  reads_dev: one contig, file order; reads->qual (optional) holds the base qualities at the
+ * same base index as seq2.  hp_dev [n_reads]: HP tag (1 / 2, 0 = untagged).  end_dev / end_pm_dev [n_reads]: exclusive reference
+ * end of every alignment (nsnp_hap_read_ends) and its running maximum.  dup_prev_dev / dup_next_dev [n_reads] (both or NULL):
+ * previous / next alignment with the same query name among the alignments pysam's stepper keeps, -1 = none -- the reference
+ * keys its rows by query name (:107-121).  gpos_dev [n_groups][n_hap]: 1-based ascending positions, centre = candidate.
+ * fetch_lo_dev [n_groups]: `start` of the pysam sweep the group belongs to (alignments with end <= start are not fetched).
+ * flank < 0: first sweep (:39-46) -- only n_cols_dev [n_groups][n_hap] (pileupcolumn.n of the hap sites), depth_dev (rows) and
+ * flags_dev are written, hap_dev / pile_dev are NULL.  flank >= 0: second sweep (:93-205) -- n_cols_dev
+ * [n_groups][n_hap + 2*flank+1], and hap_dev[4] / pile_dev[4] = {sequences, hap, baseq, mapq} int32 [n_groups][cap][n_hap] /
+ * [n_groups][cap][2*flank+1], rows ordered by the centre's HP tag, padded with -2 (write_to_bins.py:14-30).
+ * flags_dev bit 0: a SEQ letter outside ACGT on a column of interest (KeyError at :123 -> the reference drops the sub-group);
+ * bit 1: more rows than cap. */
+int nsnp_hap_read_ends(const nsnp_reads_t* reads_dev, int32_t* end_dev, void* stream);
+int nsnp_hap_group_matrices(const nsnp_reads_t* reads_dev, const uint8_t* hp_dev, const int32_t* end_dev, const int32_t* end_pm_dev,
+                            const int32_t* dup_prev_dev, const int32_t* dup_next_dev, const int32_t* gpos_dev,
+                            const int32_t* fetch_lo_dev, int64_t n_groups, int32_t n_hap, int32_t flank, int32_t cap,
+                            int32_t* n_cols_dev, int32_t* depth_dev, int32_t* flags_dev, int32_t* const* hap_dev,
+                            int32_t* const* pile_dev, void* stream);
+
 /* ---- per-kernel timing (bench.py) ---------------------------------------------------------------
  * When enabled, every kernel launch of this library is bracketed by cudaEventRecord on the launching stream.
  * nsnp_profile_read synchronises, adds the elapsed times per kernel slot into ms_out[NSNP_PROF_SLOTS] and
@@ -324,6 +345,11 @@ int32_t nsnp_bam_fetch(nsnp_bam_reader_t* r, int32_t ref_id, int64_t beg, int64_
                        int64_t* n_bases_padded);
 int nsnp_bam_take(nsnp_bam_reader_t* r, int32_t* pos, uint16_t* flag, uint8_t* mapq, int64_t* cigar_off, uint32_t* cigar,
                   int64_t* seq_off, uint8_t* seq2, uint8_t* nmask, int32_t* any_n);
+/* HaplotypeModel s4 inputs: with keep != 0 the reader also keeps, for every record it decodes from then on, the base
+ * qualities (one byte per base at the read's seq_off, 0xFF = absent), the HP:i tag (0 = none) and a 64-bit FNV-1a hash of the
+ * query name; nsnp_bam_take_aux copies them out (qual: n_bases_padded bytes; hp, qname_hash: n_reads). */
+int nsnp_bam_keep_aux(nsnp_bam_reader_t* r, int keep);
+int nsnp_bam_take_aux(nsnp_bam_reader_t* r, uint8_t* qual, uint8_t* hp, uint64_t* qname_hash);
 
 /* ---- synthetic inputs (bench / tests) --------------------------------------- */
 typedef struct nsnp_synth_cfg {

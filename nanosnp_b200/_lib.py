@@ -100,6 +100,8 @@ SYMBOLS = {
     "nsnp_hap_model_pack_weights": (C.c_int, [C.POINTER(HapWeights), _P, _SZ]),
     "nsnp_hap_model_workspace_bytes": (_SZ, [_I64]),
     "nsnp_hap_model_forward": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
+    "nsnp_hap_read_ends": (C.c_int, [C.POINTER(Reads), _P, _P]),
+    "nsnp_hap_group_matrices": (C.c_int, [C.POINTER(Reads), _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "nsnp_profile_enable": (None, [C.c_int]),
     "nsnp_profile_read": (C.c_int, [_P, _P]),
     "nsnp_check_status": (C.c_int, [_P, _P]),
@@ -130,6 +132,8 @@ SYMBOLS = {
     "nsnp_bam_next_contig": (_I32, [_P, _P, _P, _P, _P]),
     "nsnp_bam_fetch": (_I32, [_P, _I32, _I64, _I64, _P, _P, _P]),
     "nsnp_bam_take": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nsnp_bam_keep_aux": (C.c_int, [_P, C.c_int]),
+    "nsnp_bam_take_aux": (C.c_int, [_P, _P, _P, _P]),
     "nsnp_synth_ref_host": (C.c_int, [C.POINTER(SynthCfg), _P]),
     "nsnp_synth_count_host": (C.c_int, [C.POINTER(SynthCfg), _P, _P, _P, _P, _P]),
     "nsnp_synth_fill_host": (C.c_int, [C.POINTER(SynthCfg), _P, _P, _P, _P, _P]),

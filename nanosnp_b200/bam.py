@@ -9,7 +9,8 @@ from __future__ import annotations
 import ctypes as C
 import struct
 import zlib
-from typing import Dict, List, Tuple
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -78,15 +79,36 @@ def parse_header(raw: bytes) -> Tuple[str, List[Tuple[str, int]], int]:
     return text, refs, o
 
 
+@dataclass
+class ReadAux:
+    """What the HaplotypeModel s4 stage needs beside PackedReads (create_pileup_haplotype.py:105-131): base qualities at the
+    reads' seq_off base index, HP tag per read (0 = untagged) and a 64-bit hash of the query name (rows are keyed by name)."""
+    qual: np.ndarray                    # uint8 [n_bases]
+    hp: np.ndarray                      # uint8 [n_reads]
+    qhash: np.ndarray                   # uint64 [n_reads]
+    names: Optional[List[str]] = None   # only used by write_bam
+
+
+def qname_hash(name: str) -> int:
+    h = 1469598103934665603
+    for c in name.encode():
+        h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
 class BamReader:
     """Streaming BAM reader (native: csrc/bam_stream.cu).  BGZF blocks are inflated on `threads` host threads 32 MB at a
     time; records are decoded contig by contig, or region by region when a .bai lies next to the file."""
 
-    def __init__(self, path: str, threads: int = 0):
+    def __init__(self, path: str, threads: int = 0, keep_aux: bool = False):
         self.lib = _lib.load()
         self.h = self.lib.nsnp_bam_open(path.encode(), int(threads))
         if not self.h:
             raise ValueError(self.lib.nsnp_last_error().decode())
+        self.keep_aux = bool(keep_aux)
+        self.aux: Optional[ReadAux] = None          # aux data of the contig / region decoded last (keep_aux=True)
+        if keep_aux:
+            _lib.check(self.lib.nsnp_bam_keep_aux(self.h, 1))
         n = self.lib.nsnp_bam_n_ref(self.h)
         self.refs: List[Tuple[str, int]] = [(self.lib.nsnp_bam_ref_name(self.h, i).decode(), int(self.lib.nsnp_bam_ref_len(self.h, i))) for i in range(n)]
         self.has_index = bool(self.lib.nsnp_bam_has_index(self.h))
@@ -115,6 +137,10 @@ class BamReader:
         any_n = C.c_int32(0)
         _lib.check(self.lib.nsnp_bam_take(self.h, pos.ctypes.data, flag.ctypes.data, mapq.ctypes.data, cigar_off.ctypes.data, cigar.ctypes.data,
                                           seq_off.ctypes.data, seq2.ctypes.data, nmask.ctypes.data, C.byref(any_n)))
+        if self.keep_aux:
+            qual = np.zeros(n_bases + 16, np.uint8); hp = np.zeros(n, np.uint8); qh = np.zeros(n, np.uint64)
+            _lib.check(self.lib.nsnp_bam_take_aux(self.h, qual.ctypes.data, hp.ctypes.data, qh.ctypes.data))
+            self.aux = ReadAux(qual, hp, qh)
         return PackedReads(pos, flag, mapq, cigar_off, cigar[:n_cig], seq_off, seq2, nmask if any_n.value else None)
 
     def contigs(self, only=None):
@@ -194,9 +220,9 @@ def _write_bai(path: str, n_ref: int, recs) -> None:
 
 
 def write_bam(path: str, refs: List[Tuple[str, int]], reads_by_contig: Dict[str, PackedReads], long_cigar_as_tag: int = 65535,
-              index: bool = False) -> None:
-    """Coordinate-sorted BAM from packed reads (tests / interoperability).  Qualities are written as 0xFF (absent).
-    index=True also writes <path>.bai (bins + 16 kb linear index)."""
+              index: bool = False, aux: Optional[Dict[str, "ReadAux"]] = None) -> None:
+    """Coordinate-sorted BAM from packed reads (tests / interoperability).  Qualities are written as 0xFF (absent) unless `aux`
+    carries them (then also query names and HP:C tags).  index=True also writes <path>.bai (bins + 16 kb linear index)."""
     code4 = np.array([1, 2, 4, 8], np.uint8)
     parts = [b"BAM\x01"]
     text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
@@ -223,14 +249,18 @@ def write_bam(path: str, refs: List[Tuple[str, int]], reads_by_contig: Dict[str,
             if l_seq & 1:
                 c4 = np.append(c4, 0).astype(np.uint8)
             seq = ((c4[0::2] << 4) | c4[1::2]).astype(np.uint8).tobytes()
-            rname = f"r{i}".encode() + b"\0"
+            ax = aux.get(name) if aux else None
+            rname = (ax.names[i] if (ax is not None and ax.names is not None) else f"r{i}").encode() + b"\0"
             tags = b""
+            if ax is not None and int(ax.hp[i]):
+                tags += b"HPC" + struct.pack("<B", int(ax.hp[i]))
+            qbytes = b"\xff" * l_seq if ax is None else ax.qual[int(rd.seq_off[i]): int(rd.seq_off[i]) + l_seq].tobytes()
             cig_bytes = cg.tobytes(); n_cig = len(cg)
             if n_cig > long_cigar_as_tag:              # SAM spec: real CIGAR in CG:B,I, placeholder <l_seq>S<ref_len>N in the record
-                tags = b"CGBI" + struct.pack("<I", n_cig) + cig_bytes
+                tags += b"CGBI" + struct.pack("<I", n_cig) + cig_bytes
                 cig_bytes = struct.pack("<II", (l_seq << 4) | 4, (ref_len << 4) | 3); n_cig = 2
             body = struct.pack("<iiBBHHHIiii", rid, int(rd.pos[i]), len(rname), int(rd.mapq[i]), 4680, n_cig, int(rd.flag[i]), l_seq, -1, -1, 0)
-            body += rname + cig_bytes + seq + b"\xff" * l_seq + tags
+            body += rname + cig_bytes + seq + qbytes + tags
             parts += [struct.pack("<i", len(body)), body]
             rec_info.append((rid, int(rd.pos[i]), int(rd.pos[i]) + ref_len, upos, upos + 4 + len(body)))
             upos += 4 + len(body)

@@ -89,6 +89,8 @@ struct nsnp_bam_reader {
     std::vector<int32_t> pos; std::vector<uint16_t> flag; std::vector<uint8_t> mapq;
     std::vector<int64_t> cigar_off, seq_off; std::vector<uint32_t> cigar; std::vector<uint8_t> seq2, nmask;
     int64_t n_bases = 0; bool any_n = false;
+    bool keep_aux = false;                  // HaplotypeModel s4: also keep base qualities, HP tag and a query-name hash
+    std::vector<uint8_t> qual, hp; std::vector<uint64_t> qhash;
     int64_t inflated_bytes = 0;
     double t_wait = 0, t_buf = 0, t_fill = 0;     // seconds: waiting for inflate, buffer upkeep, record fill (NSNP_TRACE)
     static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -183,14 +185,40 @@ struct nsnp_bam_reader {
 
     void clear_arrays() {
         pos.clear(); flag.clear(); mapq.clear(); cigar_off.assign(1, 0); seq_off.clear(); cigar.clear();
-        seq2.clear(); nmask.clear(); n_bases = 0; any_n = false; pend.clear(); pend_cig = 0; pend_bases = 0; merge_needed = false;
+        seq2.clear(); nmask.clear(); qual.clear(); hp.clear(); qhash.clear(); n_bases = 0; any_n = false; pend.clear(); pend_cig = 0; pend_bases = 0; merge_needed = false;
     }
 
     // ---- decode: records are indexed sequentially (cheap: header fields only), then filled by all threads ----
-    struct RecRef { const uint8_t* p; const uint8_t* cg; const uint8_t* seq; uint32_t nc, l_seq; int64_t cig_o, base_o; };
+    struct RecRef { const uint8_t* p; const uint8_t* cg; const uint8_t* seq; uint32_t nc, l_seq; int64_t cig_o, base_o; const uint8_t* aux; const uint8_t* end; };
     std::vector<RecRef> pend;
     int64_t pend_cig = 0, pend_bases = 0;
     bool merge_needed = false;
+
+    // value of the HP:i tag (whatshap haplotag: 1 or 2), 0 when absent; walks the aux fields per the SAM spec
+    static uint8_t aux_hp(const uint8_t* t, const uint8_t* end) {
+        while (t + 3 <= end) {
+            const char a = (char)t[0], b = (char)t[1], ty = (char)t[2];
+            t += 3; size_t sz = 0;
+            if (ty == 'A' || ty == 'c' || ty == 'C') sz = 1;
+            else if (ty == 's' || ty == 'S') sz = 2;
+            else if (ty == 'i' || ty == 'I' || ty == 'f') sz = 4;
+            else if (ty == 'Z' || ty == 'H') { const uint8_t* e = t; while (e < end && *e) ++e; sz = (size_t)(e - t) + 1; }
+            else if (ty == 'B') {
+                if (t + 5 > end) return 0;
+                const char sub = (char)t[0]; const uint32_t cnt = rd_u32(t + 1);
+                sz = 5 + (size_t)((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4) * cnt;
+            } else return 0;
+            if (t + sz > end) return 0;
+            if (a == 'H' && b == 'P') {
+                int64_t v = 0;
+                switch (ty) { case 'c': v = (int8_t)t[0]; break; case 'C': v = t[0]; break; case 's': v = (int16_t)rd_u16(t); break;
+                              case 'S': v = rd_u16(t); break; case 'i': v = rd_i32(t); break; case 'I': v = rd_u32(t); break; default: v = 0; }
+                return (v >= 0 && v <= 255) ? (uint8_t)v : 0;
+            }
+            t += sz;
+        }
+        return 0;
+    }
 
     // queues the record at p (block_size bytes after the 4-byte length)
     void queue(const uint8_t* p, int64_t bs) {
@@ -223,7 +251,7 @@ struct nsnp_bam_reader {
             }
         }
         const int64_t padded = ((int64_t)l_seq + 15) / 16 * 16;     // every read starts on a 16-base boundary of seq2 / nmask
-        pend.push_back(RecRef{p, cg, seq, nc, l_seq, (int64_t)cigar.size() + pend_cig, n_bases + pend_bases});
+        pend.push_back(RecRef{p, cg, seq, nc, l_seq, (int64_t)cigar.size() + pend_cig, n_bases + pend_bases, q, end});
         pend_cig += nc; pend_bases += padded;
     }
 
@@ -235,6 +263,7 @@ struct nsnp_bam_reader {
         pos.resize(n0 + nr); flag.resize(n0 + nr); mapq.resize(n0 + nr); seq_off.resize(n0 + nr); cigar_off.resize(n0 + nr + 1);
         cigar.resize(cigar.size() + (size_t)pend_cig);
         seq2.resize(seq2.size() + (size_t)pend_bases / 4, 0); nmask.resize(nmask.size() + (size_t)pend_bases / 8, 0);
+        if (keep_aux) { qual.resize(qual.size() + (size_t)pend_bases, 0); hp.resize(n0 + nr, 0); qhash.resize(n0 + nr, 0); }
         std::atomic<size_t> ticket{0};
         std::atomic<bool> saw_n{false}, need_merge{false};
         auto work = [&]() {
@@ -275,6 +304,13 @@ struct nsnp_bam_reader {
                         }
                     }
                     if (nacc) my_n = true;
+                    if (keep_aux) {
+                        memcpy(qual.data() + r.base_o, r.seq + nb, r.l_seq);
+                        uint64_t hsh = 1469598103934665603ull;                     // FNV-1a of the query name (without the NUL)
+                        for (const uint8_t* c = r.p + 36; *c; ++c) hsh = (hsh ^ *c) * 1099511628211ull;
+                        qhash[n0 + i] = hsh;
+                        hp[n0 + i] = aux_hp(r.aux, r.end);
+                    }
                 }
             }
             if (my_n) saw_n = true;
@@ -496,6 +532,22 @@ int nsnp_bam_take(nsnp_bam_reader_t* r, int32_t* pos, uint16_t* flag, uint8_t* m
     if (!r->seq2.empty()) memcpy(seq2, r->seq2.data(), r->seq2.size());
     if (nmask && !r->nmask.empty()) memcpy(nmask, r->nmask.data(), r->nmask.size());
     if (any_n) *any_n = r->any_n ? 1 : 0;
+    return NSNP_OK;
+}
+
+int nsnp_bam_keep_aux(nsnp_bam_reader_t* r, int keep)
+{
+    if (!r) return nsnp::set_error(NSNP_E_INVALID, "nsnp_bam_keep_aux: null reader");
+    r->keep_aux = keep != 0;
+    return NSNP_OK;
+}
+
+int nsnp_bam_take_aux(nsnp_bam_reader_t* r, uint8_t* qual, uint8_t* hp, uint64_t* qname_hash)
+{
+    if (!r || !qual || !hp || !qname_hash) return nsnp::set_error(NSNP_E_INVALID, "nsnp_bam_take_aux: null argument");
+    if (!r->keep_aux || r->hp.size() != r->pos.size()) return nsnp::set_error(NSNP_E_INVALID, "nsnp_bam_take_aux: call nsnp_bam_keep_aux(reader, 1) before decoding");
+    if (!r->qual.empty()) memcpy(qual, r->qual.data(), r->qual.size());
+    if (!r->hp.empty()) { memcpy(hp, r->hp.data(), r->hp.size()); memcpy(qname_hash, r->qhash.data(), r->qhash.size() * 8); }
     return NSNP_OK;
 }
 

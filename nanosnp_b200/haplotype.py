@@ -6,8 +6,9 @@
     predict(...) -> `ctg\\tpos\\tGT\\tqual` rows                                        # predict_dev.py:27-48
 
 The reference reads PyTables `.bin` files written by write_to_bins.py (PyTables / pysam are absent here), so the dataset takes the
-same eight arrays from an `.npz` (keys as the HDF5 node names).  The s4 feature build from HP-tagged BAMs (H1-H3: pysam pileup
-semantics) is not built.  There is no CPU fallback.
+same eight arrays from an `.npz` (keys as the HDF5 node names; nanosnp_b200.hap_groups writes them from the pileup VCF and the
+HP-tagged BAMs: SURVEY 8a H1-H3).  predict_from_bams() runs s4 + s5 without the files in between: group selection on the host,
+read matrices, the 105-channel features and the model on the GPU.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -131,7 +132,8 @@ def frequency_features(seq, bq, mq, hp, refcode, device="cuda:0") -> torch.Tenso
     """int32 [n, depth, L] matrices + int32 [n, L] reference codes -> float32 [n, 105, L] on the device."""
     lib = _lib.load()
     device = require_cuda(device)
-    arrs = [torch.as_tensor(np.ascontiguousarray(a, np.int32)).to(device) for a in (seq, bq, mq, hp, refcode)]
+    arrs = [(a.to(device, torch.int32) if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(a, np.int32)).to(device)).contiguous()
+            for a in (seq, bq, mq, hp, refcode)]
     n, depth, L = (int(v) for v in arrs[0].shape)
     out = torch.empty((n, 105, L), dtype=torch.float32, device=device)
     with torch.cuda.device(device):
@@ -200,6 +202,48 @@ def predict(model: LSTMNetwork, test_data: str, reference_path: str, batch_size:
                 for j in range(len(go)):
                     ctg, pos = ds.positions[s + j].split(":")
                     fw.write(ctg + "\t" + pos + "\t" + GT10[go[j]] + "\t" + str(calculate_score(gp[j])) + "\n")
+                    n_rows += 1
+    return n_rows
+
+
+def predict_from_bams(model: LSTMNetwork, pileup_vcf: str, bams: str, reference_path: str, output_file: str, batch_size: int = 1000,
+                      pileup_flanking_size: int = 16, adjacent_size: int = 5, low_quality_threshold: float = 19, hete_support_quality: float = 14,
+                      max_coverage: int = 150, max_depth: Optional[int] = None, threads: int = 1, device="cuda:0") -> int:
+    """scripts/s4_haplotype_model_feature_generation.sh + s5_haplotype_model_predict.sh in one pass, nothing written in between:
+    groups (hap_groups.select_snp_multiprocess) -> read matrices on the GPU (hap_groups.group_matrices; chunking and sub-groups as
+    make_predict_bins.py with `threads`) -> 105-channel features -> model -> `ctg\tpos\tGT\tqual` rows.  max_depth = the
+    --max_pileup_depth / --max_haplotype_depth cut (3 x coverage in the reference's script)."""
+    from . import hap_groups as hg
+    device = require_cuda(device)
+    references = load_reference_file(reference_path)
+    groups = hg.select_snp_multiprocess(pileup_vcf, low_quality_threshold, adjacent_size, hete_support_quality, nthreads=threads)
+    n_hap = 2 * adjacent_size + 1
+    n_rows = 0
+    with open(output_file, "w") as fw:
+        for ctg, g in groups.items():
+            chunks = hg.plan_chunks(len(g), threads)
+            al = hg.load_contig(os.path.join(bams, ctg + ".bam"), ctg, device) if chunks else None
+            if al is None:
+                continue
+            subs = [(lo + a, lo + b) for lo, hi in chunks for a, b in hg.plan_subgroups(g[lo:hi])]
+            gm = hg.group_matrices(al, g, subs, max_coverage, pileup_flanking_size)
+            if len(gm.positions) == 0:
+                continue
+            ref = references.get(ctg)
+            cand = gm.positions[:, n_hap // 2]
+            win = cand[:, None] + np.arange(-pileup_flanking_size, pileup_flanking_size + 1)[None, :]
+            pref = reference_codes(ref, win) if ref is not None else np.zeros(win.shape, np.int32)
+            href = reference_codes(ref, gm.positions) if ref is not None else np.zeros(gm.positions.shape, np.int32)
+            d = gm.hap[0].shape[1] if max_depth is None else min(gm.hap[0].shape[1], max_depth)
+            for s in range(0, len(cand), batch_size):
+                sl = slice(s, s + batch_size)
+                xp = frequency_features(gm.pile[0][sl, :d], gm.pile[2][sl, :d], gm.pile[3][sl, :d], gm.pile[1][sl, :d], pref[sl], device)
+                xh = frequency_features(gm.hap[0][sl, :d], gm.hap[2][sl, :d], gm.hap[3][sl, :d], gm.hap[1][sl, :d], href[sl], device)
+                gt, _ = model.predict(xp, xh)
+                gq = gt.cpu().numpy()
+                gp = gq.max(axis=1); go = gq.argmax(axis=1)
+                for j in range(len(go)):
+                    fw.write(ctg + "\t" + str(int(cand[s + j])) + "\t" + GT10[go[j]] + "\t" + str(calculate_score(gp[j])) + "\n")
                     n_rows += 1
     return n_rows
 

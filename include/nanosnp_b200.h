@@ -204,7 +204,9 @@ int nsnp_hap_model_forward(const void* blob_dev, const float* xp_dev, const floa
  * Replaces single_group_pileup_haplotype_feature (HaplotypeModel/create_pileup_haplotype.py:23-216): the two pysam pileup
  * sweeps + pandas of one sub-group.  reads_dev: one contig, file order; reads->qual (optional) holds the base qualities at the
  * same base index as seq2.  hp_dev [n_reads]: HP tag (1 / 2, 0 = untagged).  end_dev / end_pm_dev [n_reads]: exclusive reference
- * end of every alignment (nsnp_hap_read_ends) and its running maximum.  dup_prev_dev / dup_next_dev [n_reads] (both or NULL):
+ * end of every alignment (nsnp_hap_read_ends) and its running maximum.  checkpoints_dev (optional, 8-byte aligned):
+ * 2 x nsnp_hap_checkpoint_count() int32, the (reference, query) position every 32 CIGAR ops, also written by nsnp_hap_read_ends:
+ * lets the kernel jump to a column instead of walking there.  dup_prev_dev / dup_next_dev [n_reads] (both or NULL):
  * previous / next alignment with the same query name among the alignments pysam's stepper keeps, -1 = none -- the reference
  * keys its rows by query name (:107-121).  gpos_dev [n_groups][n_hap]: 1-based ascending positions, centre = candidate.
  * fetch_lo_dev [n_groups]: `start` of the pysam sweep the group belongs to (alignments with end <= start are not fetched).
@@ -214,8 +216,10 @@ int nsnp_hap_model_forward(const void* blob_dev, const float* xp_dev, const floa
  * [n_groups][cap][2*flank+1], rows ordered by the centre's HP tag, padded with -2 (write_to_bins.py:14-30).
  * flags_dev bit 0: a SEQ letter outside ACGT on a column of interest (KeyError at :123 -> the reference drops the sub-group);
  * bit 1: more rows than cap. */
-int nsnp_hap_read_ends(const nsnp_reads_t* reads_dev, int32_t* end_dev, void* stream);
+int64_t nsnp_hap_checkpoint_count(int64_t n_reads, int64_t n_cigar);
+int nsnp_hap_read_ends(const nsnp_reads_t* reads_dev, int32_t* end_dev, int32_t* checkpoints_dev, void* stream);
 int nsnp_hap_group_matrices(const nsnp_reads_t* reads_dev, const uint8_t* hp_dev, const int32_t* end_dev, const int32_t* end_pm_dev,
+                            const int32_t* checkpoints_dev,
                             const int32_t* dup_prev_dev, const int32_t* dup_next_dev, const int32_t* gpos_dev,
                             const int32_t* fetch_lo_dev, int64_t n_groups, int32_t n_hap, int32_t flank, int32_t cap,
                             int32_t* n_cols_dev, int32_t* depth_dev, int32_t* flags_dev, int32_t* const* hap_dev,

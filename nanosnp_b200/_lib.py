@@ -100,8 +100,9 @@ SYMBOLS = {
     "nsnp_hap_model_pack_weights": (C.c_int, [C.POINTER(HapWeights), _P, _SZ]),
     "nsnp_hap_model_workspace_bytes": (_SZ, [_I64]),
     "nsnp_hap_model_forward": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
-    "nsnp_hap_read_ends": (C.c_int, [C.POINTER(Reads), _P, _P]),
-    "nsnp_hap_group_matrices": (C.c_int, [C.POINTER(Reads), _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "nsnp_hap_checkpoint_count": (_I64, [_I64, _I64]),
+    "nsnp_hap_read_ends": (C.c_int, [C.POINTER(Reads), _P, _P, _P]),
+    "nsnp_hap_group_matrices": (C.c_int, [C.POINTER(Reads), _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "nsnp_profile_enable": (None, [C.c_int]),
     "nsnp_profile_read": (C.c_int, [_P, _P]),
     "nsnp_check_status": (C.c_int, [_P, _P]),

@@ -29,14 +29,22 @@ __device__ __forceinline__ uint32_t ld_cig(const nsnp_reads_t& rd, int64_t i) {
     return rd.cigar_bits == 16 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(rd.cigar) + i) : __ldg(rd.cigar + i);
 }
 
-__global__ void read_end_kernel(nsnp_reads_t rd, int32_t* __restrict__ end)
+constexpr int kCkShift = 5;                        // one (reference, query) checkpoint per 32 CIGAR ops
+
+// checkpoint slots of read r: (cigar_off[r] >> kCkShift) + r + j for block j of its ops
+__device__ __forceinline__ int64_t ck_slot0(const nsnp_reads_t& rd, int64_t r) { return (rd.cigar_off[r] >> kCkShift) + r; }
+
+__global__ void read_end_kernel(nsnp_reads_t rd, int32_t* __restrict__ end, int2* __restrict__ ck)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rd.n_reads) return;
-    int x = rd.pos[r];
-    for (int64_t k = rd.cigar_off[r]; k < rd.cigar_off[r + 1]; ++k) {
-        const uint32_t c = ld_cig(rd, k); const int op = c & 15;
-        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) x += (int)(c >> 4);
+    int x = rd.pos[r], y = 0;
+    const int64_t c0 = rd.cigar_off[r], s0 = ck_slot0(rd, r);
+    for (int64_t k = c0; k < rd.cigar_off[r + 1]; ++k) {
+        if (ck && ((k - c0) & ((1 << kCkShift) - 1)) == 0) ck[s0 + ((k - c0) >> kCkShift)] = make_int2(x, y);
+        const uint32_t c = ld_cig(rd, k); const int op = c & 15, len = (int)(c >> 4);
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) x += len;
+        if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) y += len;
     }
     end[r] = x;
 }
@@ -50,17 +58,27 @@ __device__ __forceinline__ bool stepper_pass(uint32_t flag) {
 struct Cell { int v, hp, bq, mq; };
 
 // Walks alignment r over the sorted 0-based columns tg[0..nt) and calls f(column index, cell) for every column it covers.
+// A column that lies far ahead is reached through the read's checkpoints (binary search, then <= 32 ops) instead of op by op.
 // Returns true when it met a SEQ letter outside ACGT on one of the columns.
 template <class F>
-__device__ bool walk_read(const nsnp_reads_t& rd, const uint8_t* __restrict__ qual, int tag, int64_t r, const int* tg, int nt, F&& f)
+__device__ bool walk_read(const nsnp_reads_t& rd, const int2* __restrict__ ck, const uint8_t* __restrict__ qual, int tag, int64_t r,
+                          const int* tg, int nt, F&& f)
 {
     int x = rd.pos[r], y = 0, ti = 0;
     while (ti < nt && tg[ti] < x) ++ti;
     if (ti >= nt) return false;
     const int mq = rd.mapq[r];
     const int64_t so = rd.seq_off[r];
+    const int64_t k0 = rd.cigar_off[r], ke = rd.cigar_off[r + 1], s0 = ck_slot0(rd, r);
     bool bad = false;
-    for (int64_t k = rd.cigar_off[r], ke = rd.cigar_off[r + 1]; k < ke && ti < nt; ++k) {
+    int sought = -1;
+    for (int64_t k = k0; k < ke && ti < nt; ++k) {
+        if (ck && ti != sought && tg[ti] - x >= 128) {                 // seek: the last checkpoint at or before the column
+            sought = ti;
+            int64_t lo = (k - k0) >> kCkShift, hi = (ke - 1 - k0) >> kCkShift;
+            while (lo < hi) { const int64_t m = (lo + hi + 1) >> 1; if (ck[s0 + m].x <= tg[ti]) lo = m; else hi = m - 1; }
+            if (k0 + (lo << kCkShift) > k) { const int2 c = ck[s0 + lo]; k = k0 + (lo << kCkShift); x = c.x; y = c.y; }
+        }
         const uint32_t c = ld_cig(rd, k); const int op = c & 15, len = (int)(c >> 4);
         if (op == 0 || op == 7 || op == 8) {
             while (ti < nt && tg[ti] < x + len) {
@@ -86,6 +104,7 @@ struct GroupArgs {
     const uint8_t* hp;            // [n_reads] HP tag, 0 = none
     const int32_t* end;           // [n_reads] exclusive reference end
     const int32_t* end_pm;        // [n_reads] running maximum of end
+    const int2* ck;               // CIGAR checkpoints (nsnp_hap_read_ends), may be NULL
     const int32_t* dup_prev;      // [n_reads] previous / next alignment of the same query name (file order), -1; may be NULL
     const int32_t* dup_next;
     const int32_t* gpos;          // [G][n_hap] 1-based, ascending
@@ -151,7 +170,7 @@ __global__ void __launch_bounds__(kWarps * 32) hap_group_kernel(const GroupArgs 
         int v = 0; hp_out = 0;
         for (int64_t m = r; m >= 0 && m < hi; m = a.dup_next ? a.dup_next[m] : -1) {
             if (m != r && !in_scope(m)) continue;
-            walk_read(rd, nullptr, tag_of(m), m, one, 1, [&](int, const Cell& c) { v = c.v; hp_out = c.hp; });
+            walk_read(rd, a.ck, nullptr, tag_of(m), m, one, 1, [&](int, const Cell& c) { v = c.v; hp_out = c.hp; });
         }
         return v;
     };
@@ -194,7 +213,7 @@ __global__ void __launch_bounds__(kWarps * 32) hap_group_kernel(const GroupArgs 
             if (row && hpv == t + 1) my_row = base[t] + run[t] + __popc(m & ((1u << lane) - 1u));
             run[t] += __popc(m);
         }
-        if (!own) continue;
+        if (!own || !write) continue;
         const bool put = write && my_row >= 0 && my_row < a.cap;
         if (put) {
             for (int k = 0; k < 4; ++k) {
@@ -206,7 +225,7 @@ __global__ void __launch_bounds__(kWarps * 32) hap_group_kernel(const GroupArgs 
         }
         for (int64_t m = r; m >= 0 && m < hi; m = a.dup_next ? a.dup_next[m] : -1) {
             if (m != r && !in_scope(m)) continue;
-            bad |= walk_read(rd, rd.qual, tag_of(m), m, tg, nt, [&](int i, const Cell& c) {
+            bad |= walk_read(rd, a.ck, rd.qual, tag_of(m), m, tg, nt, [&](int i, const Cell& c) {
                 if (!put) return;
                 const int vals[4] = {c.v, c.hp, c.bq, c.mq};
                 for (int k = 0; k < 4; ++k) {
@@ -240,15 +259,18 @@ __global__ void __launch_bounds__(kWarps * 32) hap_group_kernel(const GroupArgs 
 
 using namespace nsnp;
 
-extern "C" int nsnp_hap_read_ends(const nsnp_reads_t* reads_dev, int32_t* end_dev, void* stream)
+extern "C" int64_t nsnp_hap_checkpoint_count(int64_t n_reads, int64_t n_cigar) { return (n_cigar >> kCkShift) + n_reads + 1; }
+
+extern "C" int nsnp_hap_read_ends(const nsnp_reads_t* reads_dev, int32_t* end_dev, int32_t* checkpoints_dev, void* stream)
 {
     if (!reads_dev || !end_dev) return set_error(NSNP_E_INVALID, "nsnp_hap_read_ends: null argument");
     if (reads_dev->n_reads == 0) return NSNP_OK;
-    read_end_kernel<<<(unsigned)((reads_dev->n_reads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*reads_dev, end_dev);
+    read_end_kernel<<<(unsigned)((reads_dev->n_reads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*reads_dev, end_dev, reinterpret_cast<int2*>(checkpoints_dev));
     return cuda_status("read_end_kernel");
 }
 
 extern "C" int nsnp_hap_group_matrices(const nsnp_reads_t* reads_dev, const uint8_t* hp_dev, const int32_t* end_dev, const int32_t* end_pm_dev,
+                                       const int32_t* checkpoints_dev,
                                        const int32_t* dup_prev_dev, const int32_t* dup_next_dev, const int32_t* gpos_dev,
                                        const int32_t* fetch_lo_dev, int64_t n_groups, int32_t n_hap, int32_t flank, int32_t cap,
                                        int32_t* n_cols_dev, int32_t* depth_dev, int32_t* flags_dev, int32_t* const* hap_dev,
@@ -261,7 +283,7 @@ extern "C" int nsnp_hap_group_matrices(const nsnp_reads_t* reads_dev, const uint
     if ((dup_prev_dev == nullptr) != (dup_next_dev == nullptr)) return set_error(NSNP_E_INVALID, "nsnp_hap_group_matrices: dup_prev and dup_next go together");
     if (n_groups <= 0) return NSNP_OK;
     GroupArgs a;
-    a.rd = *reads_dev; a.hp = hp_dev; a.end = end_dev; a.end_pm = end_pm_dev; a.dup_prev = dup_prev_dev; a.dup_next = dup_next_dev;
+    a.rd = *reads_dev; a.hp = hp_dev; a.end = end_dev; a.end_pm = end_pm_dev; a.ck = reinterpret_cast<const int2*>(checkpoints_dev); a.dup_prev = dup_prev_dev; a.dup_next = dup_next_dev;
     a.gpos = gpos_dev; a.fetch_lo = fetch_lo_dev; a.n_groups = n_groups; a.n_hap = n_hap; a.flank = flank; a.cap = cap;
     a.n_cols = n_cols_dev; a.depth = depth_dev; a.gflags = flags_dev;
     for (int k = 0; k < 4; ++k) { a.hap[k] = hap_dev ? hap_dev[k] : nullptr; a.pile[k] = pile_dev ? pile_dev[k] : nullptr; }

@@ -141,6 +141,7 @@ class ContigAlignments:
     hp: torch.Tensor                    # uint8 [n]
     end: torch.Tensor                   # int32 [n]
     end_pm: torch.Tensor                # int32 [n] running maximum
+    ck: Optional[torch.Tensor]          # int32 [2 * nsnp_hap_checkpoint_count] CIGAR checkpoints
     dup_prev: Optional[torch.Tensor]    # int32 [n] or None
     dup_next: Optional[torch.Tensor]
     device: torch.device
@@ -177,13 +178,21 @@ def upload_alignments(reads: PackedReads, aux: ReadAux, device="cuda:0") -> Cont
     if qual.numel() < reads.n_bases:
         qual = torch.cat([qual, torch.zeros(reads.n_bases - qual.numel(), dtype=torch.uint8, device=device)])
     hp = torch.from_numpy(np.ascontiguousarray(aux.hp)).to(device)
+    end, end_pm, ck = read_ends(rd, device)
+    return ContigAlignments(rd, qual, hp, end, end_pm, ck, None if prev is None else torch.from_numpy(prev).to(device),
+                            None if nxt is None else torch.from_numpy(nxt).to(device), device)
+
+
+def read_ends(rd: PackedReads, device):
+    """(end, running maximum of end, CIGAR checkpoints) of device-resident reads."""
+    lib = _lib.load()
+    n = rd.n_reads
     end = torch.empty(max(1, n), dtype=torch.int32, device=device)
+    ck = torch.empty(2 * int(lib.nsnp_hap_checkpoint_count(n, rd.n_cigar)), dtype=torch.int32, device=device)
     st = rd.as_struct()
     with torch.cuda.device(device):
-        _lib.check(lib.nsnp_hap_read_ends(C.byref(st), end.data_ptr(), _stream(device)))
-    end_pm = torch.cummax(end[:n], 0).values.contiguous() if n else end
-    return ContigAlignments(rd, qual, hp, end, end_pm, None if prev is None else torch.from_numpy(prev).to(device),
-                            None if nxt is None else torch.from_numpy(nxt).to(device), device)
+        _lib.check(lib.nsnp_hap_read_ends(C.byref(st), end.data_ptr(), ck.data_ptr(), _stream(device)))
+    return end, (torch.cummax(end[:n], 0).values.contiguous() if n else end), ck
 
 
 def _launch(al: ContigAlignments, gpos: torch.Tensor, fetch_lo: torch.Tensor, flank: int, cap: int, want_matrices: bool):
@@ -202,7 +211,7 @@ def _launch(al: ContigAlignments, gpos: torch.Tensor, fetch_lo: torch.Tensor, fl
         hp_ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in hap]); pl_ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in pile])
     st = al.struct()
     with torch.cuda.device(dev):
-        _lib.check(lib.nsnp_hap_group_matrices(C.byref(st), al.hp.data_ptr(), al.end.data_ptr(), al.end_pm.data_ptr(),
+        _lib.check(lib.nsnp_hap_group_matrices(C.byref(st), al.hp.data_ptr(), al.end.data_ptr(), al.end_pm.data_ptr(), 0 if al.ck is None else al.ck.data_ptr(),
                                                0 if al.dup_prev is None else al.dup_prev.data_ptr(), 0 if al.dup_next is None else al.dup_next.data_ptr(),
                                                gpos.data_ptr(), fetch_lo.data_ptr(), G, n_hap, flank, cap, n_cols.data_ptr(), depth.data_ptr(),
                                                flags.data_ptr(), hp_ptrs, pl_ptrs, _stream(dev)))
@@ -231,8 +240,9 @@ def group_matrices(al: ContigAlignments, groups: np.ndarray, subgroups: List[Tup
     # first sweep (:39-60): depth of the group sites; the sweep starts at the sub-group's first site
     first = np.array([groups[lo:hi].min() for lo, hi in subgroups], np.int64)
     gp = torch.from_numpy(groups.astype(np.int32)).to(dev)
-    n1, _, _, _, _ = _launch(al, gp, torch.from_numpy(first[sub].astype(np.int32)).to(dev), -1, 0, False)
+    n1, d1, _, _, _ = _launch(al, gp, torch.from_numpy(first[sub].astype(np.int32)).to(dev), -1, 0, False)
     alive = ~(n1.cpu().numpy() > max_coverage).any(axis=1)
+    d1 = d1.cpu().numpy()
     idx = np.nonzero(alive)[0]
     empty = GroupMatrices(np.zeros((0, n_hap), np.int64), np.zeros(0, np.int32), [torch.zeros((0, 1, n_hap), dtype=torch.int32, device=dev)] * 4,
                           [torch.zeros((0, 1, 2 * flank + 1), dtype=torch.int32, device=dev)] * 4, np.zeros(0, np.int64))
@@ -245,8 +255,7 @@ def group_matrices(al: ContigAlignments, groups: np.ndarray, subgroups: List[Tup
     np.minimum.at(start, s2, col_lo)
     gp2 = torch.from_numpy(g2.astype(np.int32)).to(dev)
     flo2 = torch.from_numpy(start[s2].astype(np.int32)).to(dev)
-    _, d1, _, _, _ = _launch(al, gp2, flo2, flank, 0, False)                     # rows per group -> capacity
-    cap = max(1, int(d1.max().item()))
+    cap = max(1, int(d1[idx].max()))              # rows need the centre covered, so they do not depend on where a sweep starts
     n2, depth, flags, hap, pile = _launch(al, gp2, flo2, flank, cap, True)
     n2 = n2.cpu().numpy(); fl = flags.cpu().numpy(); depth = depth.cpu().numpy()
     if (fl & 2).any():

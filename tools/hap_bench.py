@@ -27,11 +27,8 @@ n = reads.n_reads
 g = torch.Generator(device="cpu"); g.manual_seed(7)
 qual = torch.randint(1, 42, (reads.n_bases,), dtype=torch.uint8, generator=g).to(dev)
 hp = torch.randint(0, 3, (n,), dtype=torch.uint8, generator=g).to(dev)
-lib = _lib.load()
-end = torch.empty(n, dtype=torch.int32, device=dev)
-st = reads.as_struct()
-_lib.check(lib.nsnp_hap_read_ends(C.byref(st), end.data_ptr(), torch.cuda.current_stream().cuda_stream))
-al = hg.ContigAlignments(reads, qual, hp, end, torch.cummax(end, 0).values.contiguous(), None, None, dev)
+end, end_pm, ck = hg.read_ends(reads, dev)
+al = hg.ContigAlignments(reads, qual, hp, end, end_pm, ck if os.environ.get("HAP_NO_CK") is None else None, None, None, dev)
 
 # sites every ~1 kb, a third of them low-quality candidates (human: ~1 het SNP per kb)
 rng = np.random.default_rng(3)

@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--precision", default="f16x3", choices=["fp32", "f16x3"])
+    ap.add_argument("--weights", default=None, help="checkpoint: the reference's .chkpt or a flat .npz (default: the committed fixture of the shipped one)")
     ap.add_argument("--genome-scale", type=float, default=1.0, help="N > 1: shrink every contig of the 3.1 Gb genome (smoke runs)")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the secondary weak-scaling line")
     ap.add_argument("--no-selfcheck", action="store_true")
@@ -57,9 +58,15 @@ def synth_cfg(args, rank, contig_len):
                        seed_ref=1000 + rank, seed_var=2000 + rank, seed_reads=3000 + rank)
 
 
-def load_weights():
-    from nanosnp_b200.utils import load_weights_npz     # the committed checkpoint fixture (flat .npz of the shipped .chkpt)
-    return load_weights_npz(ROOT / "tests" / "golden" / "ont_pileup_weights.npz")
+def load_weights(path=None):
+    """The committed checkpoint fixture (flat .npz of the shipped ont_pileup.chkpt), or --weights: a .npz of that form or the
+    reference's own .chkpt (torch.save of {'encoder': ..., 'forward_layer': ...}, PileupModel/utils.py:67-77)."""
+    from nanosnp_b200.utils import load_weights_npz
+    if path and not str(path).endswith(".npz"):
+        import torch
+        ck = torch.load(path, map_location="cpu")
+        return tuple({k: v.detach().cpu().numpy() for k, v in ck[part].items()} for part in ("encoder", "forward_layer"))
+    return load_weights_npz(path or ROOT / "tests" / "golden" / "ont_pileup_weights.npz")
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -70,7 +77,7 @@ def cpu_reference_run(args, steps, warmup):
     cores = os.cpu_count() or 1
     cfg = synth_cfg(args, 0, args.cpu_sample_kb * 1e3)
     ref, reads = generate_host(cfg)
-    weights = load_weights()
+    weights = load_weights(args.weights)
     times, res = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -228,7 +235,7 @@ def main_ours(args):
     K, W = args.steps, max(args.warmup, 3)
     lib = _lib.load()
     eng = PileupEngine(dev)
-    enc, fwd = load_weights()
+    enc, fwd = load_weights(args.weights)
     prec = _lib.PREC_FP32 if args.precision == "fp32" else _lib.PREC_F16X3
     model = PileupModelForward(PileupModelWeights(enc, fwd, device=dev), precision=prec)
     runner = RegionRunner(eng, model, records=True)        # device-resident result = compact site records (fused s1 -> s2 hand-off)

@@ -24,7 +24,7 @@ def _compare_vcf(got_text, ref_text):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "f16x3"])
-def test_predict_cli_from_pd_text_and_from_reads(tmp_path, golden, small_case, precision):
+def test_predict_cli_from_pd_text_and_from_reads(tmp_path, golden, golden_weights, small_case, precision):
     from nanosnp_b200 import predict as P
     from nanosnp_b200.dataset import save_reads_npz
     from oracle.pyoracle import write_fasta
@@ -57,6 +57,15 @@ def test_predict_cli_from_pd_text_and_from_reads(tmp_path, golden, small_case, p
     P.main(["-config", cfg, "-model_path", str(golden / "ont_pileup_weights.npz"), "-data", bam, "-reference", fa, "-output", out3,
             "--precision", precision])
     assert open(out3).read() == open(out1).read()
+    # (d) the checkpoint as the reference ships it: torch.save({'encoder': state_dict, 'forward_layer': state_dict}) (utils.py:67-77)
+    import torch
+    enc, fwd = golden_weights
+    ck = str(tmp_path / "ont_pileup.chkpt")
+    torch.save({"encoder": {k: torch.from_numpy(np.array(v)) for k, v in enc.items()},
+                "forward_layer": {k: torch.from_numpy(np.array(v)) for k, v in fwd.items()}, "epoch": 0}, ck)
+    out4 = str(tmp_path / "d.vcf")
+    P.main(["-config", cfg, "-model_path", ck, "-data", str(d2), "-reference", fa, "-output", out4, "--precision", precision])
+    assert open(out4).read() == open(out1).read()
     with pytest.raises(SystemExit):
         P.main(["-config", cfg, "-model_path", "x", "-data", str(d2), "-reference", fa, "-output", out2, "--no_cuda"])
 

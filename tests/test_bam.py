@@ -150,3 +150,37 @@ def test_index_fetch_and_contig_skip(tmp_path):
         assert only == [("ctg2", rd2.n_reads)] and r.inflated_bytes < 0.6 * total
     with BamReader(path) as r:
         assert r.fetch(1, 0, 10).n_reads == 0
+
+
+def test_spec_built_aux_tags_hp_and_qualities(tmp_path):
+    """keep_aux: the HP tag is found behind every other aux type of the SAM spec (A c C s S i I f Z H B) and in every integer
+    encoding htslib may choose for it; qualities come back at the reads' base offsets; the name hash is FNV-1a of QNAME."""
+    import struct
+    from nanosnp_b200.bam import BamReader, qname_hash
+    hdr_text = b"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:cA\tLN:1000\n"
+    raw = b"BAM\x01" + struct.pack("<i", len(hdr_text)) + hdr_text + struct.pack("<i", 1) + struct.pack("<i", 3) + b"cA\0" + struct.pack("<i", 1000)
+    junk = (b"XAAq" + b"Xcc\xfe" + b"XCC\x07" + b"Xss" + struct.pack("<h", -300) + b"XSS" + struct.pack("<H", 60000) + b"Xii" + struct.pack("<i", -7)
+            + b"XII" + struct.pack("<I", 4000000000) + b"Xff" + struct.pack("<f", 1.5) + b"XZZHP:i:2 not a tag\0" + b"XHH1AE3\0"
+            + b"XBBs" + struct.pack("<I", 3) + struct.pack("<hhh", 1, 2, 3) + b"XDBC" + struct.pack("<I", 2) + b"HP")
+    cases = [(b"HPC\x01", 1), (b"HPc\x02", 2), (b"HPS" + struct.pack("<H", 2), 2), (b"HPs" + struct.pack("<h", 1), 1),
+             (b"HPi" + struct.pack("<i", 2), 2), (b"HPI" + struct.pack("<I", 1), 1), (b"", 0), (b"PSi" + struct.pack("<i", 77), 0)]
+    recs, names, quals = b"", [], []
+    for k, (tag, _) in enumerate(cases):
+        name = b"read/%d\0" % k
+        seq = "ACGTACGTA"[: 5 + (k % 5)]
+        q = bytes((7 * k + j) % 60 for j in range(len(seq)))
+        body = _bam_record(0, 10 + k, 60, 0, [(len(seq), "M")], seq, tags=(junk + tag) if k % 2 == 0 else (tag + junk), name=name)
+        # _bam_record writes 0xFF qualities: patch the real ones in (they follow the packed sequence)
+        off = 4 + 32 + len(name) + 4 + (len(seq) + 1) // 2
+        body = body[:off] + q + body[off + len(seq):]
+        recs += body; names.append(name[:-1].decode()); quals.append(q)
+    path = tmp_path / "aux.bam"
+    path.write_bytes(_bgzf_block(raw + recs) + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    with BamReader(str(path), keep_aux=True) as r:
+        (_, _, rd), = list(r.contigs())
+        ax = r.aux
+    assert list(ax.hp) == [v for _, v in cases]
+    assert list(ax.qhash) == [qname_hash(n) for n in names]
+    for i, q in enumerate(quals):
+        so = int(rd.seq_off[i])
+        assert bytes(ax.qual[so:so + len(q)]) == q

@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--genome-scale", type=float, default=1.0, help="N > 1: shrink every contig of the 3.1 Gb genome (smoke runs)")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the secondary weak-scaling line")
     ap.add_argument("--no-selfcheck", action="store_true")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the secondary NSNP_PREC_F16X1 measurement")
     ap.add_argument("--write-vcf", action="store_true", help="N > 1: also place the text segments into ONE file on /dev/shm inside the timed region")
     return ap.parse_args()
 
@@ -381,6 +382,38 @@ def main_ours(args):
                 if not ok:
                     raise SystemExit(f"bench.py self-check failed: {res['selfcheck']}")
             del host_regions
+        if with_selfcheck and not args.no_fast_mode and args.precision == "f16x3":
+            # secondary, outside the timed region of the headline: the opt-in single-pass mode (NSNP_PREC_F16X1: one fp16 MMA per
+            # product, low-margin sites re-evaluated with the three-pass path) on the same device-resident workload, and its
+            # records of one region against the headline path's: calls must be identical, QUAL may drift
+            x1 = PileupModelForward(model.w, _lib.PREC_F16X1)
+            r1 = RegionRunner(eng, x1, records=True)
+
+            def step1():
+                return sum(r1.run_device(rd, rf, rg).n for rg, rd, rf in work)
+            step1()
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(steps):
+                n1 = step1()
+            q1.record(); torch.cuda.synchronize()
+            ms1 = q0.elapsed_time(q1)
+            rec3 = runner.run_device(dev_regions[0], ref, regions[0]).rec.clone().cpu().numpy()
+            rec1 = r1.run_device(dev_regions[0], ref, regions[0]).rec.clone().cpu().numpy()
+            n_low = x1.reevaluated()
+            same_calls = bool(rec1.shape == rec3.shape and (rec1[:, [0, 1, 3]] == rec3[:, [0, 1, 3]]).all() and ((rec1[:, 2] & 1) == (rec3[:, 2] & 1)).all()
+                              and (rec1[:, 4:8] == rec3[:, 4:8]).all() and (rec1[:, 16:24] == rec3[:, 16:24]).all())
+            qa = np.ascontiguousarray(rec1[:, 8:16]).view(np.int32).astype(np.int64); qb = np.ascontiguousarray(rec3[:, 8:16]).view(np.int32).astype(np.int64)
+            res["fast_mode"] = {"precision": "f16x1: one fp16 tensor-core pass per product, fp32 accumulate; sites with a top-2 margin < 0.02 re-evaluated with the three-pass path",
+                                "value": n1 * steps / (ms1 * 1e-3), "unit": "sites/s", "ms_per_step": ms1 / steps, "steps": steps,
+                                "calls_identical_to_headline_path": same_calls, "qual_drift_max": float(np.abs(qa - qb).max()) / 100.0,
+                                "records_with_other_qual_pct": float(((qa != qb).any(axis=1)).mean() * 100.0),
+                                "reevaluated_sites_in_region0": int(n_low), "sites_in_region0": int(rec3.shape[0]),
+                                "note": "opt-in (LSTMNetwork(precision='f16x1') / --precision f16x1); not the headline: QUAL text differs from the three-pass path on ~3 % of the records (by at most 0.06)"}
+            if not same_calls:
+                raise SystemExit(f"bench.py: single-pass mode changed a call: {res['fast_mode']}")
+            del x1, r1, rec1, rec3
         return res
 
     # ================================================================ genome-shaped strong scaling (N > 1)
@@ -583,6 +616,8 @@ def main_ours(args):
         line["weak"] = weak
     if main_res.get("selfcheck"):
         line["selfcheck"] = main_res["selfcheck"]
+    if main_res.get("fast_mode"):
+        line["fast_mode"] = main_res["fast_mode"]
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, 1, 0)
         line["cpu_baseline"] = {"value": r["value"], "unit": "sites/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],

@@ -161,12 +161,19 @@ int nsnp_pileup_model_forward(const void* blob_dev, const int32_t* x_i32_dev, co
                               void* workspace_dev, size_t workspace_bytes, int precision, void* stream);
 /* Same network, reading each site's window straight from the count tensor of its region: a window is the contiguous row span
  * counts[pos - 16 .. pos + 16] (create_pileup_tensor, main.cpp:220-251), so the [n][33][18] tensor of the dataset seam need not
- * be materialised between s1 and s2 (saves one 4.7 KB/site gather and its read-back).  NSNP_PREC_F16X3 only. */
+ * be materialised between s1 and s2 (saves one 4.7 KB/site gather and its read-back).  NSNP_PREC_F16X3 / F16X1 only. */
 int nsnp_pileup_model_forward_sites(const void* blob_dev, const int32_t* counts_dev, int64_t region_start, int64_t region_len,
                                     const int32_t* pos_dev, int64_t n, const int32_t* n_dev, float* gt_prob_dev, float* zy_prob_dev,
                                     void* workspace_dev, size_t workspace_bytes, int precision, void* stream);
 #define NSNP_PREC_FP32    0   /* fp32 FFMA everywhere (parity path) */
 #define NSNP_PREC_F16X3   1   /* tcgen05 tensor-core path: fp16 hi/lo split operands (3 MMAs per product), fp32 accumulate */
+#define NSNP_PREC_F16X1   2   /* opt-in: ONE fp16 MMA per product (operands rounded to fp16, fp32 accumulate), then every site whose
+                                 top-2 margin is below 0.02 in either head is re-evaluated with NSNP_PREC_F16X3 (<= 4096 per call), so
+                                 the genotype / zygosity calls are those of NSNP_PREC_F16X3; other sites: |dp| < 5e-3 (observed 3e-3),
+                                 QUAL may move by up to ~0.06.  Batches of <= 16384 sites run NSNP_PREC_F16X3 directly. */
+/* NSNP_PREC_F16X1: number of low-margin sites the LAST forward call on this workspace found (synchronises the stream);
+ * NSNP_E_OVERFLOW when it exceeded the 4096 that were re-evaluated. */
+int nsnp_model_f16x1_reevaluated(const void* workspace_dev, int64_t n_sites, int64_t* count_out, void* stream);
 
 /* debug aid for the tensor-core path: raw gate pre-activations [m][256] (TMEM column order) of the FIRST step of one
  * (layer, direction); cg = 1 or 2 CTAs per MMA.  Used by the GPU tests to validate operand layouts. */

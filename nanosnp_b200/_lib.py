@@ -17,7 +17,7 @@ OK, E_INVALID, E_CUDA, E_WORKSPACE, E_OVERFLOW, E_NO_DEVICE, E_UNSUPPORTED = 0, 
 CHANNELS, FLANK, WINDOW = 18, 16, 33
 GT_CLASSES, ZY_CLASSES = 21, 3
 F_COVERED, F_GATE = 1, 2
-PREC_FP32, PREC_F16X3 = 0, 1
+PREC_FP32, PREC_F16X3, PREC_F16X1 = 0, 1, 2
 PROF_SLOTS = ("read_scan_kernel", "pileup_tile_kernel", "select_kernels", "gather_kernel", "lstm_layer0", "lstm_layer1", "tail_kernel", "site_record_kernel", "vcf_text_kernels")
 
 
@@ -95,6 +95,7 @@ SYMBOLS = {
     "nsnp_pileup_model_forward_sites": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, _P, _P, _P, _SZ, C.c_int, _P]),
     "nsnp_site_records_sites": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P]),
     "nsnp_debug_lstm_tc_gates": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _I64, _P]),
+    "nsnp_model_f16x1_reevaluated": (C.c_int, [_P, _I64, _P, _P]),
     "nsnp_hap_features": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P]),
     "nsnp_hap_model_blob_bytes": (_SZ, []),
     "nsnp_hap_model_pack_weights": (C.c_int, [C.POINTER(HapWeights), _P, _SZ]),

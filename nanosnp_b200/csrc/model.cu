@@ -241,6 +241,54 @@ constexpr size_t kTailSmem = (size_t)kTailS * (128 + 256) * sizeof(float);
 // (16.9 KB per site).  NSNP_CHUNK_WAVES (experiments) scales it.
 static const int64_t kChunkSites = [] { const char* v = getenv("NSNP_CHUNK_WAVES"); const int w = v ? atoi(v) : 4; return (int64_t)148 * 128 * (w < 1 ? 1 : w); }();
 
+
+// ---- NSNP_PREC_F16X1: single-pass tensor-core LSTM + re-evaluation of the low-margin sites in NSNP_PREC_F16X3 -------------
+// One fp16 MMA per product leaves operand rounding errors of 2^-11: |dp| up to 3e-3 (profiles/r02_precision_experiment.md),
+// enough to flip an argmax only where the two best classes of a head are closer than that.  Every site whose top-2 margin is
+// below kX1Margin in EITHER head is therefore run again through the three-pass path (its result replaces the single-pass
+// one), so genotype / zygosity calls are those of NSNP_PREC_F16X3; the other sites keep probabilities within the stated 5e-3.
+constexpr float kX1Margin = 0.02f;           // > 6x the largest single-pass error observed
+constexpr int kX1Cap = 4096;                 // re-evaluated sites per call (expected: ~0.07 % of the sites); beyond it
+                                             // nsnp_model_f16x1_reevaluated reports the overflow
+struct X1Work { int32_t* cnt; int32_t* idx; int32_t* pos_low; float* gt_low; float* zy_low; int32_t* x_low; };
+constexpr size_t kX1FixedBytes = 256 + (size_t)kX1Cap * (4 + 4 + 24 * 4);
+constexpr size_t kX1WindowBytes = (size_t)kX1Cap * kT * kF * 4;
+
+__global__ void x1_margin_kernel(const float* __restrict__ gt, const float* __restrict__ zy, int64_t n, const int32_t* __restrict__ n_dev,
+                                 float tau, int32_t* __restrict__ cnt, int32_t* __restrict__ idx)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (n_dev && i >= *n_dev)) return;
+    float a = -1.f, b = -1.f;
+    for (int k = 0; k < 21; ++k) { const float v = gt[i * 21 + k]; if (v > a) { b = a; a = v; } else if (v > b) b = v; }
+    float c = -1.f, d = -1.f;
+    for (int k = 0; k < 3; ++k) { const float v = zy[i * 3 + k]; if (v > c) { d = c; c = v; } else if (v > d) d = v; }
+    if (!(a - b >= tau) || !(c - d >= tau)) {                 // also catches NaN
+        const int k = atomicAdd(cnt, 1);
+        if (k < kX1Cap) idx[k] = (int32_t)i;
+    }
+}
+// inputs of the re-evaluation batch (always kX1Cap sites: slots beyond the count repeat site 0, their results are dropped)
+__global__ void x1_gather_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ idx, const int32_t* __restrict__ pos,
+                                 const int32_t* __restrict__ x, const float* __restrict__ xf, int32_t* __restrict__ pos_low, int32_t* __restrict__ x_low)
+{
+    const int k = blockIdx.x;
+    const int m = min(*cnt, kX1Cap);
+    const int64_t src = k < m ? idx[k] : 0;
+    if (pos) { if (threadIdx.x == 0) pos_low[k] = pos[src]; return; }
+    const int32_t* from = x ? x : reinterpret_cast<const int32_t*>(xf);          // 4-byte words either way
+    for (int j = threadIdx.x; j < kT * kF; j += blockDim.x) x_low[(int64_t)k * kT * kF + j] = from[src * kT * kF + j];
+}
+__global__ void x1_scatter_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ idx, const float* __restrict__ gt_low,
+                                  const float* __restrict__ zy_low, float* __restrict__ gt, float* __restrict__ zy)
+{
+    const int k = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= min(*cnt, kX1Cap)) return;
+    const int64_t dst = idx[k];
+    if (lane < 21) gt[dst * 21 + lane] = gt_low[(int64_t)k * 21 + lane];
+    else if (lane < 24) zy[dst * 3 + lane - 21] = zy_low[(int64_t)k * 3 + lane - 21];
+}
+
 }  // namespace
 }  // namespace nsnp
 
@@ -300,7 +348,33 @@ size_t nsnp_model_workspace_bytes(int64_t n_sites) {
     ch = (ch + 127) / 128 * 128;                      // the tensor-core path stores layer-0 output in whole 128-site tiles
     // layer-0 output of one chunk + the t = 16 state of ALL sites (the tail runs once per call, not once per chunk)
     const int64_t np = ((n_sites < 1 ? 1 : n_sites) + 127) / 128 * 128;
-    return (size_t)ch * kT * 128 * sizeof(float) + (size_t)np * 128 * sizeof(float) + 256;
+    // + the re-evaluation batch of NSNP_PREC_F16X1 (index list, outputs, gathered windows for the window-tensor entry point)
+    return (size_t)ch * kT * 128 * sizeof(float) + (size_t)np * 128 * sizeof(float) + 256 + kX1FixedBytes + kX1WindowBytes;
+}
+
+static X1Work x1_carve(void* workspace_dev, int64_t n) {
+    const int64_t ch0 = n < kChunkSites ? n : kChunkSites;
+    const int64_t ch = ((ch0 < 1 ? 1 : ch0) + 127) / 128 * 128, np = ((n < 1 ? 1 : n) + 127) / 128 * 128;
+    char* p = (char*)workspace_dev + ((size_t)ch * kT * 128 + (size_t)np * 128) * sizeof(float) + 256;
+    X1Work w;
+    w.cnt = (int32_t*)p; p += 256;
+    w.idx = (int32_t*)p; p += (size_t)kX1Cap * 4;
+    w.pos_low = (int32_t*)p; p += (size_t)kX1Cap * 4;
+    w.gt_low = (float*)p; p += (size_t)kX1Cap * 21 * 4;
+    w.zy_low = (float*)p; p += (size_t)kX1Cap * 3 * 4;
+    w.x_low = (int32_t*)p;
+    return w;
+}
+
+int nsnp_model_f16x1_reevaluated(const void* workspace_dev, int64_t n_sites, int64_t* count_out, void* stream_) {
+    if (!workspace_dev || !count_out) return set_error(NSNP_E_INVALID, "nsnp_model_f16x1_reevaluated: null argument");
+    const X1Work w = x1_carve(const_cast<void*>(workspace_dev), n_sites);
+    int32_t c = 0;
+    if (cudaMemcpyAsync(&c, w.cnt, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream_) != cudaSuccess || cudaStreamSynchronize((cudaStream_t)stream_) != cudaSuccess)
+        return cuda_status("nsnp_model_f16x1_reevaluated");
+    *count_out = c;
+    if (c > kX1Cap) return set_error(NSNP_E_OVERFLOW, "NSNP_PREC_F16X1: %d low-margin sites in one call, only %d were re-evaluated; use NSNP_PREC_F16X3 for this input", c, kX1Cap);
+    return NSNP_OK;
 }
 
 static int model_forward(const void* blob_dev, const int32_t* x_i32_dev, const float* x_f32_dev, int64_t n,
@@ -320,7 +394,7 @@ int nsnp_pileup_model_forward_sites(const void* blob_dev, const int32_t* counts_
 {
     if (n == 0) return NSNP_OK;
     if (!counts_dev || !pos_dev || region_len < NSNP_WINDOW) return set_error(NSNP_E_INVALID, "nsnp_pileup_model_forward_sites: bad argument");
-    if (precision != NSNP_PREC_F16X3) return set_error(NSNP_E_UNSUPPORTED, "window reads from the count tensor are built for NSNP_PREC_F16X3; gather the windows for the fp32 path");
+    if (precision != NSNP_PREC_F16X3 && precision != NSNP_PREC_F16X1) return set_error(NSNP_E_UNSUPPORTED, "window reads from the count tensor are built for the tensor-core path; gather the windows for the fp32 path");
     return model_forward(blob_dev, counts_dev, nullptr, n, n_dev, gt_prob_dev, zy_prob_dev, workspace_dev, workspace_bytes, precision, pos_dev,
                          region_start + NSNP_FLANK, stream_);
 }
@@ -333,7 +407,7 @@ static int model_forward(const void* blob_dev, const int32_t* x_i32_dev, const f
     if (n == 0) return NSNP_OK;          // empty batch: nothing to launch (pointers of empty tensors may be null)
     if (!blob_dev || (!x_i32_dev == !x_f32_dev) || !gt_prob_dev || !zy_prob_dev || !workspace_dev)
         return set_error(NSNP_E_INVALID, "nsnp_pileup_model_forward: null argument (exactly one of x_i32/x_f32)");
-    if (precision != NSNP_PREC_FP32 && precision != NSNP_PREC_F16X3) return set_error(NSNP_E_UNSUPPORTED, "unknown precision %d", precision);
+    if (precision != NSNP_PREC_FP32 && precision != NSNP_PREC_F16X3 && precision != NSNP_PREC_F16X1) return set_error(NSNP_E_UNSUPPORTED, "unknown precision %d", precision);
     if (n < 0) return set_error(NSNP_E_INVALID, "negative n");
     if (workspace_bytes < nsnp_model_workspace_bytes(n)) return set_error(NSNP_E_WORKSPACE, "model workspace too small");
     if (nsnp_device_count() == 0) return set_error(NSNP_E_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
@@ -352,7 +426,10 @@ static int model_forward(const void* blob_dev, const int32_t* x_i32_dev, const f
     float* h0 = (float*)workspace_dev;
     const int64_t ch = n < kChunkSites ? n : kChunkSites;
     static const bool tail_tc_env = [] { const char* v = getenv("NSNP_TAIL_TC"); return !(v && v[0] == '0'); }();
-    const bool tail_tc = tail_tc_env && precision == NSNP_PREC_F16X3;
+    const bool tc = precision == NSNP_PREC_F16X3 || precision == NSNP_PREC_F16X1;
+    // single pass only pays for batches well above the re-evaluation batch; smaller ones run the three-pass path directly
+    const bool x1 = precision == NSNP_PREC_F16X1 && n > 4 * (int64_t)kX1Cap;
+    const bool tail_tc = tail_tc_env && tc;
     float* h16 = h0 + ((ch + 127) / 128 * 128) * kT * 128;
     // n_dev (device-side site count) only makes sense for a single chunk; larger batches are chunked by the host count
     for (int64_t off = 0; off < n; off += ch) {
@@ -361,21 +438,36 @@ static int model_forward(const void* blob_dev, const int32_t* x_i32_dev, const f
         const int32_t* xi = x_i32_dev ? (pos_dev ? x_i32_dev : x_i32_dev + off * kT * kF) : nullptr;       // pos_dev: the count tensor itself
         const float* xf = x_f32_dev ? x_f32_dev + off * kT * kF : nullptr;
         dim3 g0((unsigned)((m + Cfg<0>::S - 1) / Cfg<0>::S), 2), g1((unsigned)((m + Cfg<1>::S - 1) / Cfg<1>::S), 2);
-        if (precision == NSNP_PREC_F16X3) {
-            if (int e = launch_lstm_tc(blob_dev, xi, xf, h0, h16 + off * 128, m, pos_dev ? pos_dev + off : nullptr, pos_bias, stream)) return e;
+        if (tc) {
+            if (int e = launch_lstm_tc(blob_dev, xi, xf, h0, h16 + off * 128, m, pos_dev ? pos_dev + off : nullptr, pos_bias, x1 ? 1 : 3, stream)) return e;
             if (tail_tc) continue;                   // one tensor-core tail launch over all chunks below
         } else {
             { ProfScope prof(NSNP_PROF_LSTM0, stream); lstm_dir_kernel<0><<<g0, 256, smem0, stream>>>(blob, xi, xf, nullptr, h0, m, nd); }
             { ProfScope prof(NSNP_PROF_LSTM1, stream); lstm_dir_kernel<1><<<g1, 256, smem1, stream>>>(blob, nullptr, nullptr, h0, h16, m, nd); }
         }
         ProfScope prof(NSNP_PROF_TAIL, stream);
-        tail_kernel<<<(unsigned)((m + kTailS - 1) / kTailS), 256, kTailSmem, stream>>>(blob, h16 + (precision == NSNP_PREC_F16X3 ? off * 128 : 0), m, nd,
+        tail_kernel<<<(unsigned)((m + kTailS - 1) / kTailS), 256, kTailSmem, stream>>>(blob, h16 + (tc ? off * 128 : 0), m, nd,
                                                                                          gt_prob_dev + off * 21, zy_prob_dev + off * 3);
         if (int e = cuda_status("pileup model kernels")) return e;
     }
-    if (precision == NSNP_PREC_F16X3 && tail_tc) {
+    if (tc && tail_tc) {
         ProfScope prof(NSNP_PROF_TAIL, stream);
         if (int e = launch_tail_tc(blob_dev, h16, n, n <= ch ? n_dev : nullptr, gt_prob_dev, zy_prob_dev, stream)) return e;
+    }
+    if (precision == NSNP_PREC_F16X1 && cudaMemsetAsync(x1_carve(workspace_dev, n).cnt, 0, 4, stream) != cudaSuccess) return cuda_status("cudaMemsetAsync");
+    if (x1) {
+        // low-margin sites -> one three-pass batch of kX1Cap sites (layer-0 buffer and h16 of the main pass are free again)
+        const X1Work w = x1_carve(workspace_dev, n);
+        x1_margin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gt_prob_dev, zy_prob_dev, n, n <= ch ? n_dev : nullptr, kX1Margin, w.cnt, w.idx);
+        x1_gather_kernel<<<kX1Cap, 128, 0, stream>>>(w.cnt, w.idx, pos_dev, pos_dev ? nullptr : x_i32_dev, x_f32_dev, w.pos_low, w.x_low);
+        if (int e = cuda_status("x1 margin / gather kernels")) return e;
+        const int32_t* xi_low = pos_dev ? x_i32_dev : (x_i32_dev ? w.x_low : nullptr);
+        const float* xf_low = (!pos_dev && x_f32_dev) ? reinterpret_cast<const float*>(w.x_low) : nullptr;
+        if (int e = launch_lstm_tc(blob_dev, xi_low, xf_low, h0, h16, kX1Cap, pos_dev ? w.pos_low : nullptr, pos_bias, 3, stream)) return e;
+        if (tail_tc) { if (int e = launch_tail_tc(blob_dev, h16, kX1Cap, nullptr, w.gt_low, w.zy_low, stream)) return e; }
+        else tail_kernel<<<(unsigned)((kX1Cap + kTailS - 1) / kTailS), 256, kTailSmem, stream>>>(blob, h16, kX1Cap, nullptr, w.gt_low, w.zy_low);
+        x1_scatter_kernel<<<kX1Cap / 8, 256, 0, stream>>>(w.cnt, w.idx, w.gt_low, w.zy_low, gt_prob_dev, zy_prob_dev);
+        if (int e = cuda_status("x1 re-evaluation")) return e;
     }
     return NSNP_OK;
 }

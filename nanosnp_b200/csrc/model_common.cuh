@@ -50,7 +50,7 @@ constexpr size_t kOffTcBias1 = kOffTcTail + 2 * kTcBytesTail;
 constexpr size_t kBlobBytes = kOffTcBias1 + 2 * 256 * sizeof(float);
 
 // fp16 hi/lo tensor-core LSTM (model_tc.cu).  h0: fp16 [site][33][2][128]; h16: fp32 [site][128].
-int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, const int32_t* pos, int64_t pos_bias, cudaStream_t stream);
+int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, const int32_t* pos, int64_t pos_bias, int npass, cudaStream_t stream);
 int pack_tc_weights(const nsnp_model_weights_t* w, unsigned char* blob);
 // (dense o output_proj) + tanh on the tensor cores, heads + softmax on the FMA pipe (model_tc.cu)
 int launch_tail_tc(const void* blob, const float* h16, int64_t n_max, const int32_t* n_dev, float* gt, float* zy, cudaStream_t stream);

@@ -319,6 +319,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     uint64_t* barS = bar + 2;                                        // "input part of A for the next step has landed"
     constexpr uint32_t kPartBytes = 16u * kRows * 16u;               // 32 KB
     const bool l2_prefetch = (dir_override >> 8) & 1;
+    const int npass = ((dir_override >> 16) & 3) ? ((dir_override >> 16) & 3) : 3;   // NSNP_PREC_F16X1: the hi.hi pass only
     // the padding CTA of an odd tile count (clusters come in pairs) re-reads the last real tile: it must not touch memory
     // past the layer-0 output (found by compute-sanitizer memcheck)
     const size_t src_tile = min((size_t)blockIdx.x, (size_t)((n + kRows - 1) / kRows - 1));
@@ -360,7 +361,7 @@ lstm_tc_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict
     // k-blocks [kb0, kb1) x three hi/lo passes into the accumulator at tmem_d
     auto issue = [&](int kb0, int kb1, uint32_t tmem_d, uint32_t acc) {
 #pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
+        for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll 1
             for (int kb = kb0; kb < kb1; ++kb) {
                 // pass 0: a_hi.w_hi   pass 1: a_hi.w_lo (layer-0 counts: scaled copy)   pass 2: a_lo.w_hi
@@ -517,7 +518,7 @@ struct P2Smem {
 
 __global__ void __launch_bounds__(kP2Threads, 1)
 lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __restrict__ xi, const float* __restrict__ xf,
-                   __half* __restrict__ h0_out, int64_t n, const int32_t* __restrict__ pos, int64_t pos_bias)
+                   __half* __restrict__ h0_out, int64_t n, const int32_t* __restrict__ pos, int64_t pos_bias, int npass)
 {
     // pos != nullptr: xi is the region's count tensor [L][18] and site j's window is its contiguous row span starting at
     // pos[j] - pos_bias (pos_bias = region_start + 16): the [n][33][18] feature tensor is never materialised
@@ -654,7 +655,7 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
             mbar_wait(barTurn + grp, phaseT);                      // and it is this group's turn on the tensor pipe
             tc_fence_after();
 #pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {
+            for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll 1
                 for (int kb = 0; kb < (step == 0 ? IN / 16 : KB); ++kb) {      // h = 0 at the first step of a tile: input k-blocks only
                     uint32_t aa = pass == 2 ? a_lo : a_hi;
@@ -718,7 +719,7 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
     if (threadIdx.x < 32) tmem_dealloc<2>(*tmem_slot, 512);
 }
 
-int launch_l0_pair2(const void* blob, const int32_t* xi, const float* xf, void* h0_out, int64_t m, const int32_t* pos, int64_t pos_bias, cudaStream_t stream) {
+int launch_l0_pair2(const void* blob, const int32_t* xi, const float* xf, void* h0_out, int64_t m, const int32_t* pos, int64_t pos_bias, int npass, cudaStream_t stream) {
     using S = P2Smem;
     static bool attr_done = false;
     if (!attr_done) {
@@ -738,7 +739,7 @@ int launch_l0_pair2(const void* blob, const int32_t* xi, const float* xf, void* 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, lstm0_pair2_kernel, (const unsigned char*)blob, xi, xf, (__half*)h0_out, m, pos, pos_bias);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, lstm0_pair2_kernel, (const unsigned char*)blob, xi, xf, (__half*)h0_out, m, pos, pos_bias, npass);
     if (e != cudaSuccess) return set_error(NSNP_E_CUDA, "lstm0_pair2_kernel: %s", cudaGetErrorString(e));
     return NSNP_OK;
 }
@@ -987,20 +988,20 @@ int launch_tail_tc(const void* blob, const float* h16, int64_t n_max, const int3
     return cuda_status("tail_tc_kernel");
 }
 
-int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, const int32_t* pos, int64_t pos_bias, cudaStream_t stream) {
+int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h0, float* h16, int64_t m, const int32_t* pos, int64_t pos_bias, int npass, cudaStream_t stream) {
     // layer 0: CTA pairs share W (53 KB each) so two CTAs fit per SM and one CTA's MMAs overlap the other's epilogue
     {
         ProfScope prof(NSNP_PROF_LSTM0, stream);
         // default: two alternating groups per CTA (lstm0_pair2_kernel); NSNP_L0_VARIANT=0 selects two independent CTAs per SM
         static const int variant = [] { const char* v = getenv("NSNP_L0_VARIANT"); return v ? atoi(v) : 1; }();
         if (pos && variant != 1) return set_error(NSNP_E_UNSUPPORTED, "window reads from the count tensor need the default layer-0 kernel");
-        if (int e = variant == 1 ? launch_l0_pair2(blob, xi, xf, h0, m, pos, pos_bias, stream)
-                                 : launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, 0, stream)) return e;
+        if (int e = variant == 1 ? launch_l0_pair2(blob, xi, xf, h0, m, pos, pos_bias, npass, stream)
+                                 : launch_one<0, 2, 2, false>(blob, xi, xf, nullptr, h0, nullptr, nullptr, m, npass << 16, stream)) return e;
     }
     // layer 1: W only fits split across a CTA pair (2 x 104 KB); one CTA per SM, 16 warps for the epilogue
     ProfScope prof(NSNP_PROF_LSTM1, stream);
     static const int pf = [] { const char* v = getenv("NSNP_L1_PREFETCH"); return v ? atoi(v) : 1; }();
-    return launch_one<1, 2, 4, false>(blob, nullptr, nullptr, h0, nullptr, h16, nullptr, m, pf << 8, stream);
+    return launch_one<1, 2, 4, false>(blob, nullptr, nullptr, h0, nullptr, h16, nullptr, m, (pf << 8) | (npass << 16), stream);
 }
 
 int debug_tc_gates(const void* blob, const int32_t* xi, int layer, int dir, int cg, const void* h0, float* gates_out, int64_t m, cudaStream_t stream) {

@@ -57,7 +57,7 @@ class LSTMNetwork:
         self.config = config
         self.encoder = _StateHolder(self, _ENC_KEYS)
         self.forward_layer = _StateHolder(self, _FWD_KEYS, _FWD_OPTIONAL)
-        self.precision = {"fp32": _lib.PREC_FP32, "f16x3": _lib.PREC_F16X3}[precision]
+        self.precision = {"fp32": _lib.PREC_FP32, "f16x3": _lib.PREC_F16X3, "f16x1": _lib.PREC_F16X1}[precision]
         self.device: Optional[torch.device] = None
         self._fwd: Optional[PileupModelForward] = None
 

@@ -194,6 +194,8 @@ class PileupModelForward:
         self.device = weights.device
         self.precision = precision
         self._ws = None
+        self._last_n = 0
+        self.tensor_core = precision in (_lib.PREC_F16X3, _lib.PREC_F16X1)
 
     def __call__(self, x: torch.Tensor, n_dev: Optional[torch.Tensor] = None, gt=None, zy=None):
         assert x.is_cuda and x.is_contiguous() and tuple(x.shape[1:]) == (_lib.WINDOW, _lib.CHANNELS)
@@ -202,6 +204,7 @@ class PileupModelForward:
             gt = torch.empty((n, _lib.GT_CLASSES), dtype=torch.float32, device=self.device)
         if zy is None:
             zy = torch.empty((n, _lib.ZY_CLASSES), dtype=torch.float32, device=self.device)
+        self._last_n = n
         need = self.lib.nsnp_model_workspace_bytes(n)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -217,14 +220,25 @@ class PileupModelForward:
                                                           self.precision, _stream(self.device)))
         return gt, zy
 
+    def reevaluated(self) -> int:
+        """NSNP_PREC_F16X1: low-margin sites the last call found and re-ran through the three-pass path (synchronises); raises
+        when there were more than the library re-evaluates."""
+        if self.precision != _lib.PREC_F16X1 or self._ws is None or self._last_n == 0:
+            return 0
+        c = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nsnp_model_f16x1_reevaluated(self._ws.data_ptr(), self._last_n, C.byref(c), _stream(self.device)))
+        return int(c.value)
+
     def from_counts(self, counts: torch.Tensor, region_start: int, pos: torch.Tensor, n: int, gt=None, zy=None):
         """The same forward pass with every site's window read straight from the region's count tensor [L,18] (a window is the
         contiguous row span counts[pos-16 .. pos+16]): no [n,33,18] tensor is materialised.  Tensor-core path only."""
-        assert counts.is_cuda and counts.is_contiguous() and counts.dtype == torch.int32 and self.precision == _lib.PREC_F16X3
+        assert counts.is_cuda and counts.is_contiguous() and counts.dtype == torch.int32 and self.tensor_core
         if gt is None:
             gt = torch.empty((n, _lib.GT_CLASSES), dtype=torch.float32, device=self.device)
         if zy is None:
             zy = torch.empty((n, _lib.ZY_CLASSES), dtype=torch.float32, device=self.device)
+        self._last_n = n
         need = self.lib.nsnp_model_workspace_bytes(n)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)

@@ -169,7 +169,8 @@ def main(argv=None):
     parser.add_argument("-output", required=True, help="output vcf file")
     parser.add_argument("-batch_size", type=int, default=1000, help="batch size")
     parser.add_argument("--no_cuda", action="store_true", help="refused: the B200 path has no CPU fallback")
-    parser.add_argument("--precision", default="f16x3", choices=["fp32", "f16x3"])
+    parser.add_argument("--precision", default="f16x3", choices=["fp32", "f16x3", "f16x1"],
+                        help="f16x1: single-pass tensor-core LSTM, low-margin sites re-evaluated in f16x3 (same calls, QUAL may move by ~0.06)")
     parser.add_argument("--region_len", type=int, default=12_500_000, help="positions per GPU work unit (read inputs)")
     opt = parser.parse_args(argv)
     if opt.no_cuda:

@@ -120,14 +120,14 @@ class RegionRunner:
         # fused s1 -> s2 hand-off: the model (and the record kernel) read each site's rows straight from the count tensor, the
         # [n,33,18] window tensor of the dataset seam is only materialised when the caller wants it (keep_windows) or for the
         # fp32 parity path
-        fused = self.fused and self.records and not self.keep_windows and self.model.precision == _lib.PREC_F16X3
+        fused = self.fused and self.records and not self.keep_windows and self.model.tensor_core
         if fused:
             if n:
                 timer.start("model")
                 self.model.from_counts(counts, region.start, pos, n, gt=gt, zy=zy)
                 timer.stop()
                 chunks = -(-n // 75776)
-                self.launches += 2 * chunks + 1
+                self.launches += 2 * chunks + 1 + (6 if (self.model.precision == _lib.PREC_F16X1 and n > 16384) else 0)   # + margin, gather, 2 LSTM, tail, scatter
             rec = self._buf("rec", (max(n, 1), 32), torch.uint8)[:n]
             if n:
                 eng.site_records_from_counts(gt, zy, counts, region.start, ref, pos, n, rec=rec)
@@ -143,7 +143,7 @@ class RegionRunner:
             self.model(x, gt=gt, zy=zy)
             timer.stop()
             chunks = -(-n // 75776)
-            self.launches += 1 + (2 * chunks + 1 if self.model.precision == _lib.PREC_F16X3 else 3 * chunks)   # gather + LSTM layers per chunk + tail
+            self.launches += 1 + (2 * chunks + 1 + (6 if (self.model.precision == _lib.PREC_F16X1 and n > 16384) else 0) if self.model.tensor_core else 3 * chunks)   # gather + LSTM layers per chunk + tail
         if self.records:
             rec = self._buf("rec", (max(n, 1), 32), torch.uint8)[:n]
             if n:

@@ -29,24 +29,30 @@ __device__ __forceinline__ uint32_t ld_cig(const nsnp_reads_t& rd, int64_t i) {
     return rd.cigar_bits == 16 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(rd.cigar) + i) : __ldg(rd.cigar + i);
 }
 
-constexpr int kCkShift = 5;                        // one (reference, query) checkpoint per 32 CIGAR ops
+constexpr int kCkShift = 5;                        // one (reference, query) checkpoint per 32 CIGAR ops (= one warp iteration below)
 
 // checkpoint slots of read r: (cigar_off[r] >> kCkShift) + r + j for block j of its ops
 __device__ __forceinline__ int64_t ck_slot0(const nsnp_reads_t& rd, int64_t r) { return (rd.cigar_off[r] >> kCkShift) + r; }
 
-__global__ void read_end_kernel(nsnp_reads_t rd, int32_t* __restrict__ end, int2* __restrict__ ck)
+// one warp per read: 32 ops per iteration (coalesced), the block's (reference, query) start is its checkpoint
+__global__ void __launch_bounds__(256) read_end_kernel(nsnp_reads_t rd, int32_t* __restrict__ end, int2* __restrict__ ck)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (r >= rd.n_reads) return;
     int x = rd.pos[r], y = 0;
-    const int64_t c0 = rd.cigar_off[r], s0 = ck_slot0(rd, r);
-    for (int64_t k = c0; k < rd.cigar_off[r + 1]; ++k) {
-        if (ck && ((k - c0) & ((1 << kCkShift) - 1)) == 0) ck[s0 + ((k - c0) >> kCkShift)] = make_int2(x, y);
-        const uint32_t c = ld_cig(rd, k); const int op = c & 15, len = (int)(c >> 4);
-        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) x += len;
-        if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) y += len;
+    const int64_t c0 = rd.cigar_off[r], c1 = rd.cigar_off[r + 1], s0 = ck_slot0(rd, r);
+    for (int64_t k = c0; k < c1; k += 32) {
+        if (ck && lane == 0) ck[s0 + ((k - c0) >> kCkShift)] = make_int2(x, y);
+        int rl = 0, ql = 0;
+        if (k + lane < c1) {
+            const uint32_t c = ld_cig(rd, k + lane); const int op = c & 15, len = (int)(c >> 4);
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rl = len;
+            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) ql = len;
+        }
+        x += __reduce_add_sync(0xffffffffu, rl); y += __reduce_add_sync(0xffffffffu, ql);
     }
-    end[r] = x;
+    if (lane == 0) end[r] = x;
 }
 
 __device__ __forceinline__ bool stepper_pass(uint32_t flag) {
@@ -265,7 +271,7 @@ extern "C" int nsnp_hap_read_ends(const nsnp_reads_t* reads_dev, int32_t* end_de
 {
     if (!reads_dev || !end_dev) return set_error(NSNP_E_INVALID, "nsnp_hap_read_ends: null argument");
     if (reads_dev->n_reads == 0) return NSNP_OK;
-    read_end_kernel<<<(unsigned)((reads_dev->n_reads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*reads_dev, end_dev, reinterpret_cast<int2*>(checkpoints_dev));
+    read_end_kernel<<<(unsigned)((reads_dev->n_reads + 7) / 8), 256, 0, (cudaStream_t)stream>>>(*reads_dev, end_dev, reinterpret_cast<int2*>(checkpoints_dev));
     return cuda_status("read_end_kernel");
 }
 

@@ -101,3 +101,31 @@ def test_tensor_core_random_weights(small_case):
     g0, z0 = m.predict64(x)
     g1, z1 = tc(torch.from_numpy(x).cuda())
     assert np.abs(g1.cpu().numpy() - g0.numpy()).max() < F16X3_ATOL and np.abs(z1.cpu().numpy() - z0.numpy()).max() < F16X3_ATOL
+
+
+def test_single_pass_mode_small_batches(weights, small_case):
+    """NSNP_PREC_F16X1 just above its activation threshold (16 384 sites), int32 and float32 windows, with a device-side
+    count: calls equal the three-pass path's, the low-margin sites carry its values, <= 16 384 sites are the three-pass path."""
+    import torch
+    from nanosnp_b200 import _lib
+    from nanosnp_b200.pipeline import PileupModelForward
+    tc = PileupModelForward(weights, _lib.PREC_F16X3)
+    x1 = PileupModelForward(weights, _lib.PREC_F16X1)
+    base = torch.from_numpy(small_case["windows"]).cuda()
+    x = base.repeat(4, 1, 1)[:20_001].contiguous()                  # odd tile count, one chunk
+    g3, z3 = tc(x)
+    for inp in (x, x.float()):
+        g1, z1 = x1(inp)
+        n_low = x1.reevaluated()
+        assert 0 < n_low <= 4096
+        assert torch.equal(g1.argmax(1), g3.argmax(1)) and torch.equal(z1.argmax(1), z3.argmax(1))
+        err = max(float((g1 - g3).abs().max()), float((z1 - z3).abs().max()))
+        assert 1e-5 < err < 5e-3, err
+        top = g3.topk(2, dim=1).values
+        tight = (top[:, 0] - top[:, 1]) < 0.012
+        assert int(tight.sum()) > 0 and torch.equal(g1[tight], g3[tight]) and torch.equal(z1[tight], z3[tight])
+    nd = torch.tensor([17_000], dtype=torch.int32, device="cuda")   # device-side count below the host bound
+    g1, z1 = x1(x, n_dev=nd)
+    assert torch.equal(g1[:17_000].argmax(1), g3[:17_000].argmax(1))
+    g1, z1 = x1(x[:16_384].contiguous())
+    assert torch.equal(g1, g3[:16_384]) and x1.reevaluated() == 0

@@ -171,9 +171,12 @@ int nsnp_pileup_model_forward_sites(const void* blob_dev, const int32_t* counts_
                                  top-2 margin is below 0.02 in either head is re-evaluated with NSNP_PREC_F16X3 (<= 4096 per call), so
                                  the genotype / zygosity calls are those of NSNP_PREC_F16X3; other sites: |dp| < 5e-3 (observed 3e-3),
                                  QUAL may move by up to ~0.06.  Batches of <= 16384 sites run NSNP_PREC_F16X3 directly. */
-/* NSNP_PREC_F16X1: number of low-margin sites the LAST forward call on this workspace found (synchronises the stream);
- * NSNP_E_OVERFLOW when it exceeded the 4096 that were re-evaluated. */
-int nsnp_model_f16x1_reevaluated(const void* workspace_dev, int64_t n_sites, int64_t* count_out, void* stream);
+/* NSNP_PREC_F16X1 keeps two counters in the first bytes of the model workspace: the low-margin sites the LAST forward call
+ * found and their maximum over all calls since nsnp_model_f16x1_reset (call it once on a fresh workspace).
+ * nsnp_model_f16x1_reevaluated returns the former (synchronises the stream) and NSNP_E_OVERFLOW when ANY call since the reset
+ * found more than the 4096 that are re-evaluated. */
+int nsnp_model_f16x1_reset(void* workspace_dev, void* stream);
+int nsnp_model_f16x1_reevaluated(const void* workspace_dev, int64_t* count_out, void* stream);
 
 /* debug aid for the tensor-core path: raw gate pre-activations [m][256] (TMEM column order) of the FIRST step of one
  * (layer, direction); cg = 1 or 2 CTAs per MMA.  Used by the GPU tests to validate operand layouts. */

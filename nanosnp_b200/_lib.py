@@ -95,7 +95,8 @@ SYMBOLS = {
     "nsnp_pileup_model_forward_sites": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, _P, _P, _P, _SZ, C.c_int, _P]),
     "nsnp_site_records_sites": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P]),
     "nsnp_debug_lstm_tc_gates": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _I64, _P]),
-    "nsnp_model_f16x1_reevaluated": (C.c_int, [_P, _I64, _P, _P]),
+    "nsnp_model_f16x1_reset": (C.c_int, [_P, _P]),
+    "nsnp_model_f16x1_reevaluated": (C.c_int, [_P, _P, _P]),
     "nsnp_hap_features": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P]),
     "nsnp_hap_model_blob_bytes": (_SZ, []),
     "nsnp_hap_model_pack_weights": (C.c_int, [C.POINTER(HapWeights), _P, _SZ]),

@@ -279,10 +279,11 @@ __global__ void x1_gather_kernel(const int32_t* __restrict__ cnt, const int32_t*
     const int32_t* from = x ? x : reinterpret_cast<const int32_t*>(xf);          // 4-byte words either way
     for (int j = threadIdx.x; j < kT * kF; j += blockDim.x) x_low[(int64_t)k * kT * kF + j] = from[src * kT * kF + j];
 }
-__global__ void x1_scatter_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ idx, const float* __restrict__ gt_low,
+__global__ void x1_scatter_kernel(int32_t* __restrict__ cnt, const int32_t* __restrict__ idx, const float* __restrict__ gt_low,
                                   const float* __restrict__ zy_low, float* __restrict__ gt, float* __restrict__ zy)
 {
     const int k = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(cnt + 1, *cnt);            // sticky maximum: an overflow stays visible
     if (k >= min(*cnt, kX1Cap)) return;
     const int64_t dst = idx[k];
     if (lane < 21) gt[dst * 21 + lane] = gt_low[(int64_t)k * 21 + lane];
@@ -349,15 +350,16 @@ size_t nsnp_model_workspace_bytes(int64_t n_sites) {
     // layer-0 output of one chunk + the t = 16 state of ALL sites (the tail runs once per call, not once per chunk)
     const int64_t np = ((n_sites < 1 ? 1 : n_sites) + 127) / 128 * 128;
     // + the re-evaluation batch of NSNP_PREC_F16X1 (index list, outputs, gathered windows for the window-tensor entry point)
-    return (size_t)ch * kT * 128 * sizeof(float) + (size_t)np * 128 * sizeof(float) + 256 + kX1FixedBytes + kX1WindowBytes;
+    // 256-byte header first (NSNP_PREC_F16X1 counters: [0] low-margin sites of the last call, [1] their maximum since the reset)
+    return 256 + (size_t)ch * kT * 128 * sizeof(float) + (size_t)np * 128 * sizeof(float) + 256 + kX1FixedBytes + kX1WindowBytes;
 }
 
 static X1Work x1_carve(void* workspace_dev, int64_t n) {
     const int64_t ch0 = n < kChunkSites ? n : kChunkSites;
     const int64_t ch = ((ch0 < 1 ? 1 : ch0) + 127) / 128 * 128, np = ((n < 1 ? 1 : n) + 127) / 128 * 128;
-    char* p = (char*)workspace_dev + ((size_t)ch * kT * 128 + (size_t)np * 128) * sizeof(float) + 256;
+    char* p = (char*)workspace_dev + 256 + ((size_t)ch * kT * 128 + (size_t)np * 128) * sizeof(float) + 256;
     X1Work w;
-    w.cnt = (int32_t*)p; p += 256;
+    w.cnt = (int32_t*)workspace_dev;
     w.idx = (int32_t*)p; p += (size_t)kX1Cap * 4;
     w.pos_low = (int32_t*)p; p += (size_t)kX1Cap * 4;
     w.gt_low = (float*)p; p += (size_t)kX1Cap * 21 * 4;
@@ -366,14 +368,19 @@ static X1Work x1_carve(void* workspace_dev, int64_t n) {
     return w;
 }
 
-int nsnp_model_f16x1_reevaluated(const void* workspace_dev, int64_t n_sites, int64_t* count_out, void* stream_) {
+int nsnp_model_f16x1_reset(void* workspace_dev, void* stream_) {
+    if (!workspace_dev) return set_error(NSNP_E_INVALID, "nsnp_model_f16x1_reset: null argument");
+    if (cudaMemsetAsync(workspace_dev, 0, 256, (cudaStream_t)stream_) != cudaSuccess) return cuda_status("nsnp_model_f16x1_reset");
+    return NSNP_OK;
+}
+
+int nsnp_model_f16x1_reevaluated(const void* workspace_dev, int64_t* count_out, void* stream_) {
     if (!workspace_dev || !count_out) return set_error(NSNP_E_INVALID, "nsnp_model_f16x1_reevaluated: null argument");
-    const X1Work w = x1_carve(const_cast<void*>(workspace_dev), n_sites);
-    int32_t c = 0;
-    if (cudaMemcpyAsync(&c, w.cnt, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream_) != cudaSuccess || cudaStreamSynchronize((cudaStream_t)stream_) != cudaSuccess)
+    int32_t c[2] = {0, 0};
+    if (cudaMemcpyAsync(c, workspace_dev, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream_) != cudaSuccess || cudaStreamSynchronize((cudaStream_t)stream_) != cudaSuccess)
         return cuda_status("nsnp_model_f16x1_reevaluated");
-    *count_out = c;
-    if (c > kX1Cap) return set_error(NSNP_E_OVERFLOW, "NSNP_PREC_F16X1: %d low-margin sites in one call, only %d were re-evaluated; use NSNP_PREC_F16X3 for this input", c, kX1Cap);
+    *count_out = c[0];
+    if (c[1] > kX1Cap) return set_error(NSNP_E_OVERFLOW, "NSNP_PREC_F16X1: a call found %d low-margin sites, only %d were re-evaluated; use NSNP_PREC_F16X3 for this input", c[1], kX1Cap);
     return NSNP_OK;
 }
 
@@ -423,7 +430,7 @@ static int model_forward(const void* blob_dev, const int32_t* x_i32_dev, const f
             return cuda_status("cudaFuncSetAttribute(lstm_dir_kernel)");
         attr_done = true;
     }
-    float* h0 = (float*)workspace_dev;
+    float* h0 = (float*)((char*)workspace_dev + 256);          // after the header
     const int64_t ch = n < kChunkSites ? n : kChunkSites;
     static const bool tail_tc_env = [] { const char* v = getenv("NSNP_TAIL_TC"); return !(v && v[0] == '0'); }();
     const bool tc = precision == NSNP_PREC_F16X3 || precision == NSNP_PREC_F16X1;

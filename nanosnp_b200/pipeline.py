@@ -205,9 +205,7 @@ class PileupModelForward:
         if zy is None:
             zy = torch.empty((n, _lib.ZY_CLASSES), dtype=torch.float32, device=self.device)
         self._last_n = n
-        need = self.lib.nsnp_model_workspace_bytes(n)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._workspace(n)
         if x.dtype == torch.int32:
             xi, xf = x.data_ptr(), 0
         elif x.dtype == torch.float32:
@@ -227,8 +225,19 @@ class PileupModelForward:
             return 0
         c = C.c_int64(0)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.nsnp_model_f16x1_reevaluated(self._ws.data_ptr(), self._last_n, C.byref(c), _stream(self.device)))
+            _lib.check(self.lib.nsnp_model_f16x1_reevaluated(self._ws.data_ptr(), C.byref(c), _stream(self.device)))
         return int(c.value)
+
+    def _workspace(self, n: int) -> torch.Tensor:
+        need = self.lib.nsnp_model_workspace_bytes(n)
+        if self._ws is None or self._ws.numel() < need:
+            if self._ws is not None:
+                self.reevaluated()                    # an overflow recorded in the old workspace must not get lost
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            if self.precision == _lib.PREC_F16X1:
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.nsnp_model_f16x1_reset(self._ws.data_ptr(), _stream(self.device)))
+        return self._ws
 
     def from_counts(self, counts: torch.Tensor, region_start: int, pos: torch.Tensor, n: int, gt=None, zy=None):
         """The same forward pass with every site's window read straight from the region's count tensor [L,18] (a window is the
@@ -239,9 +248,7 @@ class PileupModelForward:
         if zy is None:
             zy = torch.empty((n, _lib.ZY_CLASSES), dtype=torch.float32, device=self.device)
         self._last_n = n
-        need = self.lib.nsnp_model_workspace_bytes(n)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._workspace(n)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.nsnp_pileup_model_forward_sites(self.w.blob.data_ptr(), counts.data_ptr(), region_start, int(counts.shape[0]),
                                                                 pos.data_ptr(), n, 0, gt.data_ptr(), zy.data_ptr(), self._ws.data_ptr(),

@@ -128,6 +128,7 @@ def predict(model: LSTMNetwork, testing_paths, reference_index_file, batch_size,
         for i in mine:
             recs.setdefault(i, torch.zeros((0, 32), dtype=torch.uint8, device=device))
         write_sharded_vcf(output_file, header, contigs, regions, recs, batch_size, device)
+        model._forward().reevaluated()                          # f16x1: raises if a region had more low-margin sites than are re-run
         return
 
     with open(output_file, "wb") as fwriter:
@@ -158,6 +159,7 @@ def predict(model: LSTMNetwork, testing_paths, reference_index_file, batch_size,
                 regions = plan_regions([(contig, len(fasta[contig]))], region_len)
                 call_contig_text(get_runner(), reads, fasta[contig], contig, fwriter, batch_size, region_len, regions,
                                  _region_reads(reads, reader, rid, regions))
+        model._forward().reevaluated()                          # f16x1: raises if a region had more low-margin sites than are re-run
 
 
 def main(argv=None):

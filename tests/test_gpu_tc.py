@@ -129,3 +129,23 @@ def test_single_pass_mode_small_batches(weights, small_case):
     assert torch.equal(g1[:17_000].argmax(1), g3[:17_000].argmax(1))
     g1, z1 = x1(x[:16_384].contiguous())
     assert torch.equal(g1, g3[:16_384]) and x1.reevaluated() == 0
+
+
+def test_single_pass_mode_reports_overflow(golden_weights, small_case):
+    """More low-margin sites than the library re-evaluates (zero weights: every head is uniform) must not pass silently: the
+    count check raises NSNP_E_OVERFLOW, and keeps raising after later clean calls on the same workspace."""
+    import torch
+    from nanosnp_b200 import _lib
+    from nanosnp_b200.pipeline import PileupModelForward, PileupModelWeights
+    enc, fwd = golden_weights
+    zero = PileupModelWeights({k: np.zeros_like(v) for k, v in enc.items()}, {k: np.zeros_like(v) for k, v in fwd.items()}, device="cuda:0")
+    x1 = PileupModelForward(zero, _lib.PREC_F16X1)
+    x = torch.from_numpy(small_case["windows"]).cuda().repeat(4, 1, 1)[:20_000].contiguous()
+    g, z = x1(x)
+    assert torch.allclose(g, torch.full_like(g, 1 / 21)) and torch.allclose(z, torch.full_like(z, 1 / 3))
+    with pytest.raises(_lib.NsnpError) as e:
+        x1.reevaluated()
+    assert e.value.code == _lib.E_OVERFLOW
+    x1(x[:100].contiguous())
+    with pytest.raises(_lib.NsnpError):
+        x1.reevaluated()

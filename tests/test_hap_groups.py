@@ -235,16 +235,17 @@ def test_bam_reader_keeps_qualities_hp_tags_and_name_hashes(gold, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,threads,maxcov", [(23, 3, 150), (47, 1, 30), (5, 4, 26)])
-def test_gpu_matrices_match_oracle_on_fresh_inputs(tmp_path, seed, threads, maxcov):
+@pytest.mark.parametrize("seed,threads,maxcov,adj,flank", [(23, 3, 150, 5, 16), (47, 1, 30, 5, 16), (5, 4, 26, 5, 16), (9, 2, 150, 3, 5), (13, 3, 40, 7, 32)])
+def test_gpu_matrices_match_oracle_on_fresh_inputs(tmp_path, seed, threads, maxcov, adj, flank):
     """Other seeds than the golden file's: the GPU path against the (golden-pinned) oracle restatement on the same input."""
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     import make_golden_hapgroups as M
     contigs, refs, reads, vcf = M.make_input(seed)
     vpath = tmp_path / "p.vcf"; vpath.write_text(M.vcf_text(vcf))
-    groups = hg.select_snp_multiprocess(str(vpath), 19, 5, 14, nthreads=threads)
+    groups = hg.select_snp_multiprocess(str(vpath), 19, adj, 14, nthreads=threads)
     assert groups
     n_checked = 0
+    c_h = adj
     for ctg, g in groups.items():
         recs = [tuple(r) for r in reads[ctg]]
         sam = pysam_emul.AlignmentFile(ctg, [pysam_emul.Segment(*r) for r in recs])
@@ -252,10 +253,10 @@ def test_gpu_matrices_match_oracle_on_fresh_inputs(tmp_path, seed, threads, maxc
         al = hg.upload_alignments(rd, aux)
         chunks = hg.plan_chunks(len(g), threads)
         subs = [(lo + a, lo + b) for lo, hi in chunks for a, b in hg.plan_subgroups(g[lo:hi])]
-        gm = hg.group_matrices(al, g, subs, maxcov, 16)
+        gm = hg.group_matrices(al, g, subs, maxcov, flank)
         want = []
         for a, b in subs:
-            want += subgroup_matrices(sam, ctg, g[a:b], maxcov, 16)
+            want += subgroup_matrices(sam, ctg, g[a:b], maxcov, flank)
         assert [list(p) for p in gm.positions] == [w["positions"] for w in want]
         hap = [h.cpu().numpy() for h in gm.hap]; pile = [p.cpu().numpy() for p in gm.pile]
         for i, w in enumerate(want):
@@ -263,9 +264,9 @@ def test_gpu_matrices_match_oracle_on_fresh_inputs(tmp_path, seed, threads, maxc
             assert gm.depth[i] == d
             if d == 0:
                 continue
-            for got, exp, centre in (([m[i, :d] for m in hap], w["hap"], 5), ([m[i, :d] for m in pile], w["pile"], 16)):
+            for got, exp, centre in (([m[i, :d] for m in hap], w["hap"], c_h), ([m[i, :d] for m in pile], w["pile"], flank)):
                 for x, y in zip(canonical_rows(*got, centre), canonical_rows(*exp, centre)):
                     np.testing.assert_array_equal(x, y)
             assert (hap[0][i, d:] == -2).all() and (pile[3][i, d:] == -2).all()
             n_checked += 1
-    assert n_checked > 10
+    assert n_checked > 5

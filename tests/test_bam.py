@@ -184,3 +184,48 @@ def test_spec_built_aux_tags_hp_and_qualities(tmp_path):
     for i, q in enumerate(quals):
         so = int(rd.seq_off[i])
         assert bytes(ax.qual[so:so + len(q)]) == q
+
+
+def test_damaged_files_fail_cleanly(tmp_path):
+    """Truncated / corrupted BGZF and BAM input must come back as errors (ValueError with the library's message), never as
+    a crash or as silently shortened data: every prefix length of a small valid file, plus flipped bytes in the payload."""
+    import struct
+    from nanosnp_b200.bam import BamReader
+    hdr_text = b"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:cA\tLN:1000\n"
+    raw = b"BAM\x01" + struct.pack("<i", len(hdr_text)) + hdr_text + struct.pack("<i", 1) + struct.pack("<i", 3) + b"cA\0" + struct.pack("<i", 1000)
+    recs = b"".join(_bam_record(0, 10 + 7 * k, 60, 0, [(4, "M"), (1, "I"), (5, "M")], "ACGTACGTAC", name=b"r%d\0" % k) for k in range(40))
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    cut = len(raw) + 500
+    good = _bgzf_block((raw + recs)[:cut]) + _bgzf_block((raw + recs)[cut:]) + eof
+    path = tmp_path / "ok.bam"
+    path.write_bytes(good)
+    with BamReader(str(path)) as r:
+        (_, _, rd), = list(r.contigs())
+    assert rd.n_reads == 40
+
+    def outcome(data: bytes):
+        p = tmp_path / "bad.bam"
+        p.write_bytes(data)
+        try:
+            with BamReader(str(p)) as r:
+                got = list(r.contigs())
+            return sum(x[2].n_reads for x in got)
+        except ValueError as e:
+            assert str(e)                                   # the library's message, not an empty error
+            return "error"
+    results = {}
+    for n in list(range(0, 120, 7)) + list(range(120, len(good) - len(eof), 37)) + [len(good) - len(eof) - 1]:
+        results[n] = outcome(good[:n])
+    assert all(v == "error" or (isinstance(v, int) and v <= 40) for v in results.values())
+    assert results[0] == "error" and results[63] == "error"
+    # a complete first block but a torn second one: the records of the first block may be returned only together with an error
+    torn = outcome(good[: len(good) - len(eof) - 30])
+    assert torn == "error"
+    # corrupted deflate payload / wrong magic
+    bad = bytearray(good); bad[40] ^= 0xFF; bad[41] ^= 0x55
+    assert outcome(bytes(bad)) == "error"
+    bad = bytearray(good); bad[0] = 0
+    assert outcome(bytes(bad)) == "error"
+    # a record whose block_size runs past the end of the stream
+    lying = raw + struct.pack("<i", 10_000) + recs[4:]
+    assert outcome(_bgzf_block(lying) + eof) == "error"

@@ -719,29 +719,220 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
     if (threadIdx.x < 32) tmem_dealloc<2>(*tmem_slot, 512);
 }
 
-int launch_l0_pair2(const void* blob, const int32_t* xi, const float* xf, void* h0_out, int64_t m, const int32_t* pos, int64_t pos_bias, int npass, cudaStream_t stream) {
-    using S = P2Smem;
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (cudaFuncSetAttribute(lstm0_pair2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total) != cudaSuccess)
-            return cuda_status("cudaFuncSetAttribute(lstm0_pair2_kernel)");
-        attr_done = true;
+// ------------------------------------------------------------------------------------------------------------------
+// Layer 1, single-pass (NSNP_PREC_F16X1) variant with the same two-groups-per-CTA alternation.  With one fp16 pass only the
+// hi halves of W and of the operands are needed: this CTA's half of W (48 KB) + two 128-site operand buffers (48 KB each) fit
+// one SM, and layer 1 stops being a serial "12 MMAs, then the cell update" chain per SM (lstm_tc_kernel<1> with one pass:
+// 2,300 + 4,150 cycles per step, MUFU pipe 55 % busy): one group's MMAs run under the other group's cell update.
+// The input rows of a step (layer-0 output, already in operand layout: 32 KB per tile and position) arrive by one bulk copy
+// per group and CTA, issued as soon as the MMAs that read the previous rows have completed; the warp that issued it waits for
+// the copy before it reports the group ready.  Same MMA order and cell arithmetic as lstm_tc_kernel<1> with npass = 1:
+// bit-identical output.
+struct P2Smem1 {
+    static constexpr size_t b_bytes = (size_t)kTcK1 * 128 * 2;                  // this CTA's half of W (hi)
+    static constexpr size_t a_bytes = (size_t)kTcK1 * kRows * 2;               // one group's operand (hi): 128 input + 64 hidden columns
+    static constexpr size_t off_b = 0, off_a = b_bytes, off_bias = off_a + 2 * a_bytes, off_bar = off_bias + 256 * sizeof(float), total = off_bar + 128;
+};
+
+__global__ void __launch_bounds__(kP2Threads, 1)
+lstm1_pair2_kernel(const unsigned char* __restrict__ blob, const __half* __restrict__ h0_in, float* __restrict__ h16, int64_t n)
+{
+    using S = P2Smem1;
+    constexpr int K = kTcK1, IN = kTcIn1, KB = K / 16, XB = IN / 16, RB = 128, UB = 4, kS = TcCfg<1>::STEPS;
+    constexpr uint32_t LBO_A = kRows * 16, LBO_B = RB * 16, SBO = 128;
+    constexpr uint32_t kPartBytes = 16u * kRows * 16u;              // 32 KB: the hi half of one (tile, position) of the layer-0 output
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int grp = (int)threadIdx.x / kP2GroupThreads;
+    const int tid = (int)threadIdx.x - grp * kP2GroupThreads, lane = tid & 31, warp = tid >> 5;
+    unsigned char* sB = smem + S::off_b;
+    unsigned char* sA = smem + S::off_a + grp * S::a_bytes;
+    float* sBias = reinterpret_cast<float*>(smem + S::off_bias);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_bar);
+    uint64_t* barH = bars + grp;               // [0,1]  gates of this group complete (commit, multicast to both CTAs)
+    uint64_t* barReady = bars + 2 + grp;       // [2,3]  leader CTA: all 16 warps of this group (both CTAs) are ready for the next step
+    uint64_t* barTurn = bars + 4;              // [4,5]  leader CTA: token, barTurn[g] = "group g may issue"
+    uint64_t* barIn = bars + 6 + grp;          // [6,7]  this CTA: the input rows of this group's next step have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_bar + 64);
+
+    const int quad = warp & 3, sub = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t cta_rank = cluster_ctarank();
+    const int cluster_id = (int)(blockIdx.x >> 1);
+    const int dir = cluster_id & 1;
+    const int quad_stride = (int)(gridDim.x >> 2);
+    const int n_quads = (int)((n + 4 * kRows - 1) / (4 * kRows));
+    const int64_t last_tile = (n + kRows - 1) / kRows - 1;
+    const int q0 = cluster_id >> 1;
+    const int my_quads = q0 < n_quads ? (n_quads - q0 + quad_stride - 1) / quad_stride : 0;
+    const int total_g = my_quads * kS;                          // this group's stream of (quad, step) pairs
+    auto tile_of = [&](int qi) -> int64_t { return (int64_t)(q0 + qi * quad_stride) * 4 + (int64_t)cta_rank * 2 + grp; };
+
+    if (threadIdx.x == 0) {
+        mbar_init(bars + 0, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 16); mbar_init(bars + 3, 16);
+        mbar_init(bars + 4, 1); mbar_init(bars + 5, 1); mbar_init(bars + 6, 1); mbar_init(bars + 7, 1);
+        fence_mbar_init();
     }
+    if (threadIdx.x < 32) tmem_alloc<2>(tmem_slot, 512);
+    {
+        const uint4* ghi = reinterpret_cast<const uint4*>(blob + tc_off(1, dir, 0));
+        uint4* dhi = reinterpret_cast<uint4*>(sB);
+        for (int i = (int)threadIdx.x; i < (K / 8) * RB; i += kP2Threads) {
+            const int ch = i / RB, r = i - ch * RB;
+            dhi[i] = __ldg(ghi + ch * 256 + (int)cta_rank * RB + r);
+        }
+        const float* gb = reinterpret_cast<const float*>(blob + kOffTcBias1) + dir * 256;
+        for (int i = (int)threadIdx.x; i < 256; i += kP2Threads) sBias[i] = __ldg(gb + i);
+    }
+    __syncthreads();
+
+    float c[UB][8];
+#pragma unroll
+    for (int j = 0; j < UB; ++j)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[j][u] = 0.f;
+
+    // input rows of stream element gstep: h0[tile][t][hi][16 chunks][128 rows][8]; a padding tile re-reads the last real one
+    auto stage_in = [&](int gstep) {                            // one thread per group and CTA
+        const int qi = gstep / kS, st = gstep - qi * kS;
+        const int t = dir == 0 ? st : (kT - 1 - st);
+        const int64_t tile = min(tile_of(qi), last_tile);
+        mbar_expect_tx(barIn, kPartBytes);
+        bulk_g2s(sA, h0_in + ((size_t)tile * kT + t) * (size_t)kPartBytes, kPartBytes, barIn);     // kPartBytes halfs = hi + lo per (tile, t)
+    };
+    auto report_ready = [&]() {
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(barReady, 0);      // the leader maps to itself
+    };
+    uint32_t phaseIn = 0;
+    if (total_g > 0 && tid == 0) stage_in(0);
+    tc_fence_before();
+    cluster_sync_all();                                            // barriers initialised, TMEM allocated (both CTAs)
+    tc_fence_after();
+    if (total_g > 0) {
+        if (warp == 0) { mbar_wait(barIn, phaseIn); phaseIn ^= 1; }
+        report_ready();
+    }
+
+    const uint32_t tmem_base = *tmem_slot + (uint32_t)grp * 256u;
+    const uint32_t a_hi = smem_u32(sA), b_hi = smem_u32(sB);
+    constexpr uint32_t idesc = make_idesc(256, 256);
+    const bool issuer = cta_rank == 0 && tid == 0;
+    uint32_t phaseH = 0, phaseR = 0, phaseT = 0;
+    if (cta_rank == 0 && threadIdx.x == 0) mbar_arrive(barTurn + 0);          // group 0 issues first
+
+    int step = 0, qi = 0;
+    for (int g = 0; g < total_g; ++g) {
+        const bool more = g + 1 < total_g;
+        const int64_t site = tile_of(qi) * kRows + row;
+        const bool live = site < n;
+        if (step == 0) {                                            // a new tile: the recurrence starts from c = 0, h = 0
+#pragma unroll
+            for (int j = 0; j < UB; ++j)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) c[j][u] = 0.f;
+        }
+        if (issuer) {
+            mbar_wait_cluster(barReady, phaseR);                   // every warp of this group, in both CTAs, has reported
+            mbar_wait(barTurn + grp, phaseT);                      // and it is this group's turn on the tensor pipe
+            tc_fence_after();
+#pragma unroll 1
+            for (int kb = 0; kb < (step == 0 ? XB : KB); ++kb)      // h = 0 at the first step of a tile: input k-blocks only
+                umma_f16<2>(tmem_base, make_desc(a_hi + kb * 2 * LBO_A, LBO_A, SBO), make_desc(b_hi + kb * 2 * LBO_B, LBO_B, SBO), idesc, kb ? 1u : 0u);
+            umma_commit<2>(barH);
+            mbar_arrive(barTurn + (grp ^ 1));                      // hand the token to the other group
+        }
+        phaseR ^= 1; phaseT ^= 1;
+        mbar_wait(barH, phaseH);
+        phaseH ^= 1;
+        tc_fence_after();
+        if (more && tid == 0) stage_in(g + 1);                      // the MMAs that read the input rows are complete: fetch the next ones
+
+        uint32_t vb[2][16];
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * UB) * 32u;
+        tmem_ld16_nowait(tacc, vb[0]);
+        tmem_wait_ld();
+        float hv[8];
+#pragma unroll
+        for (int hb = 0; hb < 2 * UB; ++hb) {
+            const int jl = hb >> 1, uh = hb & 1, jb = sub * UB + jl;
+            if (hb + 1 < 2 * UB) tmem_ld16_nowait(tacc + (hb + 1) * 16, vb[(hb + 1) & 1]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t* v = vb[hb & 1];
+                // same cell update as lstm_tc_kernel<1> (scales folded into the weights, scaled cell state, bias in the epilogue)
+                const float* bq = sBias + jb * 32 + uh * 16 + u;
+                const float xi_ = fminf(__uint_as_float(v[u]) + bq[0], 36.f), xf_ = fminf(__uint_as_float(v[4 + u]) + bq[4], 36.f);
+                const float xg_ = fminf(__uint_as_float(v[8 + u]) + bq[8], 36.f), xo_ = __uint_as_float(v[12 + u]) + bq[12];
+                const float ei = ex2_approx(xi_), ef = ex2_approx(xf_), eg = ex2_approx(xg_), eo = ex2_approx(xo_);
+                const float pi = 1.f + ei, pf = 1.f + ef, pg = 1.f + eg;
+                const float pig = pi * pg;
+                const float num = fmaf(c[jl][uh * 4 + u], pig, fmaf(eg, 2.f * kLog2e, -2.f * kLog2e) * pf);
+                const float cn = num * rcp_approx(pf * pig);
+                c[jl][uh * 4 + u] = cn;
+                const float ec = ex2_approx(cn);
+                hv[uh * 4 + u] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));
+            }
+            if (hb + 1 < 2 * UB) tmem_wait_ld();
+            if (uh == 1) {
+                const HiLo8 sp = split8(hv);
+                reinterpret_cast<uint4*>(sA + (IN / 8 + jb) * LBO_A)[row] = sp.hi;
+                if (live && step == kS - 1) {
+                    float4* o = reinterpret_cast<float4*>(h16 + site * 128 + dir * kH + jb * 8);
+                    o[0] = make_float4(hv[0], hv[1], hv[2], hv[3]); o[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                }
+            }
+        }
+        if (more) {
+            if (warp == 0) { mbar_wait(barIn, phaseIn); phaseIn ^= 1; }
+            report_ready();
+        }
+        if (++step == kS) { step = 0; ++qi; }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (threadIdx.x < 32) tmem_dealloc<2>(*tmem_slot, 512);
+}
+
+template <class Kern, class... Args>
+int launch_pair2(Kern kern, const char* name, size_t smem_bytes, int64_t m, cudaStream_t stream, Args... args) {
     // persistent: at most one CTA per SM; clusters alternate between the two directions, so an even number of clusters
     const unsigned quads = (unsigned)((m + 4 * kRows - 1) / (4 * kRows));
     unsigned clusters = 2 * quads; if (clusters > (unsigned)kNumSMs / 2) clusters = ((unsigned)kNumSMs / 2) & ~1u;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters, 1, 1);
     cfg.blockDim = dim3(kP2Threads, 1, 1);
-    cfg.dynamicSmemBytes = S::total;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, lstm0_pair2_kernel, (const unsigned char*)blob, xi, xf, (__half*)h0_out, m, pos, pos_bias, npass);
-    if (e != cudaSuccess) return set_error(NSNP_E_CUDA, "lstm0_pair2_kernel: %s", cudaGetErrorString(e));
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+    if (e != cudaSuccess) return set_error(NSNP_E_CUDA, "%s: %s", name, cudaGetErrorString(e));
     return NSNP_OK;
+}
+
+int launch_l0_pair2(const void* blob, const int32_t* xi, const float* xf, void* h0_out, int64_t m, const int32_t* pos, int64_t pos_bias, int npass, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(lstm0_pair2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2Smem::total) != cudaSuccess)
+            return cuda_status("cudaFuncSetAttribute(lstm0_pair2_kernel)");
+        attr_done = true;
+    }
+    return launch_pair2(lstm0_pair2_kernel, "lstm0_pair2_kernel", P2Smem::total, m, stream, (const unsigned char*)blob, xi, xf, (__half*)h0_out, m, pos, pos_bias, npass);
+}
+
+int launch_l1_pair2(const void* blob, const void* h0_in, float* h16, int64_t m, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(lstm1_pair2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2Smem1::total) != cudaSuccess)
+            return cuda_status("cudaFuncSetAttribute(lstm1_pair2_kernel)");
+        attr_done = true;
+    }
+    return launch_pair2(lstm1_pair2_kernel, "lstm1_pair2_kernel", P2Smem1::total, m, stream, (const unsigned char*)blob, (const __half*)h0_in, h16, m);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1001,6 +1192,9 @@ int launch_lstm_tc(const void* blob, const int32_t* xi, const float* xf, void* h
     // layer 1: W only fits split across a CTA pair (2 x 104 KB); one CTA per SM, 16 warps for the epilogue
     ProfScope prof(NSNP_PROF_LSTM1, stream);
     static const int pf = [] { const char* v = getenv("NSNP_L1_PREFETCH"); return v ? atoi(v) : 1; }();
+    // single pass: two alternating groups per CTA (lstm1_pair2_kernel); NSNP_L1_VARIANT=0 keeps the one-group kernel (A/B, tests)
+    static const int l1_variant = [] { const char* v = getenv("NSNP_L1_VARIANT"); return v ? atoi(v) : 1; }();
+    if (npass == 1 && l1_variant == 1) return launch_l1_pair2(blob, h0, h16, m, stream);
     return launch_one<1, 2, 4, false>(blob, nullptr, nullptr, h0, nullptr, h16, nullptr, m, (pf << 8) | (npass << 16), stream);
 }
 

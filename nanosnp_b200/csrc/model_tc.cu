@@ -702,11 +702,11 @@ lstm0_pair2_kernel(const unsigned char* __restrict__ blob, const int32_t* __rest
             if (uh == 1) {
                 const HiLo8 sp = split8(hv);
                 reinterpret_cast<uint4*>(sAhi + (IN / 8 + jb) * LBO_A)[row] = sp.hi;
-                reinterpret_cast<uint4*>(sAlo + (IN / 8 + jb) * LBO_A)[row] = sp.lo;
+                if (npass == 3) reinterpret_cast<uint4*>(sAlo + (IN / 8 + jb) * LBO_A)[row] = sp.lo;
                 if (live) {
                     __half* o = h0_out + ((((size_t)tile_idx * kT + t) * 2) * 16 + (dir * 8 + jb)) * (kRows * 8) + row * 8;
                     *reinterpret_cast<uint4*>(o) = sp.hi;
-                    *reinterpret_cast<uint4*>(o + 16 * kRows * 8) = sp.lo;
+                    if (npass == 3) *reinterpret_cast<uint4*>(o + 16 * kRows * 8) = sp.lo;     // single pass: layer 1 reads the hi halves only
                 }
             }
         }
